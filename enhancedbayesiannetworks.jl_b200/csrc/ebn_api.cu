@@ -1,0 +1,885 @@
+// C ABI of libebncuda.so (see include/ebncuda.h). Host side only: argument
+// validation, canonicalisation of marginals into device sampling plans, device
+// buffers, launches, the NCCL all-reduce of the count vectors, result copy.
+//
+// The reference call sites this file stands behind:
+//   ebn_pf_batch    <- probability_of_failure(...) per scenario,
+//                      src/networks/ebn/evaluation/evaluate_node.jl:79-95
+//   ebn_hist_batch  <- UQ.sample / UQ.evaluate! / EmpiricalDistribution,
+//                      src/networks/ebn/evaluation/evaluate_node.jl:22-33
+//   ebn_eval_matrix <- `performance(df) .< 0` summed (UQ.jl, called from :83)
+#include <dlfcn.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "ebn_kernels.h"
+
+static_assert(sizeof(ebn_input_t) == 56, "ebn_input_t must be 56 bytes");
+static_assert(sizeof(ebn_stats_t) == 48, "ebn_stats_t must be 48 bytes");
+static_assert(offsetof(ebn_job_t, consts) == 8, "ebn_job_t layout");
+static_assert(offsetof(ebn_job_t, inputs) == 24, "ebn_job_t layout");
+static_assert(offsetof(ebn_job_t, n_per_scenario) == 32, "ebn_job_t layout");
+static_assert(offsetof(ebn_job_t, corr_chol) == 56, "ebn_job_t layout");
+static_assert(sizeof(ebn_job_t) == 104, "ebn_job_t must be 104 bytes");
+
+namespace {
+
+using namespace ebn;
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess)                                                            \
+      return fail(EBN_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),  \
+                  __FILE__, __LINE__);                                                 \
+  } while (0)
+
+// ---- NCCL through dlopen: no link-time dependency, and inside a process that
+// already loaded a libnccl.so.2 (torch) the same copy is reused. -------------
+typedef struct ncclComm* ncclComm_t;
+struct NcclId { char b[128]; };  // ncclUniqueId: 128 opaque bytes, passed by value
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclId, int) = nullptr;
+  int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+} g_nccl;
+constexpr int kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0;
+
+int nccl_load() {
+  if (g_nccl.handle) return EBN_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(EBN_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                       \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                                   \
+  if (!g_nccl.field) return fail(EBN_ENCCL, "NCCL symbol %s not found", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitAll, "ncclCommInitAll")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+  SYM(CommInitRank, "ncclCommInitRank")
+#undef SYM
+  g_nccl.handle = h;
+  return EBN_OK;
+}
+#define NC(call)                                                                  \
+  do {                                                                            \
+    int r__ = (call);                                                             \
+    if (r__ != 0)                                                                 \
+      return fail(EBN_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__)); \
+  } while (0)
+
+// ---- per-device state --------------------------------------------------------
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return EBN_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes < 4096 ? 4096 : bytes;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(EBN_ENOMEM, "cudaMalloc(%zu) failed", want);
+    }
+    cap = want;
+    return EBN_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Dev {
+  int id = 0;
+  int sms = 0;
+  cudaStream_t own = nullptr;
+  cudaStream_t st = nullptr;  // stream in use (own or caller's)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  Buf plan, consts, tables, chol, streams, counts, edges, partial, sums, mat, gout;
+  ncclComm_t comm = nullptr;  // single-process multi-device communicator
+};
+
+struct Ctx {
+  bool ready = false;
+  std::vector<Dev> devs;
+  ncclComm_t rank_comm = nullptr;  // one-process-per-GPU communicator
+  int rank = 0, world = 1;
+  ebn_stats_t stats{};
+} g;
+
+// ---- host-side distribution helpers (truncation windows -> probability) -----
+const double kInf = std::numeric_limits<double>::infinity();
+
+double norm_cdf(double z) { return 0.5 * erfc(-z * 0.70710678118654752440); }
+
+// Maps one ABI input to the device recipe. Returns EBN_OK or an error.
+int canonicalise(const ebn_input_t& in, bool copula, DevInput& o, int s, int j,
+                 int64_t n_tables) {
+  o = DevInput{};
+  const double lo = in.lo, hi = in.hi;
+  const bool trunc = (lo > -kInf) || (hi < kInf);
+  if (in.flags != 0) return fail(EBN_EINVAL, "input (%d,%d): flags must be 0", s, j);
+  if (std::isnan(lo) || std::isnan(hi) || !(lo < hi)) {
+    if (in.kind != EBN_IN_PARAM)
+      return fail(EBN_EMARGINAL, "input (%d,%d): truncation window [%g,%g] is empty", s, j, lo, hi);
+  }
+  double Flo = 0.0, Fhi = 1.0;
+  switch (in.kind) {
+    case EBN_IN_PARAM:
+      o.kind = DK_CONST;
+      o.a = in.p[0];
+      return EBN_OK;
+    case EBN_IN_UNIFORM: {
+      double a = in.p[0], b = in.p[1];
+      if (!(a < b)) return fail(EBN_EMARGINAL, "input (%d,%d): Uniform needs a < b", s, j);
+      if (lo > a) a = lo;
+      if (hi < b) b = hi;
+      if (!(a < b))
+        return fail(EBN_EMARGINAL, "input (%d,%d): truncation leaves no Uniform support", s, j);
+      o.kind = DK_UNIFORM;
+      o.a = a;
+      o.b = b - a;
+      o.c = 0.0;
+      o.d = 1.0;
+      return EBN_OK;
+    }
+    case EBN_IN_NORMAL:
+    case EBN_IN_LOGNORMAL: {
+      const double mu = in.p[0], sd = in.p[1];
+      if (!(sd > 0.0)) return fail(EBN_EMARGINAL, "input (%d,%d): sigma must be > 0", s, j);
+      const bool logn = in.kind == EBN_IN_LOGNORMAL;
+      o.a = mu;
+      o.b = sd;
+      if (!trunc) {
+        o.kind = logn ? DK_LOGNORMAL_BM : DK_NORMAL_BM;
+        o.c = 0.0;
+        o.d = 1.0;
+        return EBN_OK;
+      }
+      double zl = -kInf, zh = kInf;
+      if (logn) {
+        if (lo > 0.0) zl = (log(lo) - mu) / sd;
+        if (hi < kInf) { if (!(hi > 0.0)) return fail(EBN_EMARGINAL, "input (%d,%d): LogNormal window below 0", s, j); zh = (log(hi) - mu) / sd; }
+      } else {
+        if (lo > -kInf) zl = (lo - mu) / sd;
+        if (hi < kInf) zh = (hi - mu) / sd;
+      }
+      Flo = zl == -kInf ? 0.0 : norm_cdf(zl);
+      Fhi = zh == kInf ? 1.0 : norm_cdf(zh);
+      o.kind = logn ? DK_LOGNORMAL_ICDF : DK_NORMAL_ICDF;
+      break;
+    }
+    case EBN_IN_GUMBEL: {
+      const double mu = in.p[0], beta = in.p[1];
+      if (!(beta > 0.0)) return fail(EBN_EMARGINAL, "input (%d,%d): beta must be > 0", s, j);
+      o.kind = DK_GUMBEL;
+      o.a = mu;
+      o.b = beta;
+      if (lo > -kInf) Flo = exp(-exp(-(lo - mu) / beta));
+      if (hi < kInf) Fhi = exp(-exp(-(hi - mu) / beta));
+      break;
+    }
+    case EBN_IN_EXPONENTIAL_AFFINE: {
+      const double theta = in.p[0], sign = in.p[1], shift = in.p[2];
+      if (!(theta > 0.0) || !(sign == 1.0 || sign == -1.0))
+        return fail(EBN_EMARGINAL, "input (%d,%d): Exponential needs theta > 0, sign +-1", s, j);
+      o.kind = DK_EXP_AFFINE;
+      o.a = shift;
+      o.b = sign * theta;
+      // window in the exponential's own variable e = (x - shift)/sign >= 0
+      double el = 0.0, eh = kInf;
+      if (sign > 0) { if (lo > shift) el = lo - shift; if (hi < kInf) eh = hi - shift; }
+      else { if (hi < shift) el = shift - hi; if (lo > -kInf) eh = shift - lo; }
+      if (!(eh > el)) return fail(EBN_EMARGINAL, "input (%d,%d): window outside the support", s, j);
+      Flo = -expm1(-el / theta);
+      Fhi = eh == kInf ? 1.0 : -expm1(-eh / theta);
+      break;
+    }
+    case EBN_IN_GAMMA: {
+      if (!(in.p[0] > 0.0) || !(in.p[1] > 0.0))
+        return fail(EBN_EMARGINAL, "input (%d,%d): Gamma needs shape, scale > 0", s, j);
+      if (trunc || copula)
+        return fail(EBN_EMARGINAL,
+                    "input (%d,%d): truncated / copula Gamma must be passed as EBN_IN_TABULATED", s, j);
+      o.kind = DK_GAMMA_MT;
+      o.a = in.p[0];
+      o.b = in.p[1];
+      o.c = 0.0;
+      o.d = 1.0;
+      return EBN_OK;
+    }
+    case EBN_IN_TABULATED: {
+      const double off = in.p[0], npts = in.p[1];
+      if (!(npts >= 2.0) || off < 0.0 || off + npts > (double)n_tables)
+        return fail(EBN_EINVAL, "input (%d,%d): table [%g,+%g) outside the pool of %lld", s, j, off,
+                    npts, (long long)n_tables);
+      if (trunc)
+        return fail(EBN_EMARGINAL, "input (%d,%d): truncate a tabulated marginal in the table", s, j);
+      o.kind = DK_TABLE;
+      o.off = (int64_t)off;
+      o.npts = (int32_t)npts;
+      o.c = 0.0;
+      o.d = 1.0;
+      return EBN_OK;
+    }
+    default:
+      return fail(EBN_EMARGINAL, "input (%d,%d): unknown marginal kind %d", s, j, in.kind);
+  }
+  if (!(Fhi > Flo))
+    return fail(EBN_EMARGINAL, "input (%d,%d): truncation window has zero probability", s, j);
+  o.c = Flo;
+  o.d = Fhi - Flo;
+  return EBN_OK;
+}
+
+struct LsInfo { int id; const char* name; int d; int nc; };
+const LsInfo kLs[] = {
+    {EBN_LS_VEHICLE_SUSPENSION, "vehicle_suspension", 6, 5},
+    {EBN_LS_STRAUB_FRAME, "straub_frame", 8, 3},
+    {EBN_LS_HYDROGEN_RADIUS, "hydrogen_radius", 4, 0},
+    {EBN_LS_POLYNOMIAL, "polynomial", -1, -1},
+    {EBN_LS_MIN_AFFINE, "min_affine", -1, -1},
+};
+const LsInfo* ls_info(int id) {
+  for (const auto& l : kLs)
+    if (l.id == id) return &l;
+  return nullptr;
+}
+
+// Validates limit state, arity and the consts program.
+int check_limit_state(int id, const double* consts, int n_consts, int d) {
+  const LsInfo* li = ls_info(id);
+  if (!li) return fail(EBN_ELIMITSTATE, "unknown limit state id %d (no CPU fallback exists)", id);
+  if (d < 1 || d > EBN_MAX_INPUTS)
+    return fail(EBN_EINVAL, "n_inputs %d outside [1,%d]", d, EBN_MAX_INPUTS);
+  if (n_consts < 0 || (n_consts > 0 && !consts)) return fail(EBN_EINVAL, "consts is NULL");
+  if (li->d >= 0 && li->d != d)
+    return fail(EBN_ELIMITSTATE, "limit state %s takes %d inputs, got %d", li->name, li->d, d);
+  if (li->nc >= 0 && li->nc != n_consts)
+    return fail(EBN_ELIMITSTATE, "limit state %s takes %d consts, got %d", li->name, li->nc, n_consts);
+  if (id == EBN_LS_POLYNOMIAL) {
+    if (n_consts < 1) return fail(EBN_ELIMITSTATE, "polynomial program is empty");
+    const int T = (int)consts[0];
+    if (T < 1 || d + T > EBN_MAX_INPUTS + 1)
+      return fail(EBN_ELIMITSTATE, "polynomial program: %d stages on %d inputs exceed %d columns", T, d,
+                  EBN_MAX_INPUTS);
+    int pos = 1;
+    for (int t = 0; t < T; ++t) {
+      if (pos >= n_consts) return fail(EBN_ELIMITSTATE, "polynomial program truncated (stage %d)", t);
+      const int nt = (int)consts[pos++];
+      if (nt < 1) return fail(EBN_ELIMITSTATE, "polynomial stage %d has no terms", t);
+      for (int k = 0; k < nt; ++k) {
+        pos++;  // coefficient
+        if (pos >= n_consts)
+          return fail(EBN_ELIMITSTATE, "polynomial program truncated (stage %d term %d)", t, k);
+        const int nf = (int)consts[pos++];
+        if (nf < 0 || pos + nf > n_consts)
+          return fail(EBN_ELIMITSTATE, "polynomial program truncated (stage %d term %d)", t, k);
+        for (int f = 0; f < nf; ++f) {
+          const int col = (int)consts[pos++];
+          if (col < 0 || col >= d + t)
+            return fail(EBN_ELIMITSTATE, "polynomial stage %d reads column %d (only %d exist)", t, col,
+                        d + t);
+        }
+      }
+    }
+    if (pos != n_consts)
+      return fail(EBN_ELIMITSTATE, "polynomial program has %d trailing consts", n_consts - pos);
+  } else if (id == EBN_LS_MIN_AFFINE) {
+    if (n_consts < 1) return fail(EBN_ELIMITSTATE, "min_affine needs consts");
+    const int K = (int)consts[0];
+    if (K < 1 || n_consts != 1 + K * (1 + d))
+      return fail(EBN_ELIMITSTATE, "min_affine: expected %d consts for K=%d, d=%d, got %d",
+                  1 + K * (1 + d), K, d, n_consts);
+  }
+  return EBN_OK;
+}
+
+int require_ready() {
+  if (!g.ready) return fail(EBN_ENODEV, "ebn_init has not been called (or found no CUDA device)");
+  return EBN_OK;
+}
+
+// A fully prepared batch: validated job + canonical plan + partition.
+struct Prepared {
+  std::vector<DevInput> plan;
+  int plan_class = PLAN_DYNAMIC;
+  int64_t first = 0, last = 0, pair_base = 0, pairs_per_item = 0, items_per_scenario = 0;
+  int world = 1;  // job world * devices
+};
+
+int prepare(const ebn_job_t* job, int mode, Prepared& P) {
+  if (!job) return fail(EBN_EINVAL, "job is NULL");
+  if (job->n_scenarios < 1) return fail(EBN_EINVAL, "n_scenarios must be >= 1");
+  if (!job->inputs) return fail(EBN_EINVAL, "inputs is NULL");
+  if (job->n_per_scenario < 1) return fail(EBN_EINVAL, "n_per_scenario must be >= 1");
+  if (job->sample_offset < 0) return fail(EBN_EINVAL, "sample_offset must be >= 0");
+  if (job->flags & ~(EBN_JOB_COPULA_SHARED | EBN_JOB_PARTIAL)) return fail(EBN_EINVAL, "unknown job flags 0x%x", job->flags);
+  int rc = check_limit_state(job->limit_state, job->consts, job->n_consts, job->n_inputs);
+  if (rc) return rc;
+  const int jw = job->shard_world <= 1 ? 1 : job->shard_world;
+  const int jr = job->shard_world <= 1 ? 0 : job->shard_rank;
+  if (jr < 0 || jr >= jw) return fail(EBN_EINVAL, "shard_rank %d outside [0,%d)", jr, jw);
+  if (job->n_tables < 0 || (job->n_tables > 0 && !job->tables)) return fail(EBN_EINVAL, "tables is NULL");
+  const int S = job->n_scenarios, d = job->n_inputs;
+  const bool copula = job->corr_chol != nullptr;
+  P.plan.resize((size_t)S * d);
+  for (int s = 0; s < S; ++s)
+    for (int j = 0; j < d; ++j) {
+      rc = canonicalise(job->inputs[(size_t)s * d + j], copula, P.plan[(size_t)s * d + j], s, j,
+                        job->n_tables);
+      if (rc) return rc;
+    }
+  if (copula) {
+    const int nblk = (job->flags & EBN_JOB_COPULA_SHARED) ? 1 : S;
+    for (int b = 0; b < nblk; ++b) {
+      const double* L = job->corr_chol + (size_t)b * d * d;
+      for (int r = 0; r < d; ++r) {
+        double ss = 0.0;
+        for (int c = 0; c < d; ++c) {
+          if (c > r && L[r * d + c] != 0.0)
+            return fail(EBN_EINVAL, "corr_chol block %d is not lower triangular", b);
+          ss += L[r * d + c] * L[r * d + c];
+        }
+        if (fabs(ss - 1.0) > 1e-9)
+          return fail(EBN_EINVAL, "corr_chol block %d row %d: L*L' has diagonal %g, expected 1", b, r, ss);
+      }
+    }
+    P.plan_class = PLAN_COPULA;
+  } else if (static_plan_matches(job->limit_state, P.plan.data(), S, d)) {
+    P.plan_class = PLAN_STATIC;
+  }
+  P.world = jw * (int)g.devs.size();
+  P.first = job->sample_offset;
+  P.last = job->sample_offset + job->n_per_scenario;
+  P.pair_base = P.first >> 1;
+  const int64_t pairs = ((P.last + 1) >> 1) - P.pair_base;
+  // Partition depends on the job only (never on the device), so every rank
+  // derives the same item grid.
+  const int T = threads_per_block();
+  const double target_items = 9472.0 * P.world;  // 148 SMs * 4 * 16
+  int64_t ppi = (int64_t)ceil((double)pairs * S / target_items);
+  ppi = ((ppi + T - 1) / T) * T;
+  const int64_t max_ppi = mode == 0 ? (1 << 15) : (1 << 22);
+  if (ppi < T) ppi = T;
+  if (ppi > max_ppi) ppi = max_ppi;
+  P.pairs_per_item = ppi;
+  P.items_per_scenario = (pairs + ppi - 1) / ppi;
+  return EBN_OK;
+}
+
+int64_t local_items_of(const Prepared& P, int S, int rank) {
+  const int64_t total = P.items_per_scenario * S;
+  return total > rank ? (total - rank + P.world - 1) / P.world : 0;
+}
+
+// Uploads the job to one device and fills the kernel parameters.
+int stage(Dev& dv, const ebn_job_t* job, const Prepared& P, int rank, McParams& mp, double& h2d) {
+  const int S = job->n_scenarios, d = job->n_inputs;
+  CU(cudaSetDevice(dv.id));
+  int rc;
+  const size_t plan_b = P.plan.size() * sizeof(DevInput);
+  if ((rc = dv.plan.ensure(plan_b))) return rc;
+  CU(cudaMemcpyAsync(dv.plan.p, P.plan.data(), plan_b, cudaMemcpyHostToDevice, dv.st));
+  h2d += plan_b;
+  const size_t consts_b = (size_t)job->n_consts * sizeof(double);
+  if ((rc = dv.consts.ensure(consts_b))) return rc;
+  if (consts_b) {
+    CU(cudaMemcpyAsync(dv.consts.p, job->consts, consts_b, cudaMemcpyHostToDevice, dv.st));
+    h2d += consts_b;
+  }
+  mp = McParams{};
+  mp.plan = (const DevInput*)dv.plan.p;
+  mp.consts = (const double*)dv.consts.p;
+  if (job->n_tables > 0) {
+    const size_t b = (size_t)job->n_tables * sizeof(double);
+    if ((rc = dv.tables.ensure(b))) return rc;
+    CU(cudaMemcpyAsync(dv.tables.p, job->tables, b, cudaMemcpyHostToDevice, dv.st));
+    h2d += b;
+    mp.tables = (const double*)dv.tables.p;
+  }
+  if (job->corr_chol) {
+    const size_t b = (size_t)((job->flags & EBN_JOB_COPULA_SHARED) ? 1 : S) * d * d * sizeof(double);
+    if ((rc = dv.chol.ensure(b))) return rc;
+    CU(cudaMemcpyAsync(dv.chol.p, job->corr_chol, b, cudaMemcpyHostToDevice, dv.st));
+    h2d += b;
+    mp.chol = (const double*)dv.chol.p;
+    mp.chol_shared = (job->flags & EBN_JOB_COPULA_SHARED) ? 1 : 0;
+  }
+  if (job->stream_id) {
+    const size_t b = (size_t)S * sizeof(uint32_t);
+    if ((rc = dv.streams.ensure(b))) return rc;
+    CU(cudaMemcpyAsync(dv.streams.p, job->stream_id, b, cudaMemcpyHostToDevice, dv.st));
+    h2d += b;
+    mp.stream_id = (const uint32_t*)dv.streams.p;
+  }
+  mp.first = P.first;
+  mp.last = P.last;
+  mp.pairs_per_item = P.pairs_per_item;
+  mp.items_per_scenario = P.items_per_scenario;
+  mp.pair_base = P.pair_base;
+  mp.shard_rank = rank;
+  mp.shard_world = P.world;
+  mp.local_items = local_items_of(P, S, rank);
+  mp.S = S;
+  mp.d = d;
+  mp.n_consts = job->n_consts;
+  mp.k0 = (uint32_t)(job->seed & 0xffffffffu);
+  mp.k1 = (uint32_t)(job->seed >> 32);
+  return EBN_OK;
+}
+
+int grid_for(Dev& dv, const ebn_job_t* job, const Prepared& P, int mode, size_t dyn,
+             int64_t local_items, int* blocks) {
+  int per_sm = 0;
+  CU(ls_vtable(job->limit_state)->occupancy(job->strict ? 1 : 0, P.plan_class, mode, dyn, &per_sm));
+  if (per_sm < 1) return fail(EBN_ECUDA, "kernel does not fit on an SM (dyn smem %zu)", dyn);
+  int64_t b = (int64_t)dv.sms * per_sm;
+  if (b > local_items) b = local_items;
+  if (b < 1) b = 1;
+  *blocks = (int)b;
+  return EBN_OK;
+}
+
+// Sums `n` int64 (and optionally doubles) across devices of this process and
+// across processes. Buffers are device pointers, one per device.
+int allreduce(std::vector<void*>& i64, size_t n_i64, std::vector<void*>& f64, size_t n_f64,
+              bool across_ranks) {
+  const size_t nd = g.devs.size();
+  if (nd > 1) {
+    NC(g_nccl.GroupStart());
+    for (size_t k = 0; k < nd; ++k) {
+      Dev& dv = g.devs[k];
+      NC(g_nccl.AllReduce(i64[k], i64[k], n_i64, kNcclInt64, kNcclSum, dv.comm, dv.st));
+      if (n_f64) NC(g_nccl.AllReduce(f64[k], f64[k], n_f64, kNcclFloat64, kNcclSum, dv.comm, dv.st));
+    }
+    NC(g_nccl.GroupEnd());
+  }
+  if (across_ranks) {
+    if (!g.rank_comm)
+      return fail(EBN_ESTATE, "job is sharded over %d ranks but ebn_comm_init_rank was not called",
+                  g.world);
+    Dev& dv = g.devs[0];
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.AllReduce(i64[0], i64[0], n_i64, kNcclInt64, kNcclSum, g.rank_comm, dv.st));
+    if (n_f64) NC(g_nccl.AllReduce(f64[0], f64[0], n_f64, kNcclFloat64, kNcclSum, g.rank_comm, dv.st));
+    NC(g_nccl.GroupEnd());
+  }
+  return EBN_OK;
+}
+
+int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, int64_t* counts_out,
+              double* sum_out, double* sumsq_out) {
+  int rc = require_ready();
+  if (rc) return rc;
+  Prepared P;
+  if ((rc = prepare(job, mode, P))) return rc;
+  const int S = job->n_scenarios;
+  const size_t nd = g.devs.size();
+  const int jw = job->shard_world <= 1 ? 1 : job->shard_world;
+  const int jr = job->shard_world <= 1 ? 0 : job->shard_rank;
+  if (jw > 1 && g.rank_comm && jw != g.world && !(job->flags & EBN_JOB_PARTIAL))
+    return fail(EBN_EINVAL, "shard_world %d differs from the communicator's world %d", jw, g.world);
+  if (jw > 1 && nd > 1)
+    return fail(EBN_ESTATE, "multi-device init and multi-rank sharding cannot be combined");
+  const size_t ncnt = mode == 0 ? (size_t)S : (size_t)S * (nedges + 1);
+  const size_t dyn = mode == 0 ? 0 : (size_t)nedges * sizeof(double) + (size_t)(nedges + 1) * sizeof(unsigned);
+  std::vector<void*> ci(nd), cf(nd);
+  std::vector<McParams> mps(nd);
+  std::vector<int> blocks(nd);
+  double h2d = 0.0;
+  int64_t my_samples = 0;
+  // stage + launch on every device before waiting on any
+  for (size_t k = 0; k < nd; ++k) {
+    Dev& dv = g.devs[k];
+    const int rank = jr * (int)nd + (int)k;
+    if ((rc = stage(dv, job, P, rank, mps[k], h2d))) return rc;
+    McParams& mp = mps[k];
+    if ((rc = dv.counts.ensure(ncnt * sizeof(unsigned long long)))) return rc;
+    CU(cudaMemsetAsync(dv.counts.p, 0, ncnt * sizeof(unsigned long long), dv.st));
+    mp.counts = (unsigned long long*)dv.counts.p;
+    ci[k] = dv.counts.p;
+    if (mode == 1) {
+      if ((rc = dv.edges.ensure((size_t)nedges * sizeof(double)))) return rc;
+      CU(cudaMemcpyAsync(dv.edges.p, edges, (size_t)nedges * sizeof(double), cudaMemcpyHostToDevice, dv.st));
+      h2d += (double)nedges * sizeof(double);
+      const size_t pb = (size_t)(mp.local_items > 0 ? mp.local_items : 1) * 2 * sizeof(double);
+      if ((rc = dv.partial.ensure(pb))) return rc;
+      if ((rc = dv.sums.ensure((size_t)2 * S * sizeof(double)))) return rc;
+      mp.edges = (const double*)dv.edges.p;
+      mp.partial = (double*)dv.partial.p;
+      mp.nedges = nedges;
+      cf[k] = dv.sums.p;
+    }
+    if ((rc = grid_for(dv, job, P, mode, dyn, mp.local_items, &blocks[k]))) return rc;
+    CU(cudaEventRecord(dv.ev0, dv.st));
+    if (mp.local_items > 0)
+      CU(ls_vtable(job->limit_state)->launch(job->strict ? 1 : 0, P.plan_class, mode, mp, blocks[k], dyn, dv.st));
+    if (mode == 1)
+      CU(moments_launch(mp.partial, mp.local_items, mp.items_per_scenario, mp.shard_rank,
+                        mp.shard_world, S, (double*)dv.sums.p, (double*)dv.sums.p + S, dv.st));
+    CU(cudaEventRecord(dv.ev1, dv.st));
+  }
+  const bool partial = (job->flags & EBN_JOB_PARTIAL) != 0;
+  if (nd > 1 || (jw > 1 && !partial)) {
+    if ((rc = allreduce(ci, ncnt, cf, mode == 1 ? (size_t)2 * S : 0, jw > 1 && !partial))) return rc;
+  }
+  // results come from device 0 (after the all-reduce every device holds them)
+  Dev& d0 = g.devs[0];
+  CU(cudaSetDevice(d0.id));
+  CU(cudaMemcpyAsync(counts_out, d0.counts.p, ncnt * sizeof(int64_t), cudaMemcpyDeviceToHost, d0.st));
+  double d2h = (double)ncnt * sizeof(int64_t);
+  std::vector<double> sums;
+  if (mode == 1) {
+    sums.resize((size_t)2 * S);
+    CU(cudaMemcpyAsync(sums.data(), d0.sums.p, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, d0.st));
+    d2h += (double)sums.size() * sizeof(double);
+  }
+  double kms = 0.0;
+  for (size_t k = 0; k < nd; ++k) {
+    Dev& dv = g.devs[k];
+    CU(cudaSetDevice(dv.id));
+    CU(cudaStreamSynchronize(dv.st));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, dv.ev0, dv.ev1));
+    if (ms > kms) kms = ms;
+    // samples done by this device: every pair of its items, clipped to [first,last)
+    my_samples += 0;
+  }
+  CU(cudaSetDevice(d0.id));
+  if (mode == 1) {
+    for (int s = 0; s < S; ++s) {
+      if (sum_out) sum_out[s] = sums[s];
+      if (sumsq_out) sumsq_out[s] = sums[(size_t)S + s];
+    }
+  }
+  // samples processed by this process = its share of items (approximately
+  // n*S/world; exact accounting by items)
+  {
+    const int64_t total_items = P.items_per_scenario * S;
+    int64_t mine = 0;
+    for (size_t k = 0; k < nd; ++k) mine += mps[k].local_items;
+    my_samples = (int64_t)((double)job->n_per_scenario * S * ((double)mine / (double)total_items));
+  }
+  g.stats = ebn_stats_t{};
+  g.stats.kernel_ms = kms;
+  g.stats.h2d_bytes = h2d;
+  g.stats.d2h_bytes = d2h;
+  g.stats.samples = my_samples;
+  g.stats.launches = (int)nd * (mode == 1 ? 2 : 1);
+  g.stats.devices = (int)nd;
+  g.stats.specialised = P.plan_class == PLAN_STATIC;
+  return EBN_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// exported functions
+// ===========================================================================
+extern "C" {
+
+int ebn_abi_version(void) { return EBN_ABI_VERSION; }
+
+const char* ebn_last_error(void) { return g_err.c_str(); }
+
+int ebn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int ebn_shutdown(void) {
+  if (g.rank_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g.rank_comm);
+  g.rank_comm = nullptr;
+  g.rank = 0;
+  g.world = 1;
+  for (Dev& dv : g.devs) {
+    cudaSetDevice(dv.id);
+    if (dv.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(dv.comm);
+    for (Buf* b : {&dv.plan, &dv.consts, &dv.tables, &dv.chol, &dv.streams, &dv.counts, &dv.edges,
+                   &dv.partial, &dv.sums, &dv.mat, &dv.gout})
+      b->release();
+    if (dv.ev0) cudaEventDestroy(dv.ev0);
+    if (dv.ev1) cudaEventDestroy(dv.ev1);
+    if (dv.own) cudaStreamDestroy(dv.own);
+  }
+  g.devs.clear();
+  g.ready = false;
+  return EBN_OK;
+}
+
+int ebn_init(const int* devices, int ndev) {
+  if (g.ready) ebn_shutdown();
+  if (ndev < 0 || (ndev > 0 && !devices)) return fail(EBN_EINVAL, "bad device list");
+  const int avail = ebn_device_count();
+  if (avail < 1) return fail(EBN_ENODEV, "no CUDA device is visible; libebncuda has no CPU fallback");
+  std::vector<int> ids;
+  if (ndev == 0) ids.push_back(0);
+  for (int i = 0; i < ndev; ++i) {
+    if (devices[i] < 0 || devices[i] >= avail)
+      return fail(EBN_ENODEV, "device %d requested but only %d visible", devices[i], avail);
+    for (int k = 0; k < i; ++k)
+      if (devices[k] == devices[i]) return fail(EBN_EINVAL, "device %d listed twice", devices[i]);
+    ids.push_back(devices[i]);
+  }
+  g.devs.resize(ids.size());
+  for (size_t k = 0; k < ids.size(); ++k) {
+    Dev& dv = g.devs[k];
+    dv.id = ids[k];
+    CU(cudaSetDevice(dv.id));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dv.id));
+    if (prop.major < 10)
+      return fail(EBN_ENODEV, "device %d is sm_%d%d; libebncuda is built for sm_100a only", dv.id,
+                  prop.major, prop.minor);
+    dv.sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&dv.own, cudaStreamNonBlocking));
+    dv.st = dv.own;
+    CU(cudaEventCreate(&dv.ev0));
+    CU(cudaEventCreate(&dv.ev1));
+  }
+  if (ids.size() > 1) {
+    int rc = nccl_load();
+    if (rc) { g.devs.clear(); return rc; }
+    std::vector<ncclComm_t> comms(ids.size());
+    NC(g_nccl.CommInitAll(comms.data(), (int)ids.size(), ids.data()));
+    for (size_t k = 0; k < ids.size(); ++k) g.devs[k].comm = comms[k];
+  }
+  CU(cudaSetDevice(g.devs[0].id));
+  g.ready = true;
+  return EBN_OK;
+}
+
+int ebn_set_stream(void* cuda_stream) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (g.devs.size() != 1) return fail(EBN_ESTATE, "ebn_set_stream needs single-device mode");
+  g.devs[0].st = cuda_stream ? (cudaStream_t)cuda_stream : g.devs[0].own;
+  return EBN_OK;
+}
+
+int ebn_nccl_unique_id(void* id128) {
+  if (!id128) return fail(EBN_EINVAL, "id128 is NULL");
+  int rc = nccl_load();
+  if (rc) return rc;
+  NC(g_nccl.GetUniqueId(id128));
+  return EBN_OK;
+}
+
+int ebn_comm_init_rank(const void* id128, int rank, int world) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(EBN_EINVAL, "bad rank/world");
+  if (g.devs.size() != 1) return fail(EBN_ESTATE, "one process per GPU: init with exactly one device");
+  if ((rc = nccl_load())) return rc;
+  if (g.rank_comm) { g_nccl.CommDestroy(g.rank_comm); g.rank_comm = nullptr; }
+  CU(cudaSetDevice(g.devs[0].id));
+  NcclId id;
+  memcpy(id.b, id128, 128);
+  NC(g_nccl.CommInitRank(&g.rank_comm, world, id, rank));
+  g.rank = rank;
+  g.world = world;
+  return EBN_OK;
+}
+
+int ebn_comm_destroy(void) {
+  if (g.rank_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g.rank_comm);
+  g.rank_comm = nullptr;
+  g.rank = 0;
+  g.world = 1;
+  return EBN_OK;
+}
+
+int ebn_pf_batch(const ebn_job_t* job, int64_t* fail_count, double* pf, double* var) {
+  if (!fail_count) return fail(EBN_EINVAL, "fail_count is NULL");
+  int rc = run_batch(job, 0, nullptr, 0, fail_count, nullptr, nullptr);
+  if (rc) return rc;
+  const double n = (double)job->n_per_scenario;
+  for (int s = 0; s < job->n_scenarios; ++s) {
+    const double p = (double)fail_count[s] / n;  // sum(Bool)/n
+    if (pf) pf[s] = p;
+    if (var) var[s] = (p - p * p) / n;
+  }
+  return EBN_OK;
+}
+
+int ebn_hist_batch(const ebn_job_t* job, const double* edges, int nedges, int64_t* counts,
+                   double* sum, double* sumsq) {
+  if (!counts) return fail(EBN_EINVAL, "counts is NULL");
+  if (!edges || nedges < 1 || nedges > EBN_MAX_EDGES)
+    return fail(EBN_EINVAL, "need 1..%d histogram edges", EBN_MAX_EDGES);
+  for (int i = 0; i < nedges; ++i) {
+    if (std::isnan(edges[i])) return fail(EBN_EINVAL, "edge %d is NaN", i);
+    if (i && !(edges[i] > edges[i - 1])) return fail(EBN_EINVAL, "edges must be strictly increasing");
+  }
+  return run_batch(job, 1, edges, nedges, counts, sum, sumsq);
+}
+
+int ebn_eval_matrix(int limit_state, const double* consts, int n_consts, const double* X, int64_t n,
+                    int d, int64_t ld, int strict, int64_t* fail_count, double* g_out) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (!fail_count) return fail(EBN_EINVAL, "fail_count is NULL");
+  if (n < 0 || (n > 0 && !X) || ld < n) return fail(EBN_EINVAL, "bad matrix shape n=%lld ld=%lld", (long long)n, (long long)ld);
+  if ((rc = check_limit_state(limit_state, consts, n_consts, d))) return rc;
+  *fail_count = 0;
+  if (n == 0) return EBN_OK;
+  Dev& dv = g.devs[0];
+  CU(cudaSetDevice(dv.id));
+  const size_t xb = (size_t)ld * d * sizeof(double);
+  if ((rc = dv.mat.ensure(xb))) return rc;
+  if ((rc = dv.consts.ensure((size_t)n_consts * sizeof(double)))) return rc;
+  if ((rc = dv.counts.ensure(sizeof(unsigned long long)))) return rc;
+  if (g_out && (rc = dv.gout.ensure((size_t)n * sizeof(double)))) return rc;
+  CU(cudaMemcpyAsync(dv.mat.p, X, xb, cudaMemcpyHostToDevice, dv.st));
+  if (n_consts) CU(cudaMemcpyAsync(dv.consts.p, consts, (size_t)n_consts * sizeof(double), cudaMemcpyHostToDevice, dv.st));
+  CU(cudaMemsetAsync(dv.counts.p, 0, sizeof(unsigned long long), dv.st));
+  int64_t blocks = (n + threads_per_block() - 1) / threads_per_block();
+  const int64_t cap = (int64_t)dv.sms * 8;
+  if (blocks > cap) blocks = cap;
+  CU(cudaEventRecord(dv.ev0, dv.st));
+  CU(ls_vtable(limit_state)->matrix(strict ? 1 : 0, (const double*)dv.consts.p, n_consts,
+                   (const double*)dv.mat.p, n, d, ld, (unsigned long long*)dv.counts.p,
+                   g_out ? (double*)dv.gout.p : nullptr, (int)blocks, dv.st));
+  CU(cudaEventRecord(dv.ev1, dv.st));
+  CU(cudaMemcpyAsync(fail_count, dv.counts.p, sizeof(int64_t), cudaMemcpyDeviceToHost, dv.st));
+  if (g_out) CU(cudaMemcpyAsync(g_out, dv.gout.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, dv.st));
+  CU(cudaStreamSynchronize(dv.st));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, dv.ev0, dv.ev1));
+  g.stats = ebn_stats_t{};
+  g.stats.kernel_ms = ms;
+  g.stats.h2d_bytes = (double)xb + (double)n_consts * sizeof(double);
+  g.stats.d2h_bytes = 8.0 + (g_out ? (double)n * 8.0 : 0.0);
+  g.stats.samples = n;
+  g.stats.launches = 1;
+  g.stats.devices = 1;
+  return EBN_OK;
+}
+
+int ebn_sample_matrix(const ebn_job_t* job, int scenario, int64_t first, int64_t n, double* X,
+                      double* g_out) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (!X) return fail(EBN_EINVAL, "X is NULL");
+  if (n < 1 || first < 0) return fail(EBN_EINVAL, "bad sample range");
+  Prepared P;
+  if ((rc = prepare(job, 0, P))) return rc;
+  if (scenario < 0 || scenario >= job->n_scenarios) return fail(EBN_EINVAL, "scenario %d out of range", scenario);
+  Dev& dv = g.devs[0];
+  McParams mp;
+  double h2d = 0.0;
+  if ((rc = stage(dv, job, P, 0, mp, h2d))) return rc;
+  mp.first = first;
+  mp.last = first + n;
+  mp.pair_base = first >> 1;
+  const int d = job->n_inputs;
+  if ((rc = dv.mat.ensure((size_t)n * d * sizeof(double)))) return rc;
+  if (g_out && (rc = dv.gout.ensure((size_t)n * sizeof(double)))) return rc;
+  int64_t blocks = ((n + 1) / 2 + threads_per_block()) / threads_per_block();
+  if (blocks > (int64_t)dv.sms * 8) blocks = (int64_t)dv.sms * 8;
+  CU(ls_vtable(job->limit_state)->replay(job->strict ? 1 : 0, P.plan_class, mp, scenario, n,
+                   (double*)dv.mat.p, g_out ? (double*)dv.gout.p : nullptr, (int)blocks, dv.st));
+  CU(cudaMemcpyAsync(X, dv.mat.p, (size_t)n * d * sizeof(double), cudaMemcpyDeviceToHost, dv.st));
+  if (g_out) CU(cudaMemcpyAsync(g_out, dv.gout.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, dv.st));
+  CU(cudaStreamSynchronize(dv.st));
+  return EBN_OK;
+}
+
+int ebn_peak_fp64(double seconds, double* dfma_per_s) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (!dfma_per_s) return fail(EBN_EINVAL, "dfma_per_s is NULL");
+  Dev& dv = g.devs[0];
+  CU(cudaSetDevice(dv.id));
+  if ((rc = dv.gout.ensure(64))) return rc;
+  const int blocks = dv.sms * 8;  // 2048 threads per SM
+  const int T = threads_per_block();
+  int iters = 4096;
+  double best = 0.0, spent = 0.0;
+  if (!(seconds > 0.0)) seconds = 0.2;
+  // warm-up + calibrate, then repeat until `seconds` of device time is spent
+  for (int rep = 0; rep < 1000 && spent < seconds; ++rep) {
+    CU(cudaEventRecord(dv.ev0, dv.st));
+    CU(dfma_launch((double*)dv.gout.p, iters, blocks, dv.st));
+    CU(cudaEventRecord(dv.ev1, dv.st));
+    CU(cudaStreamSynchronize(dv.st));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, dv.ev0, dv.ev1));
+    const double dfma = (double)blocks * T * (double)iters * 64.0;
+    if (rep > 0) {
+      spent += ms * 1e-3;
+      const double rate = dfma / (ms * 1e-3);
+      if (rate > best) best = rate;
+    }
+    if (ms < 20.f && iters < (1 << 24)) iters *= 2;
+  }
+  *dfma_per_s = best;
+  return EBN_OK;
+}
+
+int ebn_last_stats(ebn_stats_t* out) {
+  if (!out) return fail(EBN_EINVAL, "out is NULL");
+  *out = g.stats;
+  return EBN_OK;
+}
+
+int ebn_limit_state_id(const char* name) {
+  if (!name) return EBN_EINVAL;
+  for (const auto& l : kLs)
+    if (strcmp(l.name, name) == 0) return l.id;
+  return fail(EBN_ELIMITSTATE, "unknown limit state '%s'", name);
+}
+
+const char* ebn_limit_state_name(int id) {
+  const LsInfo* li = ls_info(id);
+  return li ? li->name : nullptr;
+}
+
+int ebn_limit_state_arity(int id, int* n_inputs, int* n_consts) {
+  const LsInfo* li = ls_info(id);
+  if (!li) return fail(EBN_ELIMITSTATE, "unknown limit state id %d", id);
+  if (n_inputs) *n_inputs = li->d;
+  if (n_consts) *n_consts = li->nc;
+  return EBN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// Device-side plan structures shared by the kernels and the host API.
+#pragma once
+#include <cstdint>
+
+namespace ebn {
+
+// Canonical per-input sampling recipe, produced on the host from ebn_input_t
+// (truncation windows are mapped to probability space there, in fp64).
+enum DevKind : int32_t {
+  DK_CONST = 0,           // x = a                          (UQ Parameter)
+  DK_UNIFORM = 1,         // x = a + u*b
+  DK_NORMAL_BM = 2,       // x = a + b*z,  z by Box-Muller across the sample pair
+  DK_LOGNORMAL_BM = 3,    // x = exp(a + b*z)
+  DK_NORMAL_ICDF = 4,     // x = a + b*Phi^-1(c + u*d)      (truncated)
+  DK_LOGNORMAL_ICDF = 5,  // x = exp(a + b*Phi^-1(c + u*d))
+  DK_GUMBEL = 6,          // x = a - b*log(-log(c + u*d))
+  DK_EXP_AFFINE = 7,      // x = a - b*log1p(-(c + u*d))    (b carries sign*theta)
+  DK_GAMMA_MT = 8,        // Marsaglia-Tsang, shape a, scale b (untruncated)
+  DK_TABLE = 9,           // x = Q(c + u*d), Q linear on a uniform grid of npts points
+  DK_NKINDS = 10
+};
+
+struct DevInput {
+  int32_t kind;
+  int32_t npts;
+  double a, b, c, d;
+  int64_t off;  // DK_TABLE: offset of Q[0] in the tables pool
+};
+static_assert(sizeof(DevInput) == 48, "DevInput layout");
+
+struct McParams {
+  const DevInput* plan;         // [S*d]
+  const double* consts;         // [n_consts]
+  const double* tables;         // pool
+  const double* chol;           // nullable: copula factors
+  const uint32_t* stream_id;    // nullable [S]
+  unsigned long long* counts;   // PF: [S]; HIST: [S*(nedges+1)]
+  const double* edges;          // HIST: [nedges]
+  double* partial;              // HIST: [items*2] per-item (sum, sumsq)
+  int64_t first;                // first global sample index
+  int64_t last;                 // one past the last global sample index
+  int64_t pairs_per_item;       // pairs in one work item
+  int64_t items_per_scenario;
+  int64_t local_items;          // items this rank processes
+  int64_t pair_base;            // first >> 1
+  int32_t shard_rank, shard_world;
+  int32_t S, d, n_consts, nedges;
+  uint32_t k0, k1;
+  int32_t chol_shared;
+};
+
+}  // namespace ebn

@@ -1,0 +1,250 @@
+// Limit states compiled into the kernels as device functors.
+//
+// Every functor has two arithmetic policies:
+//   StrictOps — one IEEE-754 operation per Julia operation, in Julia's
+//               evaluation order, no FMA contraction (__dmul_rn & co. are never
+//               fused by nvcc). This is what ebn_eval_matrix(strict=1) uses for
+//               bit-exact fail counts on matrices exported from the reference.
+//   FastOps   — same mathematics, re-associated: reciprocals of constants
+//               hoisted, FMA contraction, shared subexpressions. |g| differs
+//               from strict by a few ulp; count differences can only come from
+//               samples with |g| ~ 1e-13 (reported as ties by the tests).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/ebncuda.h"
+
+namespace ebn {
+
+struct StrictOps {
+  static constexpr bool strict = true;
+  __device__ __forceinline__ static double add(double a, double b) { return __dadd_rn(a, b); }
+  __device__ __forceinline__ static double sub(double a, double b) { return __dsub_rn(a, b); }
+  __device__ __forceinline__ static double mul(double a, double b) { return __dmul_rn(a, b); }
+  __device__ __forceinline__ static double div(double a, double b) { return __ddiv_rn(a, b); }
+  __device__ __forceinline__ static double sqrt(double a) { return __dsqrt_rn(a); }
+  // Julia's min/minimum propagate NaN.
+  __device__ __forceinline__ static double min(double a, double b) {
+    return (b < a || b != b) ? b : a;
+  }
+};
+
+struct FastOps {
+  static constexpr bool strict = false;
+  __device__ __forceinline__ static double add(double a, double b) { return a + b; }
+  __device__ __forceinline__ static double sub(double a, double b) { return a - b; }
+  __device__ __forceinline__ static double mul(double a, double b) { return a * b; }
+  __device__ __forceinline__ static double div(double a, double b) { return a / b; }
+  __device__ __forceinline__ static double sqrt(double a) { return ::sqrt(a); }
+  __device__ __forceinline__ static double min(double a, double b) {
+    return (b < a || b != b) ? b : a;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Vehicle suspension — reference demo/vehicle_suspension.jl:17-25
+// (same body at demo/vehicle_suspension_imprecise.jl:43-51).
+// x = (A, b0, V, C, Ck, K); consts = (M, m, g, (M*g)^-1.5, (g*(M+m))^0.877).
+// ---------------------------------------------------------------------------
+template <class Ops>
+struct VehicleSuspension {
+  static constexpr int ID = EBN_LS_VEHICLE_SUSPENSION;
+  static constexpr int D = 6;    // fixed arity
+  static constexpr int XCAP = 6; // columns held per sample
+  static constexpr int NC = 5;
+  struct Ctx {
+    double M, m, gg, pow_a, pow_b;     // strict
+    double pim, mM, iM, imM, immM, mpM, Mg;
+    double k1, k2, k3, k4;             // fast
+  };
+  __device__ static void setup(Ctx& c, const double* k, int, int) {
+    const double M = k[0], m = k[1], g = k[2];
+    c.M = M;
+    c.m = m;
+    c.gg = __dmul_rn(g, g);              // g .^ 2 (g is an Int in the demo: exact)
+    c.pow_a = k[3];
+    c.pow_b = k[4];
+    c.pim = __dmul_rn(3.141592653589793, m);  // Float64(pi) * m
+    c.mpM = __dadd_rn(m, M);
+    c.mM = __dmul_rn(m, M);
+    c.immM = __dmul_rn(m, __dmul_rn(M, M));   // m * M^2
+    c.Mg = __dmul_rn(M, g);
+    if (!Ops::strict) {
+      c.iM = 1.0 / M;
+      c.imM = 1.0 / c.mM;
+      c.k1 = 1.0 / c.mpM;
+      c.k2 = 1.0 / c.immM;
+      c.k3 = 4000.0 * k[3];
+      c.k4 = c.pim / c.gg;
+    }
+  }
+  __device__ __forceinline__ static double eval(const Ctx& c, const double* x) {
+    const double A = x[0], b0 = x[1], V = x[2], C = x[3], Ck = x[4], K = x[5];
+    if (Ops::strict) {
+      // g1 = 1 - (pi*m*V*A)/(b0*K*g^2) * [(Ck/(m+M) - C/M)^2 + C^2/(m*M) + Ck*K^2/(m*M^2)]
+      const double num = Ops::mul(Ops::mul(c.pim, V), A);
+      const double den = Ops::mul(Ops::mul(b0, K), c.gg);
+      const double e = Ops::sub(Ops::div(Ck, c.mpM), Ops::div(C, c.M));
+      const double t1 = Ops::mul(e, e);
+      const double t2 = Ops::div(Ops::mul(C, C), c.mM);
+      const double t3 = Ops::div(Ops::mul(Ck, Ops::mul(K, K)), c.immM);
+      const double br = Ops::add(Ops::add(t1, t2), t3);
+      const double g1 = Ops::sub(1.0, Ops::mul(Ops::div(num, den), br));
+      // g2 = 4000*C*(M*g)^-1.5 - 8.6394
+      const double g2 = Ops::sub(Ops::mul(Ops::mul(4000.0, C), c.pow_a), 8.6394);
+      // g3 = 2*sqrt(M*g*(K^2*Ck/(C*(m+M)) + C)) - 1
+      const double in3 =
+          Ops::add(Ops::div(Ops::mul(Ops::mul(K, K), Ck), Ops::mul(C, c.mpM)), C);
+      const double g3 = Ops::sub(Ops::mul(2.0, Ops::sqrt(Ops::mul(c.Mg, in3))), 1.0);
+      // g4 = Ck - (g*(M+m))^0.877
+      const double g4 = Ops::sub(Ck, c.pow_b);
+      return Ops::min(Ops::min(Ops::min(g1, g2), g3), g4);
+    } else {
+      // one reciprocal serves both divisions by a random variable: 1/(K*C)
+      const double rKC = 1.0 / (K * C);
+      const double iK = C * rKC, iC = K * rKC;
+      const double K2Ck = K * K * Ck;
+      const double e = Ck * c.k1 - C * c.iM;
+      const double br = e * e + C * C * c.imM + K2Ck * c.k2;
+      const double g1 = 1.0 - (c.k4 * A) * (V * iK) * br / b0;
+      const double g2 = C * c.k3 - 8.6394;
+      const double g3 = 2.0 * ::sqrt(c.Mg * (K2Ck * iC * c.k1 + C)) - 1.0;
+      const double g4 = Ck - c.pow_b;
+      return Ops::min(Ops::min(Ops::min(g1, g2), g3), g4);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Straub frame — reference demo/straub_example.jl:16-39 (== test/inference/
+// variableselimination.jl:148-171) after transmission.jl:9-29 fused R1..R5
+// into the frame node. x = (Ur, V, H, e1..e5); consts = (lambda, zeta, rho).
+// ---------------------------------------------------------------------------
+template <class Ops>
+struct StraubFrame {
+  static constexpr int ID = EBN_LS_STRAUB_FRAME;
+  static constexpr int D = 8;
+  static constexpr int XCAP = 8;
+  static constexpr int NC = 3;
+  struct Ctx {
+    double lambda, rz, sd;
+  };
+  __device__ static void setup(Ctx& c, const double* k, int, int) {
+    const double lambda = k[0], zeta = k[1], rho = k[2];
+    c.lambda = lambda;
+    c.rz = __dmul_rn(rho, zeta);  // rho * zeta (then * u_r)
+    // sqrt((1 - rho^2) * zeta^2)
+    c.sd = __dsqrt_rn(__dmul_rn(__dsub_rn(1.0, __dmul_rn(rho, rho)), __dmul_rn(zeta, zeta)));
+  }
+  __device__ __forceinline__ static double eval(const Ctx& c, const double* x) {
+    const double ur = x[0], v = x[1], h = x[2];
+    const double mu = Ops::add(c.lambda, Ops::mul(c.rz, ur));
+    double r[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) r[i] = exp(Ops::add(mu, Ops::mul(c.sd, x[3 + i])));
+    const double h5 = Ops::mul(5.0, h), v5 = Ops::mul(5.0, v);
+    const double g1 = Ops::sub(Ops::add(Ops::add(Ops::add(r[0], r[1]), r[3]), r[4]), h5);
+    const double g2 = Ops::sub(Ops::add(Ops::add(r[1], Ops::mul(2.0, r[2])), r[3]), v5);
+    const double g3 = Ops::sub(
+        Ops::sub(Ops::add(Ops::add(Ops::add(r[0], Ops::mul(2.0, r[2])), Ops::mul(2.0, r[3])), r[4]),
+                 h5),
+        v5);
+    return Ops::min(Ops::min(g1, g2), g3);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Hydrogen — reference demo/Hydrogen_new/ebn.jl:98-111 (`hyram_performance`).
+// x = (scenario, r_operators, burn_r_C_3th, explosion_r_C). The two radii come
+// from HyRAM, which is not in the reference repository; here they are inputs.
+// ---------------------------------------------------------------------------
+template <class Ops>
+struct HydrogenRadius {
+  static constexpr int ID = EBN_LS_HYDROGEN_RADIUS;
+  static constexpr int D = 4;
+  static constexpr int XCAP = 4;
+  static constexpr int NC = 0;
+  struct Ctx {};
+  __device__ static void setup(Ctx&, const double*, int, int) {}
+  __device__ __forceinline__ static double eval(const Ctx&, const double* x) {
+    const double sc = x[0];
+    if (sc == 1.0) return Ops::sub(x[1], x[2]);
+    if (sc == 2.0) return Ops::sub(x[1], x[3]);
+    return 1.0;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Polynomial program — the toy models of test/networks/ebn/evaluate/
+// evaluate_node.jl:96-98, evaluate_net.jl:18-33, discretize.jl:275-277.
+// Encoding documented in include/ebncuda.h. The program is warp-uniform, the
+// column file x[] is per thread.
+// ---------------------------------------------------------------------------
+template <class Ops>
+struct PolynomialProgram {
+  static constexpr int ID = EBN_LS_POLYNOMIAL;
+  static constexpr int D = -1;  // variadic
+  static constexpr int XCAP = EBN_MAX_INPUTS;
+  static constexpr int NC = -1;
+  struct Ctx {
+    const double* prog;
+    int d;
+  };
+  __device__ static void setup(Ctx& c, const double* k, int, int d) {
+    c.prog = k;
+    c.d = d;
+  }
+  // y_out (optional) receives the value of the last MODEL stage (the column
+  // a ContinuousFunctionalNode keeps); the return value is the last stage.
+  __device__ __forceinline__ static double eval(const Ctx& c, double* x) {
+    const double* p = c.prog;
+    const int T = (int)p[0];
+    int pos = 1, col = c.d;
+    double acc = 0.0;
+    for (int t = 0; t < T; ++t) {
+      const int nterms = (int)p[pos++];
+      acc = 0.0;
+      for (int k = 0; k < nterms; ++k) {
+        double term = p[pos++];
+        const int nf = (int)p[pos++];
+        for (int f = 0; f < nf; ++f) term = Ops::mul(term, x[(int)p[pos++]]);
+        acc = (k == 0) ? term : Ops::add(acc, term);
+      }
+      if (col < XCAP) x[col] = acc;
+      ++col;
+    }
+    return acc;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// min over affine forms: g = min_k (c_k0 + sum_j c_kj x_j).
+// consts = (K, K rows of (1+d)).
+// ---------------------------------------------------------------------------
+template <class Ops>
+struct MinAffine {
+  static constexpr int ID = EBN_LS_MIN_AFFINE;
+  static constexpr int D = -1;
+  static constexpr int XCAP = EBN_MAX_INPUTS;
+  static constexpr int NC = -1;
+  struct Ctx {
+    const double* k;
+    int d;
+  };
+  __device__ static void setup(Ctx& c, const double* k, int, int d) {
+    c.k = k;
+    c.d = d;
+  }
+  __device__ __forceinline__ static double eval(const Ctx& c, double* x) {
+    const int K = (int)c.k[0];
+    double g = 0.0;
+    for (int r = 0; r < K; ++r) {
+      const double* row = c.k + 1 + r * (1 + c.d);
+      double acc = row[0];
+      for (int j = 0; j < c.d; ++j) acc = Ops::add(acc, Ops::mul(row[1 + j], x[j]));
+      g = (r == 0) ? acc : Ops::min(g, acc);
+    }
+    return g;
+  }
+};
+
+}  // namespace ebn

@@ -1,0 +1,368 @@
+// sm_100a kernels of libebncuda: fused sample -> limit state -> count.
+//
+// Replaces, for ALL scenarios of a functional node at once, the body of the
+// loop at reference src/networks/ebn/evaluation/evaluate_node.jl:79-119
+// (UQ.jl `sample` + `evaluate!` + `sum(performance(df) .< 0)`), and for
+// ContinuousFunctionalNode the body at :22-33 (histogram instead of a KDE).
+//
+// Work decomposition: item = (scenario, chunk of sample pairs). Persistent
+// blocks stride over this rank's items; threads stride over the pairs of an
+// item. No global memory is touched per sample: the only traffic is the plan
+// (48 B per input per item, L2 resident) in and one 64-bit atomic per item out.
+#pragma once
+#include <cstdio>
+#include "ebn_kernels.h"
+#include "ebn_limit_states.cuh"
+#include "ebn_sampling.cuh"
+
+namespace ebn {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// Compile-time sampling plans ------------------------------------------------
+template <int... K>
+struct StaticPlan {
+  static constexpr bool is_static = true;
+  static constexpr int n = sizeof...(K);
+  static constexpr int kinds[sizeof...(K) ? sizeof...(K) : 1] = {K...};
+};
+struct DynamicPlan {
+  static constexpr bool is_static = false;
+};
+struct CopulaPlan {
+  static constexpr bool is_static = false;
+};
+
+struct NoStaticPlan {
+  static constexpr bool is_static = false;
+  static constexpr int n = 0;
+};
+
+template <class Plan, int XCAP, int J>
+struct DrawAll {
+  __device__ __forceinline__ static void run(const DevInput* sp, const PairCtr& pc,
+                                             const double* tables, double* x0, double* x1) {
+    if constexpr (J < Plan::n) {
+      draw_pair<Plan::kinds[J]>(sp[J], pc, (uint32_t)J, tables, x0[J], x1[J]);
+      DrawAll<Plan, XCAP, J + 1>::run(sp, pc, tables, x0, x1);
+    }
+  }
+};
+
+template <class Plan, int XCAP>
+__device__ __forceinline__ void draw_inputs(const DevInput* sp, const double* sL, int d,
+                                            const PairCtr& pc, const double* tables, double* x0,
+                                            double* x1) {
+  if constexpr (Plan::is_static) {
+    DrawAll<Plan, XCAP, 0>::run(sp, pc, tables, x0, x1);
+  } else if constexpr (std::is_same<Plan, CopulaPlan>::value) {
+    draw_pair_copula(sp, sL, d, pc, tables, x0, x1);
+  } else {
+#pragma unroll
+    for (int j = 0; j < XCAP; ++j) {
+      if (j < d) draw_pair_dyn(sp[j], pc, (uint32_t)j, tables, x0[j], x1[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ int find_bin(const double* edges, int nedges, double y) {
+  // number of edges <= y  (NaN -> nedges)
+  if (!(y == y)) return nedges;
+  int lo = 0, hi = nedges;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (edges[mid] <= y) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// MODE 0: failure count. MODE 1: histogram + moments of the output.
+template <class LS, class Plan, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) mc_kernel(const McParams p) {
+  constexpr int XCAP = LS::XCAP;
+  __shared__ DevInput s_plan[EBN_MAX_INPUTS];
+  __shared__ double s_chol[std::is_same<Plan, CopulaPlan>::value ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
+  __shared__ unsigned int s_red[kWarps];
+  __shared__ double s_sum[MODE == 1 ? 2 * kWarps : 1];
+  extern __shared__ unsigned char s_dyn[];  // MODE 1: edges (double) then bins (u32)
+  double* s_edges = reinterpret_cast<double*>(s_dyn);
+  unsigned int* s_bins = reinterpret_cast<unsigned int*>(s_dyn + sizeof(double) * (MODE == 1 ? p.nedges : 0));
+
+  typename LS::Ctx ctx;
+  LS::setup(ctx, p.consts, p.n_consts, p.d);
+
+  const int tid = threadIdx.x;
+  if (MODE == 1) {
+    for (int i = tid; i < p.nedges; i += kThreads) s_edges[i] = p.edges[i];
+  }
+
+  for (int64_t li = blockIdx.x; li < p.local_items; li += gridDim.x) {
+    const int64_t w = li * p.shard_world + p.shard_rank;  // global item
+    const int s = (int)(w / p.items_per_scenario);
+    const int64_t c = w - (int64_t)s * p.items_per_scenario;
+
+    __syncthreads();  // previous item's readers are done with s_plan / s_bins
+    if (tid < p.d) s_plan[tid] = p.plan[(int64_t)s * p.d + tid];
+    if (std::is_same<Plan, CopulaPlan>::value) {
+      const double* L = p.chol + (p.chol_shared ? 0 : (int64_t)s * p.d * p.d);
+      for (int i = tid; i < p.d * p.d; i += kThreads) s_chol[i] = L[i];
+    }
+    if (MODE == 1) {
+      for (int i = tid; i <= p.nedges; i += kThreads) s_bins[i] = 0u;
+    }
+    __syncthreads();
+
+    PairCtr pc;
+    pc.stream = p.stream_id ? p.stream_id[s] : (uint32_t)s;
+    pc.k0 = p.k0;
+    pc.k1 = p.k1;
+
+    const int64_t q_begin = p.pair_base + c * p.pairs_per_item;
+    int64_t q_end = q_begin + p.pairs_per_item;
+    const int64_t q_last = (p.last + 1) >> 1;  // one past the last pair
+    if (q_end > q_last) q_end = q_last;
+
+    unsigned int cnt = 0;
+    double sum = 0.0, sumsq = 0.0;
+    for (int64_t q = q_begin + tid; q < q_end; q += kThreads) {
+      pc.qlo = (uint32_t)q;
+      pc.qhi = (uint32_t)((uint64_t)q >> 32);
+      double x0[XCAP], x1[XCAP];
+      draw_inputs<Plan, XCAP>(s_plan, s_chol, p.d, pc, p.tables, x0, x1);
+      const double g0 = LS::eval(ctx, x0);
+      const double g1 = LS::eval(ctx, x1);
+      const int64_t i0 = q << 1;
+      const bool v0 = i0 >= p.first;           // i0 < last holds by construction
+      const bool v1 = (i0 + 1) < p.last;       // i0+1 >= first holds by construction
+      if (MODE == 0) {
+        cnt += (unsigned)(v0 && g0 < 0.0) + (unsigned)(v1 && g1 < 0.0);
+      } else {
+        if (v0) {
+          atomicAdd(&s_bins[find_bin(s_edges, p.nedges, g0)], 1u);
+          if (g0 == g0) { sum += g0; sumsq = fma(g0, g0, sumsq); }
+        }
+        if (v1) {
+          atomicAdd(&s_bins[find_bin(s_edges, p.nedges, g1)], 1u);
+          if (g1 == g1) { sum += g1; sumsq = fma(g1, g1, sumsq); }
+        }
+      }
+    }
+
+    if (MODE == 0) {
+      // warp shuffle -> shared memory -> one 64-bit atomic per item
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if ((tid & 31) == 0) s_red[tid >> 5] = cnt;
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) tot += s_red[i];
+        if (tot) atomicAdd(&p.counts[s], tot);
+      }
+    } else {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        sumsq += __shfl_down_sync(0xffffffffu, sumsq, o);
+      }
+      if ((tid & 31) == 0) {
+        s_sum[2 * (tid >> 5)] = sum;
+        s_sum[2 * (tid >> 5) + 1] = sumsq;
+      }
+      __syncthreads();
+      for (int i = tid; i <= p.nedges; i += kThreads) {
+        const unsigned int b = s_bins[i];
+        if (b) atomicAdd(&p.counts[(int64_t)s * (p.nedges + 1) + i], (unsigned long long)b);
+      }
+      if (tid == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) {
+          a += s_sum[2 * i];
+          b += s_sum[2 * i + 1];
+        }
+        // per-item partials, combined in item order afterwards (deterministic)
+        p.partial[2 * li] = a;
+        p.partial[2 * li + 1] = b;
+      }
+    }
+  }
+}
+
+// Sampler replay: the n samples [first, first+n) of one scenario, exactly as
+// mc_kernel draws them, written column-major with ld = n.
+template <class LS, class Plan>
+__global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int scenario,
+                                                          int64_t n, double* X, double* g_out) {
+  constexpr int XCAP = LS::XCAP;
+  __shared__ DevInput s_plan[EBN_MAX_INPUTS];
+  __shared__ double s_chol[std::is_same<Plan, CopulaPlan>::value ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
+  typename LS::Ctx ctx;
+  LS::setup(ctx, p.consts, p.n_consts, p.d);
+  if (threadIdx.x < p.d) s_plan[threadIdx.x] = p.plan[(int64_t)scenario * p.d + threadIdx.x];
+  if (std::is_same<Plan, CopulaPlan>::value) {
+    const double* L = p.chol + (p.chol_shared ? 0 : (int64_t)scenario * p.d * p.d);
+    for (int i = threadIdx.x; i < p.d * p.d; i += kThreads) s_chol[i] = L[i];
+  }
+  __syncthreads();
+  PairCtr pc;
+  pc.stream = p.stream_id ? p.stream_id[scenario] : (uint32_t)scenario;
+  pc.k0 = p.k0;
+  pc.k1 = p.k1;
+  const int64_t q_last = (p.last + 1) >> 1;
+  for (int64_t q = p.pair_base + (int64_t)blockIdx.x * kThreads + threadIdx.x; q < q_last;
+       q += (int64_t)gridDim.x * kThreads) {
+    pc.qlo = (uint32_t)q;
+    pc.qhi = (uint32_t)((uint64_t)q >> 32);
+    double x0[XCAP], x1[XCAP];
+    draw_inputs<Plan, XCAP>(s_plan, s_chol, p.d, pc, p.tables, x0, x1);
+    const int64_t i0 = q << 1;
+    double y0[XCAP], y1[XCAP];
+#pragma unroll
+    for (int j = 0; j < XCAP; ++j) { y0[j] = x0[j]; y1[j] = x1[j]; }
+    const double g0 = LS::eval(ctx, y0);
+    const double g1 = LS::eval(ctx, y1);
+    if (i0 >= p.first) {
+      const int64_t r = i0 - p.first;
+#pragma unroll
+      for (int j = 0; j < XCAP; ++j)
+        if (j < p.d) X[(int64_t)j * n + r] = x0[j];
+      if (g_out) g_out[r] = g0;
+    }
+    if (i0 + 1 < p.last) {
+      const int64_t r = i0 + 1 - p.first;
+#pragma unroll
+      for (int j = 0; j < XCAP; ++j)
+        if (j < p.d) X[(int64_t)j * n + r] = x1[j];
+      if (g_out) g_out[r] = g1;
+    }
+  }
+}
+
+// Limit state over a resident sample matrix (column-major). HBM-bound:
+// d*8 bytes read per row (+8 written when g_out is requested).
+template <class LS>
+__global__ void __launch_bounds__(kThreads) matrix_kernel(const double* consts, int n_consts,
+                                                          const double* X, int64_t n, int d,
+                                                          int64_t ld, unsigned long long* count,
+                                                          double* g_out) {
+  constexpr int XCAP = LS::XCAP;
+  __shared__ unsigned int s_red[kWarps];
+  typename LS::Ctx ctx;
+  LS::setup(ctx, consts, n_consts, d);
+  unsigned int cnt = 0;
+  for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < n;
+       r += (int64_t)gridDim.x * kThreads) {
+    double x[XCAP];
+#pragma unroll
+    for (int j = 0; j < XCAP; ++j) x[j] = (j < d) ? __ldg(&X[(int64_t)j * ld + r]) : 0.0;
+    const double g = LS::eval(ctx, x);
+    if (g_out) g_out[r] = g;
+    cnt += (unsigned)(g < 0.0);
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) tot += s_red[i];
+    if (tot) atomicAdd(count, tot);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-limit-state table of launchers (one translation unit per limit state so
+// the build parallelises)
+// ---------------------------------------------------------------------------
+template <template <class> class LST, class SPlan>
+struct LsLaunch {
+  template <class LS, class Plan>
+  static cudaError_t occ2(int mode, size_t dyn, int* out) {
+    if (mode == 0)
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, mc_kernel<LS, Plan, 0>, kThreads, dyn);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, mc_kernel<LS, Plan, 1>, kThreads, dyn);
+  }
+  template <class LS, class Plan>
+  static cudaError_t launch2(int mode, const McParams& p, int blocks, size_t dyn, cudaStream_t st) {
+    if (mode == 0) mc_kernel<LS, Plan, 0><<<blocks, kThreads, dyn, st>>>(p);
+    else mc_kernel<LS, Plan, 1><<<blocks, kThreads, dyn, st>>>(p);
+    return cudaGetLastError();
+  }
+  template <class LS, class Plan>
+  static cudaError_t replay2(const McParams& p, int scenario, int64_t n, double* X, double* g,
+                             int blocks, cudaStream_t st) {
+    replay_kernel<LS, Plan><<<blocks, kThreads, 0, st>>>(p, scenario, n, X, g);
+    return cudaGetLastError();
+  }
+
+  template <class LS>
+  static cudaError_t occ1(int plan_class, int mode, size_t dyn, int* out) {
+    if (plan_class == PLAN_COPULA) return occ2<LS, CopulaPlan>(mode, dyn, out);
+    if constexpr (SPlan::is_static) {
+      if (plan_class == PLAN_STATIC) return occ2<LS, SPlan>(mode, dyn, out);
+    }
+    return occ2<LS, DynamicPlan>(mode, dyn, out);
+  }
+  template <class LS>
+  static cudaError_t launch1(int plan_class, int mode, const McParams& p, int blocks, size_t dyn,
+                             cudaStream_t st) {
+    if (plan_class == PLAN_COPULA) return launch2<LS, CopulaPlan>(mode, p, blocks, dyn, st);
+    if constexpr (SPlan::is_static) {
+      if (plan_class == PLAN_STATIC) return launch2<LS, SPlan>(mode, p, blocks, dyn, st);
+    }
+    return launch2<LS, DynamicPlan>(mode, p, blocks, dyn, st);
+  }
+  template <class LS>
+  static cudaError_t replay1(int plan_class, const McParams& p, int scenario, int64_t n, double* X,
+                             double* g, int blocks, cudaStream_t st) {
+    if (plan_class == PLAN_COPULA) return replay2<LS, CopulaPlan>(p, scenario, n, X, g, blocks, st);
+    if constexpr (SPlan::is_static) {
+      if (plan_class == PLAN_STATIC) return replay2<LS, SPlan>(p, scenario, n, X, g, blocks, st);
+    }
+    return replay2<LS, DynamicPlan>(p, scenario, n, X, g, blocks, st);
+  }
+
+  static cudaError_t occupancy(int strict, int plan_class, int mode, size_t dyn, int* out) {
+    return strict ? occ1<LST<StrictOps>>(plan_class, mode, dyn, out)
+                  : occ1<LST<FastOps>>(plan_class, mode, dyn, out);
+  }
+  static cudaError_t launch(int strict, int plan_class, int mode, const McParams& p, int blocks,
+                            size_t dyn, cudaStream_t st) {
+    return strict ? launch1<LST<StrictOps>>(plan_class, mode, p, blocks, dyn, st)
+                  : launch1<LST<FastOps>>(plan_class, mode, p, blocks, dyn, st);
+  }
+  static cudaError_t replay(int strict, int plan_class, const McParams& p, int scenario, int64_t n,
+                            double* X, double* g, int blocks, cudaStream_t st) {
+    return strict ? replay1<LST<StrictOps>>(plan_class, p, scenario, n, X, g, blocks, st)
+                  : replay1<LST<FastOps>>(plan_class, p, scenario, n, X, g, blocks, st);
+  }
+  static cudaError_t matrix(int strict, const double* consts, int n_consts, const double* X,
+                            int64_t n, int d, int64_t ld, unsigned long long* count, double* g_out,
+                            int blocks, cudaStream_t st) {
+    if (strict)
+      matrix_kernel<LST<StrictOps>><<<blocks, kThreads, 0, st>>>(consts, n_consts, X, n, d, ld, count, g_out);
+    else
+      matrix_kernel<LST<FastOps>><<<blocks, kThreads, 0, st>>>(consts, n_consts, X, n, d, ld, count, g_out);
+    return cudaGetLastError();
+  }
+  static LsVTable vtable() {
+    LsVTable v;
+    v.occupancy = &occupancy;
+    v.launch = &launch;
+    v.replay = &replay;
+    v.matrix = &matrix;
+    if constexpr (SPlan::is_static) {
+      v.static_kinds = SPlan::kinds;
+      v.n_static = SPlan::n;
+    } else {
+      v.static_kinds = nullptr;
+      v.n_static = 0;
+    }
+    return v;
+  }
+};
+
+}  // namespace ebn

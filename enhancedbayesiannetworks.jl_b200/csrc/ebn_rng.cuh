@@ -1,0 +1,66 @@
+// Counter-based RNG and uniform/normal primitives (device side).
+//
+// Stream layout v1 (DESIGN.md "Random streams"):
+//   key     = (seed lo32, seed hi32)
+//   counter = (pair lo32, pair hi32, stream id of the scenario, slot)
+//   pair    = global sample index >> 1   (two samples share one Philox call)
+//   slot    = input index j  (+ 16*(1+2*attempt+e) for Gamma attempts)
+//   A = w1:w0, B = w3:w2;  U(x) = ((x >> 12) + 0.5) * 2^-52  in (0,1)
+// The replacement for `rand(dist, n)` inside UQ.jl's `sample(inputs, n)`
+// (called from reference src/networks/ebn/evaluation/evaluate_node.jl:24,83).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ebn {
+
+struct Philox4 {
+  uint32_t w0, w1, w2, w3;
+};
+
+// Philox4x32-10 (Salmon et al., SC'11). 2 IMAD.WIDE + 2 LOP3 per round; the
+// key schedule is uniform across the grid so it lives in uniform registers.
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                 uint32_t c3, uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0;
+    const uint64_t p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += W0;
+    k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+// 52 random bits -> (0,1), never 0 or 1: ((x>>12)+0.5)*2^-52. The subtraction is
+// exact (result has <= 53 significant bits), so this is bit-reproducible anywhere.
+__device__ __forceinline__ double u52(uint32_t lo, uint32_t hi) {
+  const uint32_t mlo = (lo >> 12) | (hi << 20);
+  const uint32_t mhi = (hi >> 12) | 0x3FF00000u;
+  const double d = __hiloint2double((int)mhi, (int)mlo);  // [1,2)
+  return d - 0x1.fffffffffffffp-1;  // 1 - 2^-53
+}
+
+// 32 random bits -> (0,1): (w+0.5)*2^-32
+__device__ __forceinline__ double u32(uint32_t w) {
+  return ((double)w + 0.5) * 2.3283064365386962890625e-10;
+}
+
+// Box-Muller: two independent N(0,1) from two uniforms in (0,1).
+__device__ __forceinline__ void box_muller(double ua, double ub, double& z0, double& z1) {
+  const double r = sqrt(-2.0 * log(ua));
+  double s, c;
+  sincospi(2.0 * ub, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+}  // namespace ebn

@@ -1,0 +1,399 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * bit-exact fail counts on identical sample matrices (strict mode); the fast mode may
+    differ only on samples with |g| below 1e-12 * scale, which are reported as ties;
+  * independent-RNG estimates of pf within 3 standard errors of the oracle's;
+  * counts independent of partition, grid, chunking and sharding.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import cpu as ocpu
+from oracle import replay
+
+pytestmark = pytest.mark.gpu
+
+INF = math.inf
+
+
+def _vehicle_matrix(rng, n):
+    X = np.empty((n, 6))
+    X[:, 0] = rng.choice([0.15915, 0.8], n)
+    X[:, 1] = rng.choice([0.27, 0.5], n)
+    X[:, 2] = rng.uniform(7, 12, n)
+    X[:, 3] = rng.normal(431.7221, 10, n)
+    X[:, 4] = rng.normal(1475.5503, 10, n)
+    X[:, 5] = rng.normal(55.0406, 10, n)
+    return X
+
+
+def _straub_matrix(rng, n):
+    X = np.empty((n, 8))
+    X[:, 0] = rng.normal(0, 1, n)
+    X[:, 1] = rng.gamma(25.0, 2.4, n)
+    X[:, 2] = rng.gumbel(40.99893584908611, 15.593936024673523, n)
+    X[:, 3:] = rng.normal(0, 1, (n, 5))
+    return X
+
+
+def poly_program(stages):
+    """stages: list of list of (coef, [cols]) → consts array for EBN_LS_POLYNOMIAL."""
+    out = [float(len(stages))]
+    for terms in stages:
+        out.append(float(len(terms)))
+        for coef, cols in terms:
+            out.append(float(coef))
+            out.append(float(len(cols)))
+            out.extend(float(c) for c in cols)
+    return np.array(out)
+
+
+# test/networks/ebn/evaluate/evaluate_node.jl:96-98: model C = A + B, performance 2 - C
+PROG_2_MINUS_A_PLUS_B = poly_program([[(1.0, [0]), (1.0, [1])], [(2.0, []), (-1.0, [2])]])
+
+
+# ---------------------------------------------------------------------------
+# 1. limit states on identical matrices: bit-exact counts and g (strict)
+# ---------------------------------------------------------------------------
+def test_eval_matrix_vehicle_strict_bit_exact(ebn):
+    from ebn_b200 import workloads as W
+    rng = np.random.default_rng(1)
+    X = _vehicle_matrix(rng, 300_000)
+    k = W.vehicle_consts()
+    want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_VEHICLE, k, X, want_g=True)
+    got_cnt, got_g = ebn.eval_matrix(ebn._lib.LS_VEHICLE_SUSPENSION, k, X, strict=True, want_g=True)
+    assert got_cnt == want_cnt
+    assert np.array_equal(got_g, want_g), f"max |dg| = {np.max(np.abs(got_g - want_g))}"
+    # second, independent restatement (NumPy) agrees too
+    assert np.array_equal(replay.g_vehicle(X, k), want_g)
+    assert 0 < want_cnt < len(X)
+
+
+def test_eval_matrix_vehicle_fast_ties_only(ebn):
+    from ebn_b200 import workloads as W
+    rng = np.random.default_rng(2)
+    X = _vehicle_matrix(rng, 300_000)
+    k = W.vehicle_consts()
+    want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_VEHICLE, k, X, want_g=True)
+    got_cnt, got_g = ebn.eval_matrix(ebn._lib.LS_VEHICLE_SUSPENSION, k, X, strict=False, want_g=True)
+    # stated fp64 tolerance on g: 1e-12 relative to the magnitude of the terms (|g| <= ~1e2)
+    assert np.max(np.abs(got_g - want_g)) < 1e-11
+    flips = np.flatnonzero((got_g < 0) != (want_g < 0))
+    assert np.all(np.abs(want_g[flips]) < 1e-12), "fast mode flipped a sample that is not a tie"
+    assert abs(got_cnt - want_cnt) <= len(flips)
+    print(f"ties |g|<1e-12: {len(flips)} of {len(X)}")
+
+
+def test_eval_matrix_straub(ebn):
+    from ebn_b200 import workloads as W
+    rng = np.random.default_rng(3)
+    X = _straub_matrix(rng, 200_000)
+    k = W.straub_consts()
+    want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_STRAUB, k, X, want_g=True)
+    got_cnt, got_g = ebn.eval_matrix(ebn._lib.LS_STRAUB_FRAME, k, X, strict=True, want_g=True)
+    # exp() is not correctly rounded anywhere (Julia, glibc, CUDA all < 1 ulp): g carries a
+    # relative tolerance of 1e-13 on terms of magnitude ~1e3; counts may differ only on ties.
+    assert np.max(np.abs(got_g - want_g)) < 1e-9
+    flips = np.flatnonzero((got_g < 0) != (want_g < 0))
+    assert np.all(np.abs(want_g[flips]) < 1e-9)
+    assert abs(got_cnt - want_cnt) <= len(flips)
+    assert 0 < want_cnt < len(X)
+
+
+def test_eval_matrix_polynomial_and_min_affine_bit_exact(ebn):
+    rng = np.random.default_rng(4)
+    X = rng.normal(0.5, 1.0, (100_000, 2))
+    for strict in (True, False):
+        want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_POLYNOMIAL, PROG_2_MINUS_A_PLUS_B, X, want_g=True)
+        got_cnt, got_g = ebn.eval_matrix(ebn._lib.LS_POLYNOMIAL, PROG_2_MINUS_A_PLUS_B, X, strict=strict, want_g=True)
+        if strict:
+            assert got_cnt == want_cnt and np.array_equal(got_g, want_g)
+            assert np.array_equal(want_g, 2.0 - (X[:, 0] + X[:, 1]))
+        else:
+            assert np.max(np.abs(got_g - want_g)) < 1e-13
+    # quadratic model x^2 - 0.7 + y (test/networks/ebn/evaluate/evaluate_net.jl style)
+    prog = poly_program([[(1.0, [0, 0]), (-0.7, []), (1.0, [1])]])
+    want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_POLYNOMIAL, prog, X, want_g=True)
+    got_cnt, got_g = ebn.eval_matrix(ebn._lib.LS_POLYNOMIAL, prog, X, strict=True, want_g=True)
+    assert got_cnt == want_cnt and np.array_equal(got_g, want_g)
+    assert np.array_equal(want_g, (X[:, 0] * X[:, 0] - 0.7) + X[:, 1])
+    # min of two affine forms
+    k = np.array([2.0, 1.0, -1.0, 0.5, 0.25, 2.0, -0.75])
+    want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_MIN_AFFINE, k, X, want_g=True)
+    got_cnt, got_g = ebn.eval_matrix(ebn._lib.LS_MIN_AFFINE, k, X, strict=True, want_g=True)
+    assert got_cnt == want_cnt and np.array_equal(got_g, want_g)
+
+
+def test_eval_matrix_hydrogen_and_edge_cases(ebn):
+    rng = np.random.default_rng(5)
+    X = np.column_stack([rng.integers(0, 4, 50_000).astype(float), rng.uniform(0, 10, 50_000),
+                         rng.uniform(0, 10, 50_000), rng.uniform(0, 10, 50_000)])
+    want = ocpu.eval_matrix(ocpu.LS_HYDROGEN, np.zeros(0), X)
+    got = ebn.eval_matrix(ebn._lib.LS_HYDROGEN_RADIUS, np.zeros(0), X, strict=True)
+    assert got == want
+    # empty matrix, single row, NaN rows (NaN is safe: `NaN < 0` is false)
+    assert ebn.eval_matrix(ebn._lib.LS_HYDROGEN_RADIUS, np.zeros(0), np.zeros((0, 4))) == 0
+    assert ebn.eval_matrix(ebn._lib.LS_HYDROGEN_RADIUS, np.zeros(0), np.array([[1.0, 1.0, 2.0, 0.0]])) == 1
+    Xn = np.array([[np.nan, -5.0], [1.0, 5.0], [np.nan, np.nan]])
+    assert ebn.eval_matrix(ebn._lib.LS_POLYNOMIAL, PROG_2_MINUS_A_PLUS_B, Xn) == 1
+
+
+# ---------------------------------------------------------------------------
+# 2. the sampler: replayed matrices against the NumPy twin of the stream layout
+# ---------------------------------------------------------------------------
+ALL_KINDS_ROW = [
+    (0, 3.25, 0, 0, 0, -INF, INF),            # Parameter
+    (1, 1.0, 2.0, 0, 0, -INF, INF),           # Normal (Box-Muller)
+    (1, 1.0, 2.0, 0, 0, 0.5, 4.0),            # truncated Normal
+    (2, 0.3, 0.25, 0, 0, -INF, INF),          # LogNormal
+    (2, 0.3, 0.25, 0, 0, 1.0, 2.0),           # truncated LogNormal
+    (3, 7.0, 12.0, 0, 0, 8.5, 9.5),           # truncated Uniform
+    (4, 41.0, 15.6, 0, 0, -INF, INF),         # Gumbel
+    (4, 41.0, 15.6, 0, 0, 30.0, 80.0),        # truncated Gumbel
+    (5, 25.0, 2.4, 0, 0, -INF, INF),          # Gamma (shape >= 1)
+    (5, 0.6, 1.5, 0, 0, -INF, INF),           # Gamma (shape < 1)
+    (6, 2.0, 1.0, 3.0, 0, -INF, INF),         # 3 + Exponential(2)
+    (6, 2.0, -1.0, 3.0, 0, 0.0, INF),         # 3 - Exponential(2), truncated to >= 0
+    (7, 0.0, 5.0, 0, 0, -INF, INF),           # tabulated quantile
+]
+TABLE = np.array([-1.0, 0.0, 0.5, 2.0, 10.0])
+
+
+def _min_affine_all(d):
+    return np.array([1.0, 0.0] + [1.0] * d)
+
+
+@pytest.mark.parametrize("first,n", [(0, 4096), (7, 1001), (2**33 + 5, 512)])
+def test_replay_matches_numpy_twin(ebn, first, n):
+    rows = [ALL_KINDS_ROW, ALL_KINDS_ROW]
+    inputs = ebn.make_inputs(rows)
+    d = inputs.shape[1]
+    job = ebn.Job(ebn._lib.LS_MIN_AFFINE, _min_affine_all(d), inputs, n=first + n, seed=0xABCDEF0123456789,
+                  tables=TABLE)
+    for s in (0, 1):
+        X = ebn.sample_matrix(job, s, first, n)
+        ref = replay.sample_matrix(inputs[s], s, 0xABCDEF0123456789, first, n, tables=TABLE)
+        scale = np.maximum(np.abs(ref), 1.0)
+        err = np.max(np.abs(X - ref) / scale, axis=0)
+        # transcendental implementations differ (CUDA libdevice vs NumPy/SciPy) by a few ulp;
+        # the inverse-normal tails amplify that slightly
+        assert np.all(err < 5e-12), f"scenario {s}: per-input max rel err {err}"
+    # different scenarios are different streams
+    assert not np.allclose(ebn.sample_matrix(job, 0, first, n)[:, 1], ebn.sample_matrix(job, 1, first, n)[:, 1])
+
+
+def test_replay_moments(ebn):
+    """Distribution sanity of the sampler on 2e6 draws (means within 5 standard errors)."""
+    n = 2_000_000
+    inputs = ebn.make_inputs([ALL_KINDS_ROW])
+    job = ebn.Job(ebn._lib.LS_MIN_AFFINE, _min_affine_all(inputs.shape[1]), inputs, n=n, seed=11, tables=TABLE)
+    X = ebn.sample_matrix(job, 0, 0, n)
+    from scipy import stats
+    expect = {
+        1: stats.norm(1, 2), 2: stats.truncnorm((0.5 - 1) / 2, (4 - 1) / 2, 1, 2),
+        3: stats.lognorm(0.25, scale=math.exp(0.3)), 5: stats.uniform(8.5, 1.0),
+        6: stats.gumbel_r(41.0, 15.6), 8: stats.gamma(25.0, scale=2.4), 9: stats.gamma(0.6, scale=1.5),
+        10: stats.expon(3.0, 2.0),
+    }
+    for j, dist in expect.items():
+        se = dist.std() / math.sqrt(n)
+        assert abs(X[:, j].mean() - dist.mean()) < 5 * se, (j, X[:, j].mean(), dist.mean())
+        ks = stats.kstest(X[:200_000, j], dist.cdf)
+        assert ks.pvalue > 1e-4, (j, ks)
+    assert X[:, 2].min() >= 0.5 and X[:, 2].max() <= 4.0
+    assert X[:, 4].min() >= 1.0 and X[:, 4].max() <= 2.0
+    assert X[:, 7].min() >= 30.0 and X[:, 7].max() <= 80.0
+    assert X[:, 11].min() >= 0.0 and X[:, 11].max() <= 3.0
+
+
+# ---------------------------------------------------------------------------
+# 3. fused kernel == replay + oracle, bit for bit
+# ---------------------------------------------------------------------------
+def test_fused_count_equals_oracle_on_replayed_matrix_vehicle(ebn):
+    from ebn_b200 import workloads as W
+    n = 300_001  # odd on purpose
+    job = W.w1_vehicle(n=n, strict=True)
+    cnt, pf, var = ebn.pf_batch(job)
+    assert ebn.last_stats()["specialised"] == 1
+    for s in range(job.S):
+        X = ebn.sample_matrix(job, s, 0, n)
+        assert int(cnt[s]) == ocpu.eval_matrix(ocpu.LS_VEHICLE, job.consts, X), s
+    assert np.array_equal(pf, cnt / n)
+    assert np.allclose(var, (pf - pf * pf) / n, rtol=0, atol=0)
+    # fast mode: same streams, counts differ at most by ties
+    cnt_fast, _, _ = ebn.pf_batch(W.w1_vehicle(n=n, strict=False))
+    assert np.max(np.abs(cnt_fast - cnt)) <= 1
+
+
+def test_fused_count_equals_oracle_on_replayed_matrix_straub(ebn):
+    from ebn_b200 import workloads as W
+    n = 400_000
+    job = W.w2_straub(n=n, strict=True)
+    cnt, pf, _ = ebn.pf_batch(job)
+    assert ebn.last_stats()["specialised"] == 1
+    X, g = ebn.sample_matrix(job, 0, 0, n, want_g=True)
+    assert int(cnt[0]) == int(np.sum(g < 0))
+    want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_STRAUB, job.consts, X, want_g=True)
+    flips = np.flatnonzero((g < 0) != (want_g < 0))
+    assert np.all(np.abs(want_g[flips]) < 1e-9) and abs(int(cnt[0]) - want_cnt) <= len(flips)
+    # demo/straub_example.jl:71 anchor: pf ~ 0.026129 (atol 0.01)
+    assert abs(pf[0] - 0.026129) < 0.01
+
+
+def test_fused_dynamic_plan_all_kinds(ebn):
+    """Generic (runtime-dispatched) sampling plan: fused count == oracle on the replayed matrix."""
+    inputs = ebn.make_inputs([ALL_KINDS_ROW, ALL_KINDS_ROW[::-1][1:] + [ALL_KINDS_ROW[-1]]])
+    # keep the table input last in both rows so the layout is valid
+    d = inputs.shape[1]
+    k = np.array([1.0, -150.0] + [1.0] * d)
+    n = 100_000
+    job = ebn.Job(ebn._lib.LS_MIN_AFFINE, k, inputs, n=n, seed=5, strict=True, tables=TABLE)
+    cnt, pf, _ = ebn.pf_batch(job)
+    assert ebn.last_stats()["specialised"] == 0
+    for s in range(2):
+        X = ebn.sample_matrix(job, s, 0, n)
+        assert int(cnt[s]) == ocpu.eval_matrix(ocpu.LS_MIN_AFFINE, k, X)
+    assert 0 < cnt[0] < n
+
+
+# ---------------------------------------------------------------------------
+# 4. counts do not depend on partitioning, sharding or resume offsets
+# ---------------------------------------------------------------------------
+def test_sharding_and_offsets_are_count_invariant(ebn):
+    from ebn_b200 import workloads as W
+    n = 1_000_003
+    base, _, _ = ebn.pf_batch(W.w1_vehicle(n=n))
+    for world in (2, 3, 8):
+        tot = np.zeros_like(base)
+        for r in range(world):
+            j = W.w1_vehicle(n=n)
+            j.shard_rank, j.shard_world, j.partial = r, world, True
+            tot += ebn.pf_batch(j)[0]
+        assert np.array_equal(tot, base), world
+    # resume: [0, a) + [a, n) == [0, n) for even and odd split points
+    for a in (400_000, 400_001):
+        j1 = W.w1_vehicle(n=a)
+        j2 = W.w1_vehicle(n=n - a)
+        j2.sample_offset = a
+        assert np.array_equal(ebn.pf_batch(j1)[0] + ebn.pf_batch(j2)[0], base), a
+    # stream ids: a permuted stream assignment permutes the counts of identical scenarios
+    j = W.w5_vehicle_grid(n=100_000, side=2)
+    j.inputs[:] = j.inputs[0]
+    c0 = ebn.pf_batch(j)[0]
+    j.stream_id = np.array([3, 2, 1, 0], dtype=np.uint32)
+    j.__post_init__()
+    c1 = ebn.pf_batch(j)[0]
+    assert np.array_equal(c1, c0[::-1]) and len(set(c0.tolist())) > 1
+    # common random numbers: equal stream ids → identical counts
+    j.stream_id = np.zeros(4, dtype=np.uint32)
+    j.__post_init__()
+    c2 = ebn.pf_batch(j)[0]
+    assert len(set(c2.tolist())) == 1 and c2[0] == c0[0]
+
+
+def test_tiny_and_ragged_sizes(ebn):
+    from ebn_b200 import workloads as W
+    for n in (1, 2, 3, 255, 256, 257, 511, 513):
+        job = W.w1_vehicle(n=n, strict=True)
+        cnt = ebn.pf_batch(job)[0]
+        X = ebn.sample_matrix(job, 14, 0, n)
+        assert int(cnt[14]) == ocpu.eval_matrix(ocpu.LS_VEHICLE, job.consts, X), n
+        assert X.shape == (n, 6)
+
+
+# ---------------------------------------------------------------------------
+# 5. independent-RNG estimates within 3 standard errors of the oracle
+# ---------------------------------------------------------------------------
+def test_pf_within_3se_of_oracle_vehicle(ebn):
+    from ebn_b200 import workloads as W
+    n_gpu, n_ref = 20_000_000, 2_000_000
+    job = W.w1_vehicle(n=n_gpu)
+    cnt, pf, var = ebn.pf_batch(job)
+    ref_cnt = ocpu.pf_batch(ocpu.LS_VEHICLE, job.consts, job.inputs.view(ocpu.INPUT_DTYPE), n_ref, seed=99, threads=8)
+    pf_ref = ref_cnt / n_ref
+    var_ref = (pf_ref - pf_ref**2) / n_ref
+    z = (pf - pf_ref) / np.sqrt(var + var_ref + 1e-300)
+    print("pf gpu", np.round(pf, 6), "\npf ref", np.round(pf_ref, 6), "\nmax|z|", np.abs(z).max())
+    assert np.all(np.abs(z) <= 3.0 + 1e-9) or np.sum(np.abs(z) > 3.0) <= 1 and np.abs(z).max() < 4.0
+
+
+def test_analytic_anchors_of_reference_tests(ebn):
+    """test/networks/ebn/evaluate/evaluate_node.jl:110 — A in {1,2} Parameters, B ~ N(0,1),
+    model C = A + B, performance 2 - C: pf = Phi(-1), Phi(0) → [0.16, 0.84, 0.5, 0.5] atol 0.02.
+    :137 — model B + 1: [0.1587, 0.8413]."""
+    rows = [[(0, a, 0, 0, 0, -INF, INF), (1, 0.0, 1.0, 0, 0, -INF, INF)] for a in (1.0, 2.0)]
+    n = 4_000_000
+    job = ebn.Job(ebn._lib.LS_POLYNOMIAL, PROG_2_MINUS_A_PLUS_B, ebn.make_inputs(rows), n=n, seed=2024)
+    cnt, pf, var = ebn.pf_batch(job)
+    exact = np.array([0.15865525393145707, 0.5])
+    assert np.all(np.abs(pf - exact) <= 3 * np.sqrt(exact * (1 - exact) / n))
+    assert np.allclose([pf[0], 1 - pf[0], pf[1], 1 - pf[1]], [0.16, 0.84, 0.5, 0.5], atol=0.02)
+    # truncated normal anchor: B ~ truncated(N(0,1), -1, 2): P(B > 1) = (Phi(2)-Phi(1))/(Phi(2)-Phi(-1))
+    rows = [[(0, 1.0, 0, 0, 0, -INF, INF), (1, 0.0, 1.0, 0, 0, -1.0, 2.0)]]
+    job = ebn.Job(ebn._lib.LS_POLYNOMIAL, PROG_2_MINUS_A_PLUS_B, ebn.make_inputs(rows), n=n, seed=7)
+    pf = ebn.pf_batch(job)[1][0]
+    from scipy.special import ndtr
+    p = (ndtr(2) - ndtr(1)) / (ndtr(2) - ndtr(-1))
+    assert abs(pf - p) <= 3 * math.sqrt(p * (1 - p) / n)
+
+
+# ---------------------------------------------------------------------------
+# 6. histogram path (ContinuousFunctionalNode)
+# ---------------------------------------------------------------------------
+def test_hist_batch_matches_numpy_on_replayed_samples(ebn):
+    rows = [[(0, a, 0, 0, 0, -INF, INF), (1, 0.0, 1.0, 0, 0, -INF, INF)] for a in (1.0, 2.0, 3.0)]
+    prog = poly_program([[(1.0, [0]), (1.0, [1])]])  # C = A + B (a continuous functional node's model)
+    n = 500_001
+    job = ebn.Job(ebn._lib.LS_POLYNOMIAL, prog, ebn.make_inputs(rows), n=n, seed=3, strict=True)
+    edges = np.array([-1.0, 0.0, 1.0, 1.5, 2.0, 3.0, 6.0])
+    counts, s1, s2 = ebn.hist_batch(job, edges)
+    assert counts.shape == (3, len(edges) + 1) and np.all(counts.sum(axis=1) == n)
+    for s in range(3):
+        X = ebn.sample_matrix(job, s, 0, n)
+        y = X[:, 0] + X[:, 1]
+        want = np.bincount(np.searchsorted(edges, y, side="right"), minlength=len(edges) + 1)
+        assert np.array_equal(counts[s], want), s
+        assert abs(s1[s] - y.sum()) < 1e-6 * n and abs(s2[s] - (y * y).sum()) < 1e-6 * n
+    # same call twice → identical moments (fixed-order reduction)
+    counts2, s1b, s2b = ebn.hist_batch(job, edges)
+    assert np.array_equal(counts, counts2) and np.array_equal(s1, s1b) and np.array_equal(s2, s2b)
+
+
+# ---------------------------------------------------------------------------
+# 7. error behaviour: never a fallback, always a code + message
+# ---------------------------------------------------------------------------
+def test_errors(ebn):
+    from ebn_b200 import workloads as W
+    E = ebn.EbnError
+    job = W.w1_vehicle(n=1000)
+    job.limit_state = 99
+    with pytest.raises(E, match="EBN_ELIMITSTATE.*no CPU fallback"):
+        ebn.pf_batch(job)
+    job = W.w1_vehicle(n=1000)
+    job.consts = job.consts[:3]
+    with pytest.raises(E, match="EBN_ELIMITSTATE.*takes 5 consts"):
+        ebn.pf_batch(job)
+    job = W.w1_vehicle(n=0)
+    with pytest.raises(E, match="EBN_EINVAL"):
+        ebn.pf_batch(job)
+    job = W.w1_vehicle(n=1000)
+    job.inputs[3, 2]["lo"], job.inputs[3, 2]["hi"] = 20.0, 30.0   # window outside Uniform(7,12)
+    with pytest.raises(E, match="EBN_EMARGINAL"):
+        ebn.pf_batch(job)
+    job = W.w1_vehicle(n=1000)
+    job.inputs[0, 3]["kind"] = 42
+    with pytest.raises(E, match="EBN_EMARGINAL.*unknown marginal"):
+        ebn.pf_batch(job)
+    job = W.w1_vehicle(n=1000)
+    job.shard_rank, job.shard_world = 0, 2  # sharded without a communicator and without PARTIAL
+    with pytest.raises(E, match="EBN_ESTATE"):
+        ebn.pf_batch(job)
+    with pytest.raises(E, match="EBN_ELIMITSTATE"):
+        ebn.eval_matrix(ebn._lib.LS_POLYNOMIAL, np.array([1.0, 1.0, 1.0, 1.0, 7.0]), np.zeros((4, 2)))
+    with pytest.raises(E, match="EBN_EINVAL"):
+        ebn.hist_batch(W.w1_vehicle(n=1000), np.array([1.0, 1.0]))
+    # the library keeps working after errors
+    assert ebn.pf_batch(W.w1_vehicle(n=1000))[0].shape == (20,)
