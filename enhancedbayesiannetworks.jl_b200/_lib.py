@@ -73,7 +73,7 @@ EXPORTS = [
     "ebn_abi_version", "ebn_device_count", "ebn_init", "ebn_shutdown", "ebn_set_stream",
     "ebn_nccl_unique_id", "ebn_comm_init_rank", "ebn_comm_destroy", "ebn_pf_batch",
     "ebn_hist_batch", "ebn_eval_matrix", "ebn_sample_matrix", "ebn_peak_fp64", "ebn_last_stats",
-    "ebn_last_error", "ebn_limit_state_id", "ebn_limit_state_name", "ebn_limit_state_arity",
+    "ebn_partition", "ebn_last_error", "ebn_limit_state_id", "ebn_limit_state_name", "ebn_limit_state_arity",
 ]
 
 
@@ -109,6 +109,7 @@ def load():
     L.ebn_eval_matrix.argtypes = [C.c_int, dp, C.c_int, dp, C.c_int64, C.c_int, C.c_int64, C.c_int, i64p, dp]
     L.ebn_sample_matrix.argtypes = [C.POINTER(EbnJob), C.c_int, C.c_int64, C.c_int64, dp, dp]
     L.ebn_peak_fp64.argtypes = [C.c_double, dp]
+    L.ebn_partition.argtypes = [C.POINTER(EbnJob), C.c_int, i64p]
     L.ebn_last_stats.argtypes = [C.POINTER(EbnStats)]
     L.ebn_last_error.restype = C.c_char_p
     L.ebn_limit_state_id.argtypes = [C.c_char_p]
@@ -310,6 +311,15 @@ def sample_matrix(job: Job, scenario: int, first: int, n: int, want_g: bool = Fa
     cj = job.c_struct()
     _check(load().ebn_sample_matrix(C.byref(cj), scenario, first, n, _dp(X), _dp(g)))
     return (X, g) if want_g else X
+
+
+def partition(job: Job, histogram: bool = False) -> dict:
+    """ebn_partition: the static (scenario, chunk) work grid of a job. Needs no GPU."""
+    out = np.zeros(4, dtype=np.int64)
+    cj = job.c_struct()
+    _check(load().ebn_partition(C.byref(cj), 1 if histogram else 0, _i64p(out)))
+    return {"pairs_per_item": int(out[0]), "items_per_scenario": int(out[1]),
+            "local_items": int(out[2]), "pair_base": int(out[3])}
 
 
 def peak_fp64(seconds: float = 0.25) -> float:

@@ -342,7 +342,7 @@ struct Prepared {
   int world = 1;  // job world * devices
 };
 
-int prepare(const ebn_job_t* job, int mode, Prepared& P) {
+int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) {
   if (!job) return fail(EBN_EINVAL, "job is NULL");
   if (job->n_scenarios < 1) return fail(EBN_EINVAL, "n_scenarios must be >= 1");
   if (!job->inputs) return fail(EBN_EINVAL, "inputs is NULL");
@@ -383,7 +383,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P) {
   } else if (static_plan_matches(job->limit_state, P.plan.data(), S, d)) {
     P.plan_class = PLAN_STATIC;
   }
-  P.world = jw * (int)g.devs.size();
+  P.world = jw * (ndev_override > 0 ? ndev_override : (int)g.devs.size());
   P.first = job->sample_offset;
   P.last = job->sample_offset + job->n_per_scenario;
   P.pair_base = P.first >> 1;
@@ -853,6 +853,19 @@ int ebn_peak_fp64(double seconds, double* dfma_per_s) {
     if (ms < 20.f && iters < (1 << 24)) iters *= 2;
   }
   *dfma_per_s = best;
+  return EBN_OK;
+}
+
+int ebn_partition(const ebn_job_t* job, int histogram, int64_t out[4]) {
+  if (!out) return fail(EBN_EINVAL, "out is NULL");
+  Prepared P;
+  int rc = prepare(job, histogram ? 1 : 0, P, 1);  // host logic only: needs no device
+  if (rc) return rc;
+  const int jr = job->shard_world <= 1 ? 0 : job->shard_rank;
+  out[0] = P.pairs_per_item;
+  out[1] = P.items_per_scenario;
+  out[2] = local_items_of(P, job->n_scenarios, jr);
+  out[3] = P.pair_base;
   return EBN_OK;
 }
 

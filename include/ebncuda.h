@@ -210,6 +210,16 @@ int ebn_eval_matrix(int limit_state, const double* consts, int n_consts,
 int ebn_sample_matrix(const ebn_job_t* job, int scenario, int64_t first,
                       int64_t n, double* X, double* g_out);
 
+/*
+ * The static work partition of a job (host logic, needs no device): a work item
+ * is (scenario, chunk of sample pairs); item w = scenario*items_per_scenario +
+ * chunk belongs to rank w % shard_world. out = {pairs_per_item,
+ * items_per_scenario, items of job->shard_rank, first pair index}. The
+ * partition depends on the job only, so all ranks derive the same grid, and
+ * counts never depend on it (the RNG is a function of seed, stream, sample).
+ */
+int ebn_partition(const ebn_job_t* job, int histogram, int64_t out[4]);
+
 /* ---- measurement -------------------------------------------------------- */
 /* Independent DFMA chains at full occupancy for about `seconds`; DFMA/s.    */
 int ebn_peak_fp64(double seconds, double* dfma_per_s);

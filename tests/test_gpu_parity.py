@@ -397,3 +397,26 @@ def test_errors(ebn):
         ebn.hist_batch(W.w1_vehicle(n=1000), np.array([1.0, 1.0]))
     # the library keeps working after errors
     assert ebn.pf_batch(W.w1_vehicle(n=1000))[0].shape == (20,)
+
+
+# ---------------------------------------------------------------------------
+# 8. committed golden fixtures (tests/golden/, made by make_golden.py)
+# ---------------------------------------------------------------------------
+def test_golden_fixtures(ebn):
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(gold, "limit_states.npz"))
+    c, g = ebn.eval_matrix(ebn._lib.LS_VEHICLE_SUSPENSION, z["vehicle_k"], z["vehicle_X"], strict=True, want_g=True)
+    assert c == int(z["vehicle_count"]) and np.array_equal(g, z["vehicle_g"])
+    c, g = ebn.eval_matrix(ebn._lib.LS_STRAUB_FRAME, z["straub_k"], z["straub_X"], strict=True, want_g=True)
+    assert c == int(z["straub_count"]) and np.max(np.abs(g - z["straub_g"])) < 1e-9
+    s = np.load(os.path.join(gold, "stream_v1.npz"))
+    inputs = s["inputs"].view(ebn.INPUT_DTYPE).reshape(1, -1)
+    inputs4 = np.repeat(inputs, 4, axis=0)  # scenario 3 is stream 3
+    d = inputs.shape[1]
+    for first in (0, 7, 2**33 + 5):
+        job = ebn.Job(ebn._lib.LS_MIN_AFFINE, _min_affine_all(d), inputs4, n=first + 64, seed=int(s["seed"]),
+                      tables=s["table"])
+        X = ebn.sample_matrix(job, 3, first, 64)
+        ref = s[f"first_{first}"]
+        assert np.max(np.abs(X - ref) / np.maximum(np.abs(ref), 1.0)) < 5e-12
