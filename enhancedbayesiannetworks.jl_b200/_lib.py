@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libebncuda.so")
+LIB_PATH = os.environ.get("EBN_LIB", os.path.join(_HERE, "libebncuda.so"))  # EBN_LIB: tuning builds only
 
 # ---- constants mirrored from include/ebncuda.h ------------------------------
 EBN_ABI_VERSION = 1

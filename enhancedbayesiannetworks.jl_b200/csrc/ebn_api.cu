@@ -250,7 +250,7 @@ int canonicalise(const ebn_input_t& in, bool copula, DevInput& o, int s, int j,
       if (trunc)
         return fail(EBN_EMARGINAL, "input (%d,%d): truncate a tabulated marginal in the table", s, j);
       o.kind = DK_TABLE;
-      o.off = (int64_t)off;
+      o.toff = (int32_t)off;
       o.npts = (int32_t)npts;
       o.c = 0.0;
       o.d = 1.0;
@@ -364,6 +364,16 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
                         job->n_tables);
       if (rc) return rc;
     }
+  // word offsets in the pair's Philox stream (layout v2): inputs consume words in order;
+  // under a copula every random input takes the 3 words of its Box-Muller pair
+  for (int s = 0; s < S; ++s) {
+    int off = 0;
+    for (int j = 0; j < d; ++j) {
+      DevInput& di = P.plan[(size_t)s * d + j];
+      di.woff = off;
+      off += copula ? (di.kind == DK_CONST ? 0 : 3) : words_of_kind(di.kind);
+    }
+  }
   if (copula) {
     const int nblk = (job->flags & EBN_JOB_COPULA_SHARED) ? 1 : S;
     for (int b = 0; b < nblk; ++b) {

@@ -24,8 +24,21 @@ struct DevInput {
   int32_t kind;
   int32_t npts;
   double a, b, c, d;
-  int64_t off;  // DK_TABLE: offset of Q[0] in the tables pool
+  int32_t toff;  // DK_TABLE: offset of Q[0] in the tables pool
+  int32_t woff;  // first word of this input in the pair's Philox word stream
 };
+
+// Philox words one input consumes per sample pair (stream layout v2).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr int words_of_kind(int kind) {
+  return kind == DK_CONST ? 0
+       : kind == DK_UNIFORM ? 2
+       : (kind == DK_NORMAL_BM || kind == DK_LOGNORMAL_BM) ? 3
+       : kind == DK_GAMMA_MT ? 0
+       : 4;
+}
 static_assert(sizeof(DevInput) == 48, "DevInput layout");
 
 struct McParams {

@@ -1,0 +1,135 @@
+// Lean fp64 primitives for the sampler's hot path.
+//
+// The CUDA math library's log/sincospi/sqrt are general (denormals, infinities,
+// huge arguments) and ptxas materialises their 64-bit coefficients with UMOV
+// pairs: in the first profile of the vehicle kernel (profiles/r01_a_*) 66 % of
+// the issued instructions were NOT fp64, which capped the fp64 pipe at 45 %.
+// The sampler only ever needs
+//     -ln(u)        u in (0,1), normal
+//     sqrt(t)       t in [2^-53, 37]
+//     sin, cos      of a first-quadrant angle
+// so each is written for exactly that domain: no special cases, no branches,
+// coefficients in __constant__ memory (consumed as c[bank][off] operands).
+// Accuracy: a few ulp (measured against NumPy/mpmath in tests/test_gpu_parity.py).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ebn {
+
+#include "ebn_fastmath_tables.inc"
+
+struct FastMathConst {
+  double sinc[9];
+  double cosc[10];
+  double ln1p[5];   // -1/2, 1/3, -1/4, 1/5, -1/6  (negated for -ln)
+  double ln2;
+};
+__constant__ FastMathConst kFm = {
+    {EBN_SIN_COEFS},
+    {EBN_COS_COEFS},
+    {0.5, -0.33333333333333331483, 0.25, -0.2000000000000000111, 0.16666666666666665741},
+    0.69314718055994528623,
+};
+
+// Shared-memory copy of the log table (per-lane random index: shared memory,
+// not the constant cache, which serialises divergent addresses).
+struct FastMathSmem {
+  double2 logtab[128];
+};
+
+__device__ __forceinline__ void fastmath_init(FastMathSmem& sm, int tid, int nthreads) {
+  for (int i = tid; i < 128; i += nthreads) sm.logtab[i] = kLogTab[i];
+}
+
+// -ln(u) for a normal double u in (0,1).
+//   u = 2^e * m, m in [1,2);  cell i of 128 (top 7 mantissa bits) gives rc ~ 1/m (24 bits)
+//   and ln(rc):   -ln(u) = -e*ln2 + ln(rc) - log1p(r),  r = m*rc - 1,  |r| <= 2^-8.
+__device__ __forceinline__ double neg_log01(double u, const FastMathSmem& sm) {
+  const int hi = __double2hiint(u);
+  const int lo = __double2loint(u);
+  // m in [1,2), e = exponent: four integer instructions fewer than re-centring m on
+  // [0.75,1.5). The price is cancellation as u -> 1 (-ln u = ln 2 - ln m): an ABSOLUTE error of ~1e-16 in
+  // -ln u, i.e. ~1e-15 absolute in the radius where the radius itself is < 0.05. x = mu +
+  // sigma*z only ever needs z to absolute accuracy, so nothing is lost.
+  const int ne = 1023 - (hi >> 20);                                   // -e in [1, 53]
+  const int mhi = (hi & 0x000FFFFF) | 0x3FF00000;                     // m in [1,2)
+  const int idx = (hi >> 13) & 0x7F;                                  // top 7 mantissa bits
+  const double m = __hiloint2double(mhi, lo);
+  const double2 t = sm.logtab[idx];
+  const double r = fma(m, t.x, -1.0);
+  // int -> double without a conversion instruction: 2^52+2^51 magic (ne >= 0)
+  const double ned = __hiloint2double(0x43380000, ne) - 6755399441055744.0;
+  // log1p(r) = r - r^2*(1/2 - r*(1/3 - r*(1/4 - r*(1/5 - r/6))))
+  double p = fma(r, kFm.ln1p[4], kFm.ln1p[3]);
+  p = fma(r, p, kFm.ln1p[2]);
+  p = fma(r, p, kFm.ln1p[1]);
+  p = fma(r, p, kFm.ln1p[0]);          // 1/2 - r/3 + r^2/4 - r^3/5 + r^4/6
+  const double r2 = r * r;
+  const double base = fma(ned, kFm.ln2, t.y);   // -e*ln2 + ln(rc)
+  return fma(r2, p, base - r);                   // ... - r + r^2*(...)
+}
+
+// sqrt(t) for t in [2^-60, 2^60]: MUFU.RSQ64H seed + two coupled Newton steps.
+__device__ __forceinline__ double sqrt_pos(double t) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
+  double g = t * y;
+  double h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  return g;
+}
+
+// 1/x for normal x, |x| in [2^-500, 2^500]: MUFU.RCP64H seed + two Newton steps.
+__device__ __forceinline__ double rcp_normal(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// (cos a + sin a, cos a - sin a) for a = (pi/2)*v, v in [-1/2, 1/2):
+// sqrt(2)*(sin, cos) of the first-quadrant angle (pi/2)*(v + 1/2).
+__device__ __forceinline__ void sincos_quadrant(double v, double& cps, double& cms) {
+  const double w = v * v;
+  double s = fma(w, kFm.sinc[7], kFm.sinc[6]);
+  double c = fma(w, kFm.cosc[8], kFm.cosc[7]);
+#pragma unroll
+  for (int i = 5; i >= 0; --i) s = fma(w, s, kFm.sinc[i]);
+#pragma unroll
+  for (int i = 6; i >= 0; --i) c = fma(w, c, kFm.cosc[i]);
+  s *= v;
+  cps = c + s;
+  cms = c - s;
+}
+
+// Box-Muller for the sample pair from three 32-bit words:
+//   radius  u = mantissa(w1 & 0xfffff : w0) in (0,1)   (52 bits; the top 12 bits of w1 are free)
+//   angle   first-quadrant angle from all 32 bits of w2 (low 20 bits most significant)
+//   signs   bits 31 and 30 of w1
+// z0 = s0*R*sin(phi), z1 = s1*R*cos(phi) with R = sqrt(-2 ln u), phi uniform in (0, pi/2):
+// a uniformly random direction, so (z0, z1) are independent standard normals.
+__device__ __forceinline__ void box_muller_words(uint32_t w0, uint32_t w1, uint32_t w2,
+                                                 const FastMathSmem& sm, double& z0, double& z1) {
+  // Mask-only bit placement (one LOP3 per word half, no shifts: the integer ALU is the
+  // scarce pipe next to the fp64 pipe): the low 20 bits of a word become the high mantissa bits.
+  const double u = __hiloint2double((int)((w1 & 0x000FFFFFu) | 0x3FF00000u), (int)w0) - 0x1.fffffffffffffp-1;
+  const double v = __hiloint2double((int)((w2 & 0x000FFFFFu) | 0x3FF00000u), (int)(w2 & 0xFFF00000u)) -
+                   (1.5 - 0x1p-33);  // [-1/2, 1/2), centred
+  const double rr = sqrt_pos(neg_log01(u, sm));  // sqrt(-ln u) = R / sqrt(2)
+  double cps, cms;
+  sincos_quadrant(v, cps, cms);
+  const double a = rr * cps;  // R*sin(phi)
+  const double b = rr * cms;  // R*cos(phi)
+  z0 = __hiloint2double(__double2hiint(a) ^ (int)(w1 & 0x80000000u), __double2loint(a));
+  z1 = __hiloint2double(__double2hiint(b) ^ (int)((w1 << 1) & 0x80000000u), __double2loint(b));
+}
+
+}  // namespace ebn

@@ -4,7 +4,13 @@
 
 namespace ebn {
 
-constexpr int kThreads = 256;
+#ifndef EBN_THREADS
+#define EBN_THREADS 256
+#endif
+#ifndef EBN_MIN_BLOCKS
+#define EBN_MIN_BLOCKS 3
+#endif
+constexpr int kThreads = EBN_THREADS;
 
 // Fixed-order reduction of the per-item moment partials: one thread per
 // scenario walks its items in order, so the result does not depend on which

@@ -51,10 +51,12 @@ struct VehicleSuspension {
   static constexpr int D = 6;    // fixed arity
   static constexpr int XCAP = 6; // columns held per sample
   static constexpr int NC = 5;
+  static constexpr bool HAS_FAILS = !Ops::strict;  // sign-only test in fast mode
   struct Ctx {
     double M, m, gg, pow_a, pow_b;     // strict
     double pim, mM, iM, imM, immM, mpM, Mg;
     double k1, k2, k3, k4;             // fast
+    double thr2, c3;                   // fast, sign-only
   };
   __device__ static void setup(Ctx& c, const double* k, int, int) {
     const double M = k[0], m = k[1], g = k[2];
@@ -75,6 +77,8 @@ struct VehicleSuspension {
       c.k2 = 1.0 / c.immM;
       c.k3 = 4000.0 * k[3];
       c.k4 = c.pim / c.gg;
+      c.thr2 = 8.6394 / c.k3;            // g2 < 0  <=>  C < thr2
+      c.c3 = 0.25 * c.mpM / c.Mg;        // g3 < 0  <=>  K^2 Ck + C^2 (m+M) < c3 * C   (C > 0)
     }
   }
   __device__ __forceinline__ static double eval(const Ctx& c, const double* x) {
@@ -112,6 +116,36 @@ struct VehicleSuspension {
       return Ops::min(Ops::min(Ops::min(g1, g2), g3), g4);
     }
   }
+  // Sign of g without its value (count mode, fast arithmetic): no division, no sqrt.
+  //   g1 < 0 <=> q/D > 1 with q = (pi m/g^2) A V [..], D = b0 K      (sign of D respected)
+  //   g2 < 0 <=> C < 8.6394/(4000 (Mg)^-1.5)
+  //   g3 < 0 <=> M g (K^2 Ck/(C (m+M)) + C) < 1/4                   (sign of C respected)
+  //   g4 < 0 <=> Ck < (g (M+m))^0.877
+  // A negative sqrt argument makes g NaN in the reference arithmetic, and NaN is safe.
+  __device__ __forceinline__ static bool fails(const Ctx& c, const double* x) {
+    const double A = x[0], b0 = x[1], V = x[2], C = x[3], Ck = x[4], K = x[5];
+    const double e = Ck * c.k1 - C * c.iM;
+    const double K2Ck = K * K * Ck;
+    const double CC = C * C;
+    const double br = fma(e, e, fma(CC, c.imM, K2Ck * c.k2));
+    const double q = (c.k4 * A) * V * br;
+    const double D = b0 * K;
+    const double lhs3 = fma(CC, c.mpM, K2Ck);
+    // The comparisons are taken from the sign bits of differences with integer logic:
+    // DSETP occupies the fp64 pipe about twice as long as a DADD (tools/microbench).
+    //   f1: q/D > 1      <=> sign(D - q) != sign(D)
+    //   f2: C < thr2     <=> sign(C - thr2)
+    //   f3: lhs3*C < c3*C*C ... <=> sign(lhs3 - c3*C) != sign(C)
+    //   f4: Ck < pow_b   <=> sign(Ck - pow_b)
+    //   nan3 (negative sqrt argument) <=> sign(lhs3) != sign(C)
+    const int sC = __double2hiint(C);
+    const int t1 = __double2hiint(D - q) ^ __double2hiint(D);
+    const int t2 = __double2hiint(C - c.thr2);
+    const int t3 = __double2hiint(fma(-c.c3, C, lhs3)) ^ sC;
+    const int t4 = __double2hiint(Ck - c.pow_b);
+    const int n3 = __double2hiint(lhs3) ^ sC;
+    return (((t1 | t2 | t3 | t4) & ~n3) < 0);
+  }
 };
 
 // ---------------------------------------------------------------------------
@@ -122,6 +156,7 @@ struct VehicleSuspension {
 template <class Ops>
 struct StraubFrame {
   static constexpr int ID = EBN_LS_STRAUB_FRAME;
+  static constexpr bool HAS_FAILS = false;
   static constexpr int D = 8;
   static constexpr int XCAP = 8;
   static constexpr int NC = 3;
@@ -160,6 +195,7 @@ struct StraubFrame {
 template <class Ops>
 struct HydrogenRadius {
   static constexpr int ID = EBN_LS_HYDROGEN_RADIUS;
+  static constexpr bool HAS_FAILS = false;
   static constexpr int D = 4;
   static constexpr int XCAP = 4;
   static constexpr int NC = 0;
@@ -182,6 +218,7 @@ struct HydrogenRadius {
 template <class Ops>
 struct PolynomialProgram {
   static constexpr int ID = EBN_LS_POLYNOMIAL;
+  static constexpr bool HAS_FAILS = false;
   static constexpr int D = -1;  // variadic
   static constexpr int XCAP = EBN_MAX_INPUTS;
   static constexpr int NC = -1;
@@ -223,6 +260,7 @@ struct PolynomialProgram {
 template <class Ops>
 struct MinAffine {
   static constexpr int ID = EBN_LS_MIN_AFFINE;
+  static constexpr bool HAS_FAILS = false;
   static constexpr int D = -1;
   static constexpr int XCAP = EBN_MAX_INPUTS;
   static constexpr int NC = -1;

@@ -17,7 +17,13 @@
 
 namespace ebn {
 
-constexpr int kThreads = 256;
+#ifndef EBN_THREADS
+#define EBN_THREADS 256
+#endif
+#ifndef EBN_MIN_BLOCKS
+#define EBN_MIN_BLOCKS 3
+#endif
+constexpr int kThreads = EBN_THREADS;
 constexpr int kWarps = kThreads / 32;
 
 // Compile-time sampling plans ------------------------------------------------
@@ -39,31 +45,114 @@ struct NoStaticPlan {
   static constexpr int n = 0;
 };
 
+// Word offset of input J in a static plan, and the number of Philox calls a pair needs.
+template <class Plan, int J>
+__host__ __device__ constexpr int static_word_offset() {
+  int off = 0;
+  for (int i = 0; i < J; ++i) off += words_of_kind(Plan::kinds[i]);
+  return off;
+}
+template <class Plan>
+__host__ __device__ constexpr int static_calls() {
+  return (static_word_offset<Plan, Plan::n>() + 3) / 4;
+}
+
 template <class Plan, int XCAP, int J>
 struct DrawAll {
-  __device__ __forceinline__ static void run(const DevInput* sp, const PairCtr& pc,
-                                             const double* tables, double* x0, double* x1) {
+  __device__ __forceinline__ static void run(const DevInput* sp, const Philox4* ph,
+                                             const PairCtr& pc, const double* tables,
+                                             const FastMathSmem& sm, double* x0, double* x1) {
     if constexpr (J < Plan::n) {
-      draw_pair<Plan::kinds[J]>(sp[J], pc, (uint32_t)J, tables, x0[J], x1[J]);
-      DrawAll<Plan, XCAP, J + 1>::run(sp, pc, tables, x0, x1);
+      StaticWords<static_word_offset<Plan, J>()> ws{ph};
+      draw_pair<Plan::kinds[J]>(sp[J], ws, pc, (uint32_t)J, tables, sm, x0[J], x1[J]);
+      DrawAll<Plan, XCAP, J + 1>::run(sp, ph, pc, tables, sm, x0, x1);
     }
   }
 };
 
+// sp: the scenario's plan (registers for a static plan, shared memory otherwise).
 template <class Plan, int XCAP>
 __device__ __forceinline__ void draw_inputs(const DevInput* sp, const double* sL, int d,
-                                            const PairCtr& pc, const double* tables, double* x0,
-                                            double* x1) {
+                                            const PairCtr& pc, const double* tables,
+                                            const FastMathSmem& sm, double* x0, double* x1) {
   if constexpr (Plan::is_static) {
-    DrawAll<Plan, XCAP, 0>::run(sp, pc, tables, x0, x1);
+    constexpr int NC = static_calls<Plan>();
+    Philox4 ph[NC > 0 ? NC : 1];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      ph[c] = philox4x32_10(pc.qlo, pc.qhi, pc.stream, (uint32_t)c, pc.k0, pc.k1);
+    DrawAll<Plan, XCAP, 0>::run(sp, ph, pc, tables, sm, x0, x1);
   } else if constexpr (std::is_same<Plan, CopulaPlan>::value) {
-    draw_pair_copula(sp, sL, d, pc, tables, x0, x1);
+    draw_pair_copula(sp, sL, d, pc, tables, sm, x0, x1);
   } else {
+    Philox4 cache;
+    int cached_call = -1;
 #pragma unroll
     for (int j = 0; j < XCAP; ++j) {
-      if (j < d) draw_pair_dyn(sp[j], pc, (uint32_t)j, tables, x0[j], x1[j]);
+      if (j < d) draw_pair_dyn(sp[j], pc, cache, cached_call, (uint32_t)j, tables, sm, x0[j], x1[j]);
     }
   }
+}
+
+// All Philox calls of one pair for a static plan.
+template <class Plan>
+__device__ __forceinline__ void static_gen(Philox4* ph, uint32_t qlo, uint32_t qhi,
+                                           const PairCtr& pc) {
+  constexpr int NC = static_calls<Plan>();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) ph[c] = philox4x32_10(qlo, qhi, pc.stream, (uint32_t)c, pc.k0, pc.k1);
+}
+
+// Failure indicator of one sample. In the fast (non-strict) count mode a limit
+// state may provide a sign-only test that skips the divisions and square roots
+// whose value does not matter for `g < 0`.
+template <class LS>
+__device__ __forceinline__ bool sample_fails(const typename LS::Ctx& ctx, double* x) {
+  if constexpr (LS::HAS_FAILS) {
+    return LS::fails(ctx, x);
+  } else {
+    return LS::eval(ctx, x) < 0.0;
+  }
+}
+
+// Count loop of one work item for a static plan, software-pipelined: the Philox
+// words of the NEXT pair are generated while the current pair goes through the
+// fp64 transforms and the limit state. The integer stream (ALU / IMAD.WIDE) and
+// the fp64 stream then sit in the same basic block and ptxas interleaves them;
+// without this, warps convoy through an all-integer phase and an all-fp64 phase
+// and the two pipes never overlap (profiles/r01_b_*, tools/microbench).
+// CHECK = the item touches the [first, last) boundary and samples must be masked.
+template <class LS, class Plan, bool CHECK>
+__device__ __forceinline__ unsigned static_count_loop(const typename LS::Ctx& ctx,
+                                                      const DevInput* r_plan, PairCtr pc,
+                                                      int64_t q_begin, int64_t q_end, int tid,
+                                                      const McParams& p, const FastMathSmem& sm) {
+  constexpr int XCAP = LS::XCAP;
+  constexpr int NC = static_calls<Plan>() > 0 ? static_calls<Plan>() : 1;
+  unsigned cnt = 0;
+  int64_t q = q_begin + tid;
+  Philox4 nxt[NC];
+  static_gen<Plan>(nxt, (uint32_t)q, (uint32_t)((uint64_t)q >> 32), pc);
+  for (; q < q_end; q += kThreads) {
+    Philox4 cur[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) cur[c] = nxt[c];
+    const int64_t qn = q + kThreads;  // prefetch (one surplus generation per item and thread)
+    static_gen<Plan>(nxt, (uint32_t)qn, (uint32_t)((uint64_t)qn >> 32), pc);
+    pc.qlo = (uint32_t)q;
+    pc.qhi = (uint32_t)((uint64_t)q >> 32);
+    double x0[XCAP], x1[XCAP];
+    DrawAll<Plan, XCAP, 0>::run(r_plan, cur, pc, p.tables, sm, x0, x1);
+    const unsigned f0 = sample_fails<LS>(ctx, x0) ? 1u : 0u;
+    const unsigned f1 = sample_fails<LS>(ctx, x1) ? 1u : 0u;
+    if (CHECK) {
+      const int64_t i0 = q << 1;
+      cnt += ((i0 >= p.first) ? f0 : 0u) + (((i0 + 1) < p.last) ? f1 : 0u);
+    } else {
+      cnt += f0 + f1;
+    }
+  }
+  return cnt;
 }
 
 __device__ __forceinline__ int find_bin(const double* edges, int nedges, double y) {
@@ -80,8 +169,9 @@ __device__ __forceinline__ int find_bin(const double* edges, int nedges, double 
 
 // MODE 0: failure count. MODE 1: histogram + moments of the output.
 template <class LS, class Plan, int MODE>
-__global__ void __launch_bounds__(kThreads, 2) mc_kernel(const McParams p) {
+__global__ void __launch_bounds__(kThreads, EBN_MIN_BLOCKS) mc_kernel(const McParams p) {
   constexpr int XCAP = LS::XCAP;
+  __shared__ FastMathSmem s_fm;
   __shared__ DevInput s_plan[EBN_MAX_INPUTS];
   __shared__ double s_chol[std::is_same<Plan, CopulaPlan>::value ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
   __shared__ unsigned int s_red[kWarps];
@@ -94,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, 2) mc_kernel(const McParams p) {
   LS::setup(ctx, p.consts, p.n_consts, p.d);
 
   const int tid = threadIdx.x;
+  fastmath_init(s_fm, tid, kThreads);
   if (MODE == 1) {
     for (int i = tid; i < p.nedges; i += kThreads) s_edges[i] = p.edges[i];
   }
@@ -124,21 +215,36 @@ __global__ void __launch_bounds__(kThreads, 2) mc_kernel(const McParams p) {
     const int64_t q_last = (p.last + 1) >> 1;  // one past the last pair
     if (q_end > q_last) q_end = q_last;
 
+    // a static plan keeps the scenario's recipe in registers for the whole item
+    DevInput r_plan[Plan::is_static ? XCAP : 1];
+    if constexpr (Plan::is_static) {
+#pragma unroll
+      for (int j = 0; j < XCAP; ++j) r_plan[j] = s_plan[j];
+    }
+    const DevInput* plan_ptr = Plan::is_static ? r_plan : s_plan;
+
     unsigned int cnt = 0;
     double sum = 0.0, sumsq = 0.0;
+    if constexpr (Plan::is_static && MODE == 0) {
+      const bool interior = (q_begin << 1) >= p.first && (q_end << 1) <= p.last;
+      cnt = interior ? static_count_loop<LS, Plan, false>(ctx, r_plan, pc, q_begin, q_end, tid, p, s_fm)
+                     : static_count_loop<LS, Plan, true>(ctx, r_plan, pc, q_begin, q_end, tid, p, s_fm);
+    } else
     for (int64_t q = q_begin + tid; q < q_end; q += kThreads) {
       pc.qlo = (uint32_t)q;
       pc.qhi = (uint32_t)((uint64_t)q >> 32);
       double x0[XCAP], x1[XCAP];
-      draw_inputs<Plan, XCAP>(s_plan, s_chol, p.d, pc, p.tables, x0, x1);
-      const double g0 = LS::eval(ctx, x0);
-      const double g1 = LS::eval(ctx, x1);
+      draw_inputs<Plan, XCAP>(plan_ptr, s_chol, p.d, pc, p.tables, s_fm, x0, x1);
       const int64_t i0 = q << 1;
       const bool v0 = i0 >= p.first;           // i0 < last holds by construction
       const bool v1 = (i0 + 1) < p.last;       // i0+1 >= first holds by construction
       if (MODE == 0) {
-        cnt += (unsigned)(v0 && g0 < 0.0) + (unsigned)(v1 && g1 < 0.0);
+        const bool f0 = sample_fails<LS>(ctx, x0);
+        const bool f1 = sample_fails<LS>(ctx, x1);
+        cnt += (unsigned)(v0 && f0) + (unsigned)(v1 && f1);
       } else {
+        const double g0 = LS::eval(ctx, x0);
+        const double g1 = LS::eval(ctx, x1);
         if (v0) {
           atomicAdd(&s_bins[find_bin(s_edges, p.nedges, g0)], 1u);
           if (g0 == g0) { sum += g0; sumsq = fma(g0, g0, sumsq); }
@@ -197,10 +303,12 @@ template <class LS, class Plan>
 __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int scenario,
                                                           int64_t n, double* X, double* g_out) {
   constexpr int XCAP = LS::XCAP;
+  __shared__ FastMathSmem s_fm;
   __shared__ DevInput s_plan[EBN_MAX_INPUTS];
   __shared__ double s_chol[std::is_same<Plan, CopulaPlan>::value ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
   typename LS::Ctx ctx;
   LS::setup(ctx, p.consts, p.n_consts, p.d);
+  fastmath_init(s_fm, threadIdx.x, kThreads);
   if (threadIdx.x < p.d) s_plan[threadIdx.x] = p.plan[(int64_t)scenario * p.d + threadIdx.x];
   if (std::is_same<Plan, CopulaPlan>::value) {
     const double* L = p.chol + (p.chol_shared ? 0 : (int64_t)scenario * p.d * p.d);
@@ -217,7 +325,7 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
     pc.qlo = (uint32_t)q;
     pc.qhi = (uint32_t)((uint64_t)q >> 32);
     double x0[XCAP], x1[XCAP];
-    draw_inputs<Plan, XCAP>(s_plan, s_chol, p.d, pc, p.tables, x0, x1);
+    draw_inputs<Plan, XCAP>(s_plan, s_chol, p.d, pc, p.tables, s_fm, x0, x1);
     const int64_t i0 = q << 1;
     double y0[XCAP], y1[XCAP];
 #pragma unroll

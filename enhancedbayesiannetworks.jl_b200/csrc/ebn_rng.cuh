@@ -1,11 +1,8 @@
 // Counter-based RNG and uniform/normal primitives (device side).
 //
-// Stream layout v1 (DESIGN.md "Random streams"):
-//   key     = (seed lo32, seed hi32)
-//   counter = (pair lo32, pair hi32, stream id of the scenario, slot)
-//   pair    = global sample index >> 1   (two samples share one Philox call)
-//   slot    = input index j  (+ 16*(1+2*attempt+e) for Gamma attempts)
-//   A = w1:w0, B = w3:w2;  U(x) = ((x >> 12) + 0.5) * 2^-52  in (0,1)
+// key = (seed lo32, seed hi32); counter = (pair lo32, pair hi32, stream id of the
+// scenario, call index); pair = global sample index >> 1. How the words are
+// consumed is defined in ebn_sampling.cuh (stream layout v2).
 // The replacement for `rand(dist, n)` inside UQ.jl's `sample(inputs, n)`
 // (called from reference src/networks/ebn/evaluation/evaluate_node.jl:24,83).
 #pragma once
@@ -38,29 +35,6 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     k1 += W1;
   }
   return Philox4{c0, c1, c2, c3};
-}
-
-// 52 random bits -> (0,1), never 0 or 1: ((x>>12)+0.5)*2^-52. The subtraction is
-// exact (result has <= 53 significant bits), so this is bit-reproducible anywhere.
-__device__ __forceinline__ double u52(uint32_t lo, uint32_t hi) {
-  const uint32_t mlo = (lo >> 12) | (hi << 20);
-  const uint32_t mhi = (hi >> 12) | 0x3FF00000u;
-  const double d = __hiloint2double((int)mhi, (int)mlo);  // [1,2)
-  return d - 0x1.fffffffffffffp-1;  // 1 - 2^-53
-}
-
-// 32 random bits -> (0,1): (w+0.5)*2^-32
-__device__ __forceinline__ double u32(uint32_t w) {
-  return ((double)w + 0.5) * 2.3283064365386962890625e-10;
-}
-
-// Box-Muller: two independent N(0,1) from two uniforms in (0,1).
-__device__ __forceinline__ void box_muller(double ua, double ub, double& z0, double& z1) {
-  const double r = sqrt(-2.0 * log(ua));
-  double s, c;
-  sincospi(2.0 * ub, &s, &c);
-  z0 = r * c;
-  z1 = r * s;
 }
 
 }  // namespace ebn

@@ -1,10 +1,25 @@
-// In-register marginal transforms: one Philox call per (input, sample pair).
+// In-register marginal transforms over a packed Philox word stream.
 // Replaces `rand(dist, n)` per input inside UQ.jl's `sample(inputs, sim)`
 // (reference call sites src/networks/ebn/evaluation/evaluate_node.jl:24,83;
 // the marginals that reach it are listed in SURVEY.md F7 / rows 2 and 5).
+//
+// Random streams, layout v2: for scenario stream s and sample pair
+// q = sample index >> 1 the word stream is
+//     W[4c .. 4c+3] = Philox4x32-10(counter = (q lo, q hi, s, c), key = seed)
+// and the inputs consume words in input order:
+//     Parameter                         0 words
+//     Uniform                           2 words  (one 32-bit uniform per sample)
+//     untruncated Normal / LogNormal    3 words  (Box-Muller across the pair:
+//                                       52-bit radius, 32-bit angle, 2 sign bits)
+// Bit placement: U52(lo, hi) = ((hi & 0xfffff) * 2^32 + lo + 0.5) * 2^-52,
+//                U32(w) = (rotl(w, 12) + 0.5) * 2^-32.
+//     inverse-CDF marginals             4 words  (one 52-bit uniform per sample)
+//     Gamma (Marsaglia-Tsang)           0 words  (own counters, see gamma_mt)
+// Under a Gaussian copula every random input takes 3 words (its Box-Muller pair).
 #pragma once
 #include "../../include/ebncuda.h"
 #include "ebn_device.cuh"
+#include "ebn_fastmath.cuh"
 #include "ebn_rng.cuh"
 
 namespace ebn {
@@ -15,38 +30,85 @@ struct PairCtr {
   uint32_t k0, k1;    // key
 };
 
+// 52-bit uniform in (0,1) from two words: mantissa = (hi & 0xfffff) : lo.
+__device__ __forceinline__ double u52w(uint32_t lo, uint32_t hi) {
+  return __hiloint2double((int)((hi & 0x000FFFFFu) | 0x3FF00000u), (int)lo) - 0x1.fffffffffffffp-1;
+}
+// 32-bit uniform in (0,1): (rot(w) + 0.5) * 2^-32 with rot(w) = w rotated left by 12 (a
+// bijection of the 32-bit word, so still exactly uniform); masks only, no conversion.
+__device__ __forceinline__ double u32w(uint32_t w) {
+  return __hiloint2double((int)((w & 0x000FFFFFu) | 0x3FF00000u), (int)(w & 0xFFF00000u)) - (1.0 - 0x1p-33);
+}
+
+// Word sources -----------------------------------------------------------------
+// Static: all Philox calls of the pair are made up front, words are picked with
+// compile-time indices (registers only).
+template <int OFF>
+struct StaticWords {
+  const Philox4* ph;
+  template <int K>
+  __device__ __forceinline__ uint32_t w() const {
+    constexpr int W = OFF + K;
+    const Philox4& p = ph[W >> 2];
+    return (W & 3) == 0 ? p.w0 : (W & 3) == 1 ? p.w1 : (W & 3) == 2 ? p.w2 : p.w3;
+  }
+};
+// Dynamic: runtime offset, one cached call (inputs walk the stream in order).
+struct DynWords {
+  const PairCtr* pc;
+  Philox4* cache;
+  int* cached_call;
+  int off;
+  __device__ __forceinline__ uint32_t at(int k) const {
+    const int W = off + k;
+    const int c = W >> 2;
+    if (c != *cached_call) {
+      *cache = philox4x32_10(pc->qlo, pc->qhi, pc->stream, (uint32_t)c, pc->k0, pc->k1);
+      *cached_call = c;
+    }
+    const int r = W & 3;
+    return r == 0 ? cache->w0 : r == 1 ? cache->w1 : r == 2 ? cache->w2 : cache->w3;
+  }
+  template <int K>
+  __device__ __forceinline__ uint32_t w() const { return at(K); }
+};
+
 // Marsaglia & Tsang (2000) for shape >= 1 (shape < 1 boosted by u^(1/shape)),
-// the same algorithm class Distributions.jl's Gamma sampler uses. Attempt t of
-// sample e in the pair reads counter slot j + 16*(1 + 2*t + e): radius from
-// w1:w0 (52 bits), angle from w2, acceptance uniform from w3.
+// the algorithm class Distributions.jl's Gamma sampler uses. Attempt t of sample
+// e of input j reads its own Philox call, counter word 3 =
+// 0x80000000 | j<<16 | e<<15 | t: normal from (w0,w1,w2) (first Box-Muller
+// output), acceptance uniform from w3. The boost uniform is call t = 0x7fff.
 static __device__ __noinline__ double gamma_mt(const DevInput& in, const PairCtr& pc, uint32_t j,
-                                        int e, double uboost) {
+                                               uint32_t e, const FastMathSmem& sm) {
   const double shape = in.a;
   const double a = shape < 1.0 ? shape + 1.0 : shape;
   const double dd = a - 1.0 / 3.0;
   const double cc = 1.0 / sqrt(9.0 * dd);
+  const uint32_t base = 0x80000000u | (j << 16) | (e << 15);
   double v = 1.0;
   for (uint32_t t = 0; t < 64u; ++t) {
-    const Philox4 w =
-        philox4x32_10(pc.qlo, pc.qhi, pc.stream, j + 16u * (1u + 2u * t + (uint32_t)e), pc.k0, pc.k1);
-    const double r = sqrt(-2.0 * log(u52(w.w0, w.w1)));
-    const double z = r * cospi(2.0 * u32(w.w2));
+    const Philox4 w = philox4x32_10(pc.qlo, pc.qhi, pc.stream, base | t, pc.k0, pc.k1);
+    double z, z_unused;
+    box_muller_words(w.w0, w.w1, w.w2, sm, z, z_unused);
     const double t1 = 1.0 + cc * z;
     if (t1 <= 0.0) continue;
     v = t1 * t1 * t1;
-    const double u = u32(w.w3);
+    const double u = u32w(w.w3);
     const double z2 = z * z;
     if (u < 1.0 - 0.0331 * z2 * z2) break;
     if (log(u) < 0.5 * z2 + dd * (1.0 - v + log(v))) break;
   }
   double x = dd * v;
-  if (shape < 1.0) x *= pow(uboost, 1.0 / shape);
+  if (shape < 1.0) {
+    const Philox4 w = philox4x32_10(pc.qlo, pc.qhi, pc.stream, base | 0x7FFFu, pc.k0, pc.k1);
+    x *= pow(u52w(w.w0, w.w1), 1.0 / shape);
+  }
   return x * in.b;
 }
 
 __device__ __forceinline__ double table_quantile(const DevInput& in, const double* tables,
                                                  double u) {
-  const double* q = tables + in.off;
+  const double* q = tables + in.toff;
   const double pos = u * (double)(in.npts - 1);
   int i = (int)pos;
   i = i < 0 ? 0 : (i > in.npts - 2 ? in.npts - 2 : i);
@@ -55,82 +117,92 @@ __device__ __forceinline__ double table_quantile(const DevInput& in, const doubl
   return q0 + f * (q1 - q0);
 }
 
-// Draws input j for both samples of a pair. KIND is a DevKind.
+// x = Q(u') for the inverse-CDF kinds, u' = c + u*d already mapped into the
+// truncation window.
 template <int KIND>
-__device__ __forceinline__ void draw_pair(const DevInput& in, const PairCtr& pc, uint32_t j,
-                                          const double* tables, double& x0, double& x1) {
+__device__ __forceinline__ double icdf(const DevInput& in, const double* tables, double u) {
+  const double up = fma(u, in.d, in.c);
+  if (KIND == DK_NORMAL_ICDF) return fma(normcdfinv(up), in.b, in.a);
+  if (KIND == DK_LOGNORMAL_ICDF) return exp(fma(normcdfinv(up), in.b, in.a));
+  if (KIND == DK_GUMBEL) return in.a - in.b * log(-log(up));
+  if (KIND == DK_EXP_AFFINE) return in.a - in.b * log1p(-up);
+  return table_quantile(in, tables, up);
+}
+
+// Draws input j for both samples of a pair. KIND is a DevKind, WS a word source
+// positioned at the input's first word.
+template <int KIND, class WS>
+__device__ __forceinline__ void draw_pair(const DevInput& in, const WS& ws, const PairCtr& pc,
+                                          uint32_t j, const double* tables,
+                                          const FastMathSmem& sm, double& x0, double& x1) {
   if (KIND == DK_CONST) {
     x0 = in.a;
     x1 = in.a;
-    return;
-  }
-  const Philox4 w = philox4x32_10(pc.qlo, pc.qhi, pc.stream, j, pc.k0, pc.k1);
-  const double ua = u52(w.w0, w.w1);
-  const double ub = u52(w.w2, w.w3);
-  if (KIND == DK_UNIFORM) {
-    x0 = fma(ua, in.b, in.a);
-    x1 = fma(ub, in.b, in.a);
+  } else if (KIND == DK_UNIFORM) {
+    x0 = fma(u32w(ws.template w<0>()), in.b, in.a);
+    x1 = fma(u32w(ws.template w<1>()), in.b, in.a);
   } else if (KIND == DK_NORMAL_BM || KIND == DK_LOGNORMAL_BM) {
     double z0, z1;
-    box_muller(ua, ub, z0, z1);
+    box_muller_words(ws.template w<0>(), ws.template w<1>(), ws.template w<2>(), sm, z0, z1);
     x0 = fma(z0, in.b, in.a);
     x1 = fma(z1, in.b, in.a);
     if (KIND == DK_LOGNORMAL_BM) {
       x0 = exp(x0);
       x1 = exp(x1);
     }
-  } else if (KIND == DK_NORMAL_ICDF || KIND == DK_LOGNORMAL_ICDF) {
-    x0 = fma(normcdfinv(fma(ua, in.d, in.c)), in.b, in.a);
-    x1 = fma(normcdfinv(fma(ub, in.d, in.c)), in.b, in.a);
-    if (KIND == DK_LOGNORMAL_ICDF) {
-      x0 = exp(x0);
-      x1 = exp(x1);
-    }
-  } else if (KIND == DK_GUMBEL) {
-    x0 = in.a - in.b * log(-log(fma(ua, in.d, in.c)));
-    x1 = in.a - in.b * log(-log(fma(ub, in.d, in.c)));
-  } else if (KIND == DK_EXP_AFFINE) {
-    x0 = in.a - in.b * log1p(-fma(ua, in.d, in.c));
-    x1 = in.a - in.b * log1p(-fma(ub, in.d, in.c));
   } else if (KIND == DK_GAMMA_MT) {
-    x0 = gamma_mt(in, pc, j, 0, ua);
-    x1 = gamma_mt(in, pc, j, 1, ub);
-  } else if (KIND == DK_TABLE) {
-    x0 = table_quantile(in, tables, fma(ua, in.d, in.c));
-    x1 = table_quantile(in, tables, fma(ub, in.d, in.c));
+    x0 = gamma_mt(in, pc, j, 0u, sm);
+    x1 = gamma_mt(in, pc, j, 1u, sm);
+  } else {
+    x0 = icdf<KIND>(in, tables, u52w(ws.template w<0>(), ws.template w<1>()));
+    x1 = icdf<KIND>(in, tables, u52w(ws.template w<2>(), ws.template w<3>()));
   }
 }
 
-// Runtime (warp-uniform) dispatch on the kind.
-static __device__ __noinline__ void draw_pair_dyn(const DevInput& in, const PairCtr& pc, uint32_t j,
-                                              const double* tables, double& x0, double& x1) {
+// Runtime (warp-uniform) dispatch on the kind; the generic, slower path.
+static __device__ __noinline__ void draw_pair_dyn(const DevInput& in, const PairCtr& pc,
+                                                  Philox4& cache, int& cached_call, uint32_t j,
+                                                  const double* tables, const FastMathSmem& sm,
+                                                  double& x0, double& x1) {
+  DynWords ws{&pc, &cache, &cached_call, in.woff};
   switch (in.kind) {
-    case DK_CONST: draw_pair<DK_CONST>(in, pc, j, tables, x0, x1); break;
-    case DK_UNIFORM: draw_pair<DK_UNIFORM>(in, pc, j, tables, x0, x1); break;
-    case DK_NORMAL_BM: draw_pair<DK_NORMAL_BM>(in, pc, j, tables, x0, x1); break;
-    case DK_LOGNORMAL_BM: draw_pair<DK_LOGNORMAL_BM>(in, pc, j, tables, x0, x1); break;
-    case DK_NORMAL_ICDF: draw_pair<DK_NORMAL_ICDF>(in, pc, j, tables, x0, x1); break;
-    case DK_LOGNORMAL_ICDF: draw_pair<DK_LOGNORMAL_ICDF>(in, pc, j, tables, x0, x1); break;
-    case DK_GUMBEL: draw_pair<DK_GUMBEL>(in, pc, j, tables, x0, x1); break;
-    case DK_EXP_AFFINE: draw_pair<DK_EXP_AFFINE>(in, pc, j, tables, x0, x1); break;
-    case DK_GAMMA_MT: draw_pair<DK_GAMMA_MT>(in, pc, j, tables, x0, x1); break;
-    default: draw_pair<DK_TABLE>(in, pc, j, tables, x0, x1); break;
+    case DK_CONST: draw_pair<DK_CONST>(in, ws, pc, j, tables, sm, x0, x1); break;
+    case DK_UNIFORM: draw_pair<DK_UNIFORM>(in, ws, pc, j, tables, sm, x0, x1); break;
+    case DK_NORMAL_BM: draw_pair<DK_NORMAL_BM>(in, ws, pc, j, tables, sm, x0, x1); break;
+    case DK_LOGNORMAL_BM: draw_pair<DK_LOGNORMAL_BM>(in, ws, pc, j, tables, sm, x0, x1); break;
+    case DK_NORMAL_ICDF: draw_pair<DK_NORMAL_ICDF>(in, ws, pc, j, tables, sm, x0, x1); break;
+    case DK_LOGNORMAL_ICDF: draw_pair<DK_LOGNORMAL_ICDF>(in, ws, pc, j, tables, sm, x0, x1); break;
+    case DK_GUMBEL: draw_pair<DK_GUMBEL>(in, ws, pc, j, tables, sm, x0, x1); break;
+    case DK_EXP_AFFINE: draw_pair<DK_EXP_AFFINE>(in, ws, pc, j, tables, sm, x0, x1); break;
+    case DK_GAMMA_MT: draw_pair<DK_GAMMA_MT>(in, ws, pc, j, tables, sm, x0, x1); break;
+    default: draw_pair<DK_TABLE>(in, ws, pc, j, tables, sm, x0, x1); break;
   }
+}
+
+// Phi(z) clamped away from 0 and 1 so that the quantile functions stay finite.
+__device__ __forceinline__ double phi_clamped(double z) {
+  const double p = normcdf(z);
+  return fmin(fmax(p, 0x1p-60), 0x1.fffffffffffffp-1);
 }
 
 // Gaussian copula (UQ.jl JointDistribution + GaussianCopula): eps ~ N(0,I) by
-// Box-Muller, z = L*eps, then per marginal x = a + b*z for the normal family
-// and x = Q(Phi(z)) otherwise. L is row-major lower-triangular [d*d].
+// Box-Muller (3 words per random input, in.woff), z = L*eps, then per marginal
+// x = a + b*z for the normal family and x = Q(Phi(z)) otherwise. L is row-major
+// lower-triangular [d*d].
 static __device__ __noinline__ void draw_pair_copula(const DevInput* plan, const double* L, int d,
-                                                 const PairCtr& pc, const double* tables,
-                                                 double* x0, double* x1) {
+                                                     const PairCtr& pc, const double* tables,
+                                                     const FastMathSmem& sm, double* x0,
+                                                     double* x1) {
   double e0[EBN_MAX_INPUTS], e1[EBN_MAX_INPUTS];
+  Philox4 cache;
+  int cached_call = -1;
   for (int j = 0; j < d; ++j) {
     e0[j] = 0.0;
     e1[j] = 0.0;
     if (plan[j].kind != DK_CONST) {
-      const Philox4 w = philox4x32_10(pc.qlo, pc.qhi, pc.stream, (uint32_t)j, pc.k0, pc.k1);
-      box_muller(u52(w.w0, w.w1), u52(w.w2, w.w3), e0[j], e1[j]);
+      DynWords ws{&pc, &cache, &cached_call, plan[j].woff};
+      const uint32_t a = ws.at(0), b = ws.at(1), c = ws.at(2);
+      box_muller_words(a, b, c, sm, e0[j], e1[j]);
     }
   }
   for (int j = 0; j < d; ++j) {
@@ -149,39 +221,36 @@ static __device__ __noinline__ void draw_pair_copula(const DevInput* plan, const
     double a0, a1;
     switch (in.kind) {
       case DK_NORMAL_BM:
-      case DK_NORMAL_ICDF:
-        // (a truncated normal under a copula goes through Phi like the others)
-        if (in.kind == DK_NORMAL_BM) {
-          a0 = fma(z0, in.b, in.a);
-          a1 = fma(z1, in.b, in.a);
-        } else {
-          a0 = fma(normcdfinv(fma(normcdf(z0), in.d, in.c)), in.b, in.a);
-          a1 = fma(normcdfinv(fma(normcdf(z1), in.d, in.c)), in.b, in.a);
-        }
+        a0 = fma(z0, in.b, in.a);
+        a1 = fma(z1, in.b, in.a);
         break;
       case DK_LOGNORMAL_BM:
         a0 = exp(fma(z0, in.b, in.a));
         a1 = exp(fma(z1, in.b, in.a));
         break;
-      case DK_LOGNORMAL_ICDF:
-        a0 = exp(fma(normcdfinv(fma(normcdf(z0), in.d, in.c)), in.b, in.a));
-        a1 = exp(fma(normcdfinv(fma(normcdf(z1), in.d, in.c)), in.b, in.a));
-        break;
       case DK_UNIFORM:
-        a0 = fma(normcdf(z0), in.b, in.a);
-        a1 = fma(normcdf(z1), in.b, in.a);
+        a0 = fma(phi_clamped(z0), in.b, in.a);
+        a1 = fma(phi_clamped(z1), in.b, in.a);
+        break;
+      case DK_NORMAL_ICDF:
+        a0 = icdf<DK_NORMAL_ICDF>(in, tables, phi_clamped(z0));
+        a1 = icdf<DK_NORMAL_ICDF>(in, tables, phi_clamped(z1));
+        break;
+      case DK_LOGNORMAL_ICDF:
+        a0 = icdf<DK_LOGNORMAL_ICDF>(in, tables, phi_clamped(z0));
+        a1 = icdf<DK_LOGNORMAL_ICDF>(in, tables, phi_clamped(z1));
         break;
       case DK_GUMBEL:
-        a0 = in.a - in.b * log(-log(fma(normcdf(z0), in.d, in.c)));
-        a1 = in.a - in.b * log(-log(fma(normcdf(z1), in.d, in.c)));
+        a0 = icdf<DK_GUMBEL>(in, tables, phi_clamped(z0));
+        a1 = icdf<DK_GUMBEL>(in, tables, phi_clamped(z1));
         break;
       case DK_EXP_AFFINE:
-        a0 = in.a - in.b * log1p(-fma(normcdf(z0), in.d, in.c));
-        a1 = in.a - in.b * log1p(-fma(normcdf(z1), in.d, in.c));
+        a0 = icdf<DK_EXP_AFFINE>(in, tables, phi_clamped(z0));
+        a1 = icdf<DK_EXP_AFFINE>(in, tables, phi_clamped(z1));
         break;
-      default:  // DK_TABLE (Gamma under a copula is tabulated by the host)
-        a0 = table_quantile(in, tables, fma(normcdf(z0), in.d, in.c));
-        a1 = table_quantile(in, tables, fma(normcdf(z1), in.d, in.c));
+      default:  // DK_TABLE (Gamma under a copula is tabulated by the caller)
+        a0 = icdf<DK_TABLE>(in, tables, phi_clamped(z0));
+        a1 = icdf<DK_TABLE>(in, tables, phi_clamped(z1));
         break;
     }
     x0[j] = a0;

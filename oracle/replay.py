@@ -1,21 +1,27 @@
 """NumPy twin of the device sampler (test infrastructure, see oracle/__init__.py).
 
 Restates, independently of the CUDA sources, the stream layout of DESIGN.md
-("Random streams, layout v1") so that the uniforms the GPU consumed can be
+("Random streams, layout v2") so that the uniforms the GPU consumed can be
 regenerated on the CPU:
 
     key     = (seed & 0xffffffff, seed >> 32)
-    counter = (pair & 0xffffffff, pair >> 32, stream id of the scenario, slot)
-    pair    = global sample index >> 1,   slot = input index j
-    (w0,w1,w2,w3) = Philox4x32-10(counter, key)
-    A = w1:w0, B = w3:w2,  U(x) = ((x >> 12) + 0.5) * 2**-52
+    pair    = global sample index >> 1
+    W[4c .. 4c+3] = Philox4x32-10(counter = (pair lo, pair hi, stream id, c), key)
 
-    inverse-CDF marginals : sample 2q uses U(A), sample 2q+1 uses U(B)
-    untruncated (log)normal: r = sqrt(-2 ln U(A)), t = 2*pi*U(B);
-                             z(2q) = r cos t, z(2q+1) = r sin t      (Box-Muller)
-    Gamma (Marsaglia-Tsang): attempt t of sample e reads slot j + 16*(1+2t+e):
-                             radius U(w1:w0), angle (w2+0.5)*2**-32 (cos branch),
-                             acceptance uniform (w3+0.5)*2**-32
+    inputs consume words of W in input order:
+      Parameter 0 | Uniform 2 | untruncated Normal/LogNormal 3 | Gamma 0 | other marginals 4
+    U52(lo, hi) = ((((hi & 0xfffff) << 32) | lo) + 0.5) * 2**-52    U32(w) = (rotl(w, 12) + 0.5) * 2**-32
+
+    Uniform            : sample 2q uses U32(W[o]), sample 2q+1 uses U32(W[o+1])
+    inverse-CDF kinds  : sample 2q uses U52(W[o], W[o+1]), sample 2q+1 uses U52(W[o+2], W[o+3])
+    (Log)Normal        : Box-Muller across the pair: R = sqrt(-2 ln U52(W[o], W[o+1])),
+                         phi = (pi/2) * U32(W[o+2]);  z(2q) = s0 R sin(phi), z(2q+1) = s1 R cos(phi),
+                         s0 = -1 if W[o+1] bit 31, s1 = -1 if W[o+1] bit 30
+    Gamma (Marsaglia-Tsang): attempt t of sample e of input j is the Philox call with counter
+                         word 3 = 0x80000000 | j << 16 | e << 15 | t: normal = first Box-Muller
+                         output of (w0, w1, w2), acceptance uniform U32(w3); the shape < 1 boost
+                         uniform is U52(w0, w1) of call t = 0x7fff
+    Gaussian copula    : every random input takes 3 words (its Box-Muller pair), z = L eps
 
 Philox4x32-10 itself is pinned by the Random123 known-answer vectors in
 tests/test_oracle.py.
@@ -56,31 +62,65 @@ def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
 
 
 def _u52(lo, hi):
-    x = (hi << np.uint64(32)) | lo
-    return ((x >> np.uint64(12)).astype(np.float64) + 0.5) * 2.0**-52
+    x = ((hi & np.uint64(0xFFFFF)) << np.uint64(32)) | lo
+    return (x.astype(np.float64) + 0.5) * 2.0**-52
 
 
 def _u32(w):
-    return (w.astype(np.float64) + 0.5) * 2.0**-32
+    rot = ((w << np.uint64(12)) & _MASK) | (w >> np.uint64(20))  # rotate left by 12
+    return (rot.astype(np.float64) + 0.5) * 2.0**-32
 
 
-def _pair_words(pairs, stream: int, slot: int, seed: int):
+def _call(pairs, stream: int, c: int, seed: int):
     pairs = np.asarray(pairs, dtype=np.uint64)
-    return philox4x32_10(pairs & _MASK, pairs >> np.uint64(32), np.uint64(stream), np.uint64(slot),
+    return philox4x32_10(pairs & _MASK, pairs >> np.uint64(32), np.uint64(stream), np.uint64(c),
                          seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
 
 
-def _gamma_mt(pairs, e: int, shape: float, scale: float, stream: int, j: int, seed: int, uboost):
+class _Words:
+    """The word stream W of a set of pairs, calls made on demand."""
+
+    def __init__(self, pairs, stream, seed):
+        self.pairs, self.stream, self.seed, self.calls = pairs, stream, seed, {}
+
+    def __getitem__(self, k: int):
+        c = k >> 2
+        if c not in self.calls:
+            self.calls[c] = _call(self.pairs, self.stream, c, self.seed)
+        return self.calls[c][k & 3]
+
+
+def _box_muller(w0, w1, w2):
+    R = np.sqrt(-2.0 * np.log(_u52(w0, w1)))
+    phi = (np.pi / 2) * _u32(w2)
+    s0 = np.where(w1 & np.uint64(0x80000000), -1.0, 1.0)
+    s1 = np.where(w1 & np.uint64(0x40000000), -1.0, 1.0)
+    return s0 * R * np.sin(phi), s1 * R * np.cos(phi)
+
+
+def words_of(inp) -> int:
+    kind = int(inp["kind"])
+    trunc = np.isfinite(float(inp["lo"])) or np.isfinite(float(inp["hi"]))
+    if kind == IN_PARAM or kind == IN_GAMMA:
+        return 0
+    if kind == IN_UNIFORM:
+        return 2
+    if kind in (IN_NORMAL, IN_LOGNORMAL) and not trunc:
+        return 3
+    return 4
+
+
+def _gamma_mt(pairs, e: int, shape: float, scale: float, stream: int, j: int, seed: int):
     a = shape + 1.0 if shape < 1.0 else shape
     dd = a - 1.0 / 3.0
     cc = 1.0 / np.sqrt(9.0 * dd)
+    base = 0x80000000 | (j << 16) | (e << 15)
     out = np.empty(len(pairs))
     todo = np.arange(len(pairs))
     t = 0
     while len(todo):
-        w0, w1, w2, w3 = _pair_words(pairs[todo], stream, j + 16 * (1 + 2 * t + e), seed)
-        r = np.sqrt(-2.0 * np.log(_u52(w0, w1)))
-        z = r * np.cos(2.0 * np.pi * _u32(w2))
+        w0, w1, w2, w3 = _call(pairs[todo], stream, base | t, seed)
+        z, _ = _box_muller(w0, w1, w2)
         t1 = 1.0 + cc * z
         v = t1 * t1 * t1
         u = _u32(w3)
@@ -92,7 +132,8 @@ def _gamma_mt(pairs, e: int, shape: float, scale: float, stream: int, j: int, se
         t += 1
         assert t < 64
     if shape < 1.0:
-        out = out * uboost ** (1.0 / shape)
+        w0, w1, _, _ = _call(pairs, stream, base | 0x7FFF, seed)
+        out = out * _u52(w0, w1) ** (1.0 / shape)
     return out * scale
 
 
@@ -114,86 +155,93 @@ def _window(inp):
         return Fl, Fh
     if kind == IN_EXP_AFFINE:
         theta, sign, shift = p[0], p[1], p[2]
-        el, eh = 0.0, np.inf
         if sign > 0:
-            el = max(lo - shift, 0.0)
-            eh = hi - shift
+            el, eh = max(lo - shift, 0.0), hi - shift
         else:
-            el = max(shift - hi, 0.0)
-            eh = shift - lo
+            el, eh = max(shift - hi, 0.0), shift - lo
         return -np.expm1(-el / theta), (1.0 if not np.isfinite(eh) else -np.expm1(-eh / theta))
     return 0.0, 1.0
+
+
+def _quantile(inp, u, tables):
+    """x = Q(F(lo) + u (F(hi) - F(lo))) for the inverse-CDF marginals."""
+    kind, p = int(inp["kind"]), inp["p"]
+    Fl, Fh = _window(inp)
+    up = Fl + u * (Fh - Fl)
+    if kind == IN_NORMAL:
+        return p[0] + p[1] * special.ndtri(up)
+    if kind == IN_LOGNORMAL:
+        return np.exp(p[0] + p[1] * special.ndtri(up))
+    if kind == IN_GUMBEL:
+        return p[0] - p[1] * np.log(-np.log(up))
+    if kind == IN_EXP_AFFINE:
+        return p[2] + p[1] * (-p[0] * np.log1p(-up))
+    if kind == IN_TABULATED:
+        off, npts = int(p[0]), int(p[1])
+        q = np.asarray(tables)[off:off + npts]
+        pos = up * (npts - 1)
+        i = np.clip(pos.astype(np.int64), 0, npts - 2)
+        return q[i] + (pos - i) * (q[i + 1] - q[i])
+    raise ValueError(f"unknown marginal kind {kind}")
+
+
+def _pairs_of(first, n):
+    idx = np.arange(first, first + n, dtype=np.uint64)
+    pairs = idx >> np.uint64(1)
+    odd = (idx & np.uint64(1)).astype(bool)
+    upairs, inv = np.unique(pairs, return_inverse=True)
+    return upairs, inv, odd
 
 
 def sample_matrix(inputs_row, stream: int, seed: int, first: int, n: int, tables=None) -> np.ndarray:
     """The n samples [first, first+n) of one scenario, (n, d), as the device draws them."""
     d = len(inputs_row)
-    idx = np.arange(first, first + n, dtype=np.uint64)
-    pairs = idx >> np.uint64(1)
-    odd = (idx & np.uint64(1)).astype(bool)
-    upairs, inv = np.unique(pairs, return_inverse=True)
+    upairs, inv, odd = _pairs_of(first, n)
+    W = _Words(upairs, stream, seed)
     X = np.empty((n, d))
+    off = 0
     for j in range(d):
         inp = inputs_row[j]
         kind, p = int(inp["kind"]), inp["p"]
         lo, hi = float(inp["lo"]), float(inp["hi"])
-        trunc = np.isfinite(lo) or np.isfinite(hi)
+        nw = words_of(inp)
         if kind == IN_PARAM:
             X[:, j] = p[0]
-            continue
-        w0, w1, w2, w3 = _pair_words(upairs, stream, j, seed)
-        ua, ub = _u52(w0, w1), _u52(w2, w3)
-        u = np.where(odd, ub[inv], ua[inv])
-        if kind == IN_UNIFORM:
+        elif kind == IN_UNIFORM:
             a, b = max(p[0], lo), min(p[1], hi)
+            u = np.where(odd, _u32(W[off + 1])[inv], _u32(W[off])[inv])
             X[:, j] = a + u * (b - a)
-        elif kind in (IN_NORMAL, IN_LOGNORMAL):
-            if not trunc:
-                r = np.sqrt(-2.0 * np.log(ua))
-                z = np.where(odd, (r * np.sin(2.0 * np.pi * ub))[inv], (r * np.cos(2.0 * np.pi * ub))[inv])
-            else:
-                Fl, Fh = _window(inp)
-                z = special.ndtri(Fl + u * (Fh - Fl))
-            v = p[0] + p[1] * z
+        elif nw == 3:
+            z0, z1 = _box_muller(W[off], W[off + 1], W[off + 2])
+            v = p[0] + p[1] * np.where(odd, z1[inv], z0[inv])
             X[:, j] = np.exp(v) if kind == IN_LOGNORMAL else v
-        elif kind == IN_GUMBEL:
-            Fl, Fh = _window(inp)
-            X[:, j] = p[0] - p[1] * np.log(-np.log(Fl + u * (Fh - Fl)))
-        elif kind == IN_EXP_AFFINE:
-            Fl, Fh = _window(inp)
-            X[:, j] = p[2] + p[1] * (-p[0] * np.log1p(-(Fl + u * (Fh - Fl))))
         elif kind == IN_GAMMA:
-            assert not trunc
-            g0 = _gamma_mt(upairs, 0, p[0], p[1], stream, j, seed, ua)
-            g1 = _gamma_mt(upairs, 1, p[0], p[1], stream, j, seed, ub)
+            assert not (np.isfinite(lo) or np.isfinite(hi))
+            g0 = _gamma_mt(upairs, 0, p[0], p[1], stream, j, seed)
+            g1 = _gamma_mt(upairs, 1, p[0], p[1], stream, j, seed)
             X[:, j] = np.where(odd, g1[inv], g0[inv])
-        elif kind == IN_TABULATED:
-            off, npts = int(p[0]), int(p[1])
-            q = np.asarray(tables)[off:off + npts]
-            pos = u * (npts - 1)
-            i = np.clip(pos.astype(np.int64), 0, npts - 2)
-            X[:, j] = q[i] + (pos - i) * (q[i + 1] - q[i])
         else:
-            raise ValueError(f"unknown marginal kind {kind}")
+            u = np.where(odd, _u52(W[off + 2], W[off + 3])[inv], _u52(W[off], W[off + 1])[inv])
+            X[:, j] = _quantile(inp, u, tables)
+        off += nw
     return X
 
 
 def copula_sample_matrix(inputs_row, L, stream: int, seed: int, first: int, n: int, tables=None):
-    """Gaussian-copula variant: eps by Box-Muller per input, z = L eps, x = Q(Phi(z))."""
+    """Gaussian-copula variant: eps by Box-Muller per random input (3 words each), z = L eps,
+    x = a + b z for the (log)normal family, x = Q(Phi(z)) otherwise."""
     d = len(inputs_row)
     L = np.asarray(L, dtype=np.float64).reshape(d, d)
-    idx = np.arange(first, first + n, dtype=np.uint64)
-    pairs = idx >> np.uint64(1)
-    odd = (idx & np.uint64(1)).astype(bool)
-    upairs, inv = np.unique(pairs, return_inverse=True)
+    upairs, inv, odd = _pairs_of(first, n)
+    W = _Words(upairs, stream, seed)
     eps = np.zeros((n, d))
+    off = 0
     for j in range(d):
         if int(inputs_row[j]["kind"]) == IN_PARAM:
             continue
-        w0, w1, w2, w3 = _pair_words(upairs, stream, j, seed)
-        ua, ub = _u52(w0, w1), _u52(w2, w3)
-        r = np.sqrt(-2.0 * np.log(ua))
-        eps[:, j] = np.where(odd, (r * np.sin(2.0 * np.pi * ub))[inv], (r * np.cos(2.0 * np.pi * ub))[inv])
+        z0, z1 = _box_muller(W[off], W[off + 1], W[off + 2])
+        eps[:, j] = np.where(odd, z1[inv], z0[inv])
+        off += 3
     Z = eps @ L.T
     X = np.empty((n, d))
     for j in range(d):
@@ -204,29 +252,16 @@ def copula_sample_matrix(inputs_row, L, stream: int, seed: int, first: int, n: i
         z = Z[:, j]
         if kind == IN_PARAM:
             X[:, j] = p[0]
-        elif kind in (IN_NORMAL, IN_LOGNORMAL):
-            if trunc:
-                Fl, Fh = _window(inp)
-                z = special.ndtri(Fl + special.ndtr(z) * (Fh - Fl))
+        elif kind in (IN_NORMAL, IN_LOGNORMAL) and not trunc:
             v = p[0] + p[1] * z
             X[:, j] = np.exp(v) if kind == IN_LOGNORMAL else v
         elif kind == IN_UNIFORM:
             a, b = max(p[0], lo), min(p[1], hi)
             X[:, j] = a + special.ndtr(z) * (b - a)
-        elif kind == IN_GUMBEL:
-            Fl, Fh = _window(inp)
-            X[:, j] = p[0] - p[1] * np.log(-np.log(Fl + special.ndtr(z) * (Fh - Fl)))
-        elif kind == IN_EXP_AFFINE:
-            Fl, Fh = _window(inp)
-            X[:, j] = p[2] + p[1] * (-p[0] * np.log1p(-(Fl + special.ndtr(z) * (Fh - Fl))))
-        elif kind == IN_TABULATED:
-            off, npts = int(p[0]), int(p[1])
-            q = np.asarray(tables)[off:off + npts]
-            pos = special.ndtr(z) * (npts - 1)
-            i = np.clip(pos.astype(np.int64), 0, npts - 2)
-            X[:, j] = q[i] + (pos - i) * (q[i + 1] - q[i])
+        elif kind == IN_GAMMA:
+            raise ValueError("Gamma under a copula must be tabulated")
         else:
-            raise ValueError(f"marginal kind {kind} not supported under a copula")
+            X[:, j] = _quantile(inp, special.ndtr(z), tables)
     return X
 
 
