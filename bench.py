@@ -31,10 +31,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# FP64-pipe instructions per sample of the W1 kernel (DFMA/DMUL/DADD/DSETP warp instructions
-# executed / samples * 32), frozen from ncu `smsp__inst_executed_pipe_fp64` — see DESIGN.md
-# "Roofline" and profiles/. The SURVEY's ceiling for this figure is 339.
-F_ALG_W1 = 170.0
+# FP64-pipe instructions per sample of the W1 kernel: (DFMA 107 + DMUL 32 + DADD 18) warp
+# instructions per sample PAIR executed in the hot loop, from the ncu source page of
+# profiles/r01_c_* (= sm__inst_executed_pipe_fp64), i.e. 78.5 per sample. See DESIGN.md
+# "Roofline". The SURVEY's ceiling for this figure is 339; the first version executed 151.5.
+F_ALG_W1 = 78.5
 METRIC = "limit_state_mc_samples_per_sec"
 UNIT = "samples/s"
 
