@@ -8,7 +8,22 @@ Layout
     _lib.py       ctypes binding of include/ebncuda.h
     workloads.py  the BASELINE.json configurations as C-ABI jobs
     julia/        the `ccall` wrapper a maintainer drops into the reference
+    distributions.py, nodes.py, network.py, uq.py, evaluation.py
+                  host-side mirror of the reference's node / network API for this path
+                  (DiscreteNode, ContinuousNode, functional nodes, EnhancedBayesianNetwork,
+                  evaluate, reduce, dispatch) so the parity tests read like the reference's
 """
 from . import _lib  # noqa: F401
 from ._lib import (EbnError, Job, INPUT_DTYPE, make_inputs, pf_batch, hist_batch, eval_matrix,  # noqa: F401
                    sample_matrix, peak_fp64, last_stats, init, shutdown, device_count)
+from .distributions import (Normal, LogNormal, Uniform, Gumbel, Gamma, Exponential, Truncated, truncated,  # noqa: F401
+                            Tabulated, EmpiricalDistribution, distribution_parameters, Parameter,
+                            RandomVariable, Interval, ProbabilityBox)
+from .nodes import (DiscreteConditionalProbabilityTable, ContinuousConditionalProbabilityTable,  # noqa: F401
+                    ExactDiscretization, ApproximatedDiscretization, UnamedProbabilityBox, DiscreteNode,
+                    ContinuousNode, DiscreteFunctionalNode, ContinuousFunctionalNode, Model, Poly, Catalogue,
+                    CudaMonteCarlo, MonteCarlo, CudaDoubleLoop, DoubleLoop, CudaRandomSlicing, RandomSlicing)
+from .network import (EnhancedBayesianNetwork, BayesianNetwork, CredalNetwork, add_child, order, parents,  # noqa: F401
+                      children, discrete_ancestors)
+from .uq import probability_of_failure, UnsupportedModel  # noqa: F401
+from .evaluation import evaluate, reduce, dispatch  # noqa: F401

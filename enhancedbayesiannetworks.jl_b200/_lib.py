@@ -72,7 +72,7 @@ assert C.sizeof(EbnJob) == 104 and C.sizeof(EbnStats) == 48
 EXPORTS = [
     "ebn_abi_version", "ebn_device_count", "ebn_init", "ebn_shutdown", "ebn_set_stream",
     "ebn_nccl_unique_id", "ebn_comm_init_rank", "ebn_comm_destroy", "ebn_pf_batch",
-    "ebn_hist_batch", "ebn_eval_matrix", "ebn_sample_matrix", "ebn_peak_fp64", "ebn_last_stats",
+    "ebn_hist_batch", "ebn_eval_matrix", "ebn_sample_matrix", "ebn_sample_matrix_ex", "ebn_peak_fp64", "ebn_last_stats",
     "ebn_partition", "ebn_last_error", "ebn_limit_state_id", "ebn_limit_state_name", "ebn_limit_state_arity",
 ]
 
@@ -108,6 +108,7 @@ def load():
     L.ebn_hist_batch.argtypes = [C.POINTER(EbnJob), dp, C.c_int, i64p, dp, dp]
     L.ebn_eval_matrix.argtypes = [C.c_int, dp, C.c_int, dp, C.c_int64, C.c_int, C.c_int64, C.c_int, i64p, dp]
     L.ebn_sample_matrix.argtypes = [C.POINTER(EbnJob), C.c_int, C.c_int64, C.c_int64, dp, dp]
+    L.ebn_sample_matrix_ex.argtypes = [C.POINTER(EbnJob), C.c_int, C.c_int64, C.c_int64, C.c_int, dp, dp]
     L.ebn_peak_fp64.argtypes = [C.c_double, dp]
     L.ebn_partition.argtypes = [C.POINTER(EbnJob), C.c_int, i64p]
     L.ebn_last_stats.argtypes = [C.POINTER(EbnStats)]
@@ -303,13 +304,14 @@ def eval_matrix(limit_state: int, consts, X, strict: bool = True, want_g: bool =
     return (cnt.value, g) if want_g else cnt.value
 
 
-def sample_matrix(job: Job, scenario: int, first: int, n: int, want_g: bool = False):
-    """ebn_sample_matrix → X (n, d) exactly as ebn_pf_batch draws it (and g)."""
+def sample_matrix(job: Job, scenario: int, first: int, n: int, want_g: bool = False, ncols: int = 0):
+    """ebn_sample_matrix(_ex) → X (n, ncols or d) exactly as ebn_pf_batch draws it (and g)."""
     ensure_init()
-    X = np.empty((n, job.d), order="F")
+    ncols = ncols or job.d
+    X = np.empty((n, ncols), order="F")
     g = np.empty(n) if want_g else None
     cj = job.c_struct()
-    _check(load().ebn_sample_matrix(C.byref(cj), scenario, first, n, _dp(X), _dp(g)))
+    _check(load().ebn_sample_matrix_ex(C.byref(cj), scenario, first, n, ncols, _dp(X), _dp(g)))
     return (X, g) if want_g else X
 
 

@@ -805,8 +805,8 @@ int ebn_eval_matrix(int limit_state, const double* consts, int n_consts, const d
   return EBN_OK;
 }
 
-int ebn_sample_matrix(const ebn_job_t* job, int scenario, int64_t first, int64_t n, double* X,
-                      double* g_out) {
+int ebn_sample_matrix_ex(const ebn_job_t* job, int scenario, int64_t first, int64_t n, int ncols,
+                         double* X, double* g_out) {
   int rc = require_ready();
   if (rc) return rc;
   if (!X) return fail(EBN_EINVAL, "X is NULL");
@@ -822,16 +822,29 @@ int ebn_sample_matrix(const ebn_job_t* job, int scenario, int64_t first, int64_t
   mp.last = first + n;
   mp.pair_base = first >> 1;
   const int d = job->n_inputs;
-  if ((rc = dv.mat.ensure((size_t)n * d * sizeof(double)))) return rc;
+  if (ncols < d || ncols > EBN_MAX_INPUTS) return fail(EBN_EINVAL, "ncols %d outside [%d,%d]", ncols, d, EBN_MAX_INPUTS);
+  if (ncols > d) {
+    const int stages = job->limit_state == EBN_LS_POLYNOMIAL ? (int)job->consts[0] : 0;
+    if (ncols > d + stages)
+      return fail(EBN_EINVAL, "ncols %d: the limit state defines only %d model columns after the %d inputs", ncols, stages, d);
+  }
+  mp.ncols = ncols;
+  if ((rc = dv.mat.ensure((size_t)n * ncols * sizeof(double)))) return rc;
   if (g_out && (rc = dv.gout.ensure((size_t)n * sizeof(double)))) return rc;
   int64_t blocks = ((n + 1) / 2 + threads_per_block()) / threads_per_block();
   if (blocks > (int64_t)dv.sms * 8) blocks = (int64_t)dv.sms * 8;
   CU(ls_vtable(job->limit_state)->replay(job->strict ? 1 : 0, P.plan_class, mp, scenario, n,
                    (double*)dv.mat.p, g_out ? (double*)dv.gout.p : nullptr, (int)blocks, dv.st));
-  CU(cudaMemcpyAsync(X, dv.mat.p, (size_t)n * d * sizeof(double), cudaMemcpyDeviceToHost, dv.st));
+  CU(cudaMemcpyAsync(X, dv.mat.p, (size_t)n * ncols * sizeof(double), cudaMemcpyDeviceToHost, dv.st));
   if (g_out) CU(cudaMemcpyAsync(g_out, dv.gout.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, dv.st));
   CU(cudaStreamSynchronize(dv.st));
   return EBN_OK;
+}
+
+int ebn_sample_matrix(const ebn_job_t* job, int scenario, int64_t first, int64_t n, double* X,
+                      double* g_out) {
+  if (!job) return fail(EBN_EINVAL, "job is NULL");
+  return ebn_sample_matrix_ex(job, scenario, first, n, job->n_inputs, X, g_out);
 }
 
 int ebn_peak_fp64(double seconds, double* dfma_per_s) {

@@ -60,6 +60,7 @@ struct McParams {
   int32_t S, d, n_consts, nedges;
   uint32_t k0, k1;
   int32_t chol_shared;
+  int32_t ncols;  // replay: columns written per sample (d inputs + model outputs)
 };
 
 }  // namespace ebn

@@ -336,14 +336,14 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
       const int64_t r = i0 - p.first;
 #pragma unroll
       for (int j = 0; j < XCAP; ++j)
-        if (j < p.d) X[(int64_t)j * n + r] = x0[j];
+        if (j < p.ncols) X[(int64_t)j * n + r] = y0[j];
       if (g_out) g_out[r] = g0;
     }
     if (i0 + 1 < p.last) {
       const int64_t r = i0 + 1 - p.first;
 #pragma unroll
       for (int j = 0; j < XCAP; ++j)
-        if (j < p.d) X[(int64_t)j * n + r] = x1[j];
+        if (j < p.ncols) X[(int64_t)j * n + r] = y1[j];
       if (g_out) g_out[r] = g1;
     }
   }

@@ -1,0 +1,365 @@
+"""`probability_of_failure` and `sample`/`evaluate!` for functional nodes, lowered to ONE C-ABI call
+per node for all its scenarios.
+
+Replaces the three UQ.jl call sites of the reference hot path:
+  src/networks/ebn/evaluation/evaluate_node.jl:83      probability_of_failure(models, performance, inputs, sim)
+  src/networks/ebn/evaluation/evaluate_node.jl:24-26   sample / evaluate! / EmpiricalDistribution
+and the DoubleLoop / RandomSlicing branches at :104-117.
+There is no CPU fallback: a model that is not a `Poly` or a `Catalogue` entry raises.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .distributions import (INF, Interval, NeedsTable, Normal, Parameter, ProbabilityBox, RandomVariable,
+                            Truncated, table_for)
+from .nodes import Catalogue, CudaDoubleLoop, CudaMonteCarlo, CudaRandomSlicing, Model, Poly
+
+VEHICLE_ARGS = ("A", "b₀", "V", "C", "Cₖ", "K")
+HIST_BINS = 2048  # fine grid a ContinuousFunctionalNode's output is histogrammed on
+
+
+class UnsupportedModel(TypeError):
+    """The model chain has no device functor (include/ebncuda.h EBN_LS_*)."""
+
+
+@dataclass
+class Lowered:
+    limit_state: int
+    consts: np.ndarray
+    columns: List[str]          # input names in functor argument order
+    hidden: List[tuple]         # extra ABI rows appended to every scenario (in-model draws)
+    out_columns: List[str]      # names of all columns (inputs + model outputs) for `samples`
+
+
+def _poly_program(stages: List[Poly], columns: List[str], stage_names: List[str]) -> np.ndarray:
+    cols = list(columns)
+    out = [float(len(stages))]
+    for st, name in zip(stages, stage_names):
+        out.append(float(len(st.terms)))
+        for coef, names in st.terms:
+            out.append(coef)
+            out.append(float(len(names)))
+            for nm in names:
+                if nm not in cols:
+                    raise UnsupportedModel(f"model column '{nm}' is not among the inputs/outputs {cols}")
+                out.append(float(cols.index(nm)))
+        cols.append(name)
+    return np.array(out)
+
+
+def lower(models: Sequence[Model], performance, input_names: Sequence[str]) -> Lowered:
+    """Maps a model chain (+ performance) onto a device limit state."""
+    models = list(models)
+    seen, uniq = set(), []
+    for m in models:  # transmission may hand the same model twice (reference quirk, transmission.jl:13)
+        if m.name not in seen:
+            uniq.append(m)
+            seen.add(m.name)
+    models = uniq
+    input_names = list(input_names)
+    if all(isinstance(m.func, Poly) for m in models) and (performance is None or isinstance(performance, (Poly, str))):
+        stages = [m.func for m in models]
+        names = [m.name for m in models]
+        if isinstance(performance, Poly):
+            stages.append(performance)
+            names.append("__performance")
+        elif isinstance(performance, str) and (not models or performance != models[-1].name):
+            stages.append(Poly([(1.0, [performance])]))
+            names.append("__performance")
+        if not stages:
+            raise UnsupportedModel("empty model chain")
+        if len(input_names) + len(stages) > L.EBN_MAX_INPUTS + 1:
+            raise UnsupportedModel("too many columns for the polynomial functor")
+        prog = _poly_program(stages, input_names, names)
+        return Lowered(L.LS_POLYNOMIAL, prog, input_names, [], input_names + [m.name for m in models])
+    cats = [m for m in models if isinstance(m.func, Catalogue)]
+    if len(cats) != len(models):
+        bad = [m.name for m in models if not isinstance(m.func, (Poly, Catalogue))]
+        raise UnsupportedModel(f"models {bad or [m.name for m in models]} have no device functor: use Poly or Catalogue "
+                               "(arbitrary closures cannot run on the GPU and there is no CPU fallback)")
+    last = cats[-1]
+    if isinstance(performance, str) and performance != last.name:
+        raise UnsupportedModel("a Catalogue chain needs `performance = df -> df.<last model>`")
+    if isinstance(performance, Poly):
+        raise UnsupportedModel("a Catalogue chain cannot be followed by a polynomial performance")
+    ls = last.func.limit_state
+    if ls == "straub_frame":
+        caps = cats[:-1]
+        if len(caps) != 5 or any(c.func.limit_state != "straub_capacity" for c in caps):
+            raise UnsupportedModel("straub_frame expects the five straub_capacity models r1..r5 before it")
+        consts = np.array(caps[0].func.consts)
+        ur = caps[0].func.args[0]
+        order = [ur] + [a for a in last.func.args if a not in [c.name for c in caps]]
+        hidden = [Normal(0.0, 1.0).abi()] * 5
+        cols = order
+    elif ls == "straub_capacity":
+        raise UnsupportedModel("straub_capacity models are only supported fused into straub_frame")
+    else:
+        consts = np.array(last.func.consts)
+        if len(cats) != 1:
+            raise UnsupportedModel(f"limit state '{ls}' is a single-model functor")
+        cols = list(last.func.args) or list(input_names)
+        hidden = []
+    missing = [c for c in cols if c not in input_names]
+    if missing:
+        raise UnsupportedModel(f"limit state '{ls}' needs inputs {missing} which the node's parents do not provide")
+    return Lowered(L.limit_state_id(ls), consts, cols, hidden, cols + [m.name for m in models])
+
+
+class _TablePool:
+    def __init__(self):
+        self.chunks, self.size = [], 0
+
+    def add(self, q: np.ndarray) -> Tuple[int, int]:
+        off = self.size
+        self.chunks.append(np.asarray(q, dtype=float))
+        self.size += len(q)
+        return off, len(q)
+
+    def array(self):
+        return np.concatenate(self.chunks) if self.chunks else None
+
+
+def _abi_row(inp, pool: _TablePool) -> tuple:
+    if isinstance(inp, Parameter):
+        return (L.IN_PARAM, float(inp.value), 0.0, 0.0, 0.0, -INF, INF)
+    if isinstance(inp, RandomVariable):
+        try:
+            return inp.dist.abi()
+        except NeedsTable as nt:
+            off, n = pool.add(table_for(nt.dist, nt.lo, nt.hi))
+            return (L.IN_TABULATED, float(off), float(n), 0.0, 0.0, -INF, INF)
+    raise TypeError(f"input {inp} is imprecise: use DoubleLoop or RandomSlicing")
+
+
+def build_job(low: Lowered, scenario_inputs: Sequence[Sequence], sim: CudaMonteCarlo, stream_id=None) -> L.Job:
+    pool = _TablePool()
+    rows = []
+    for inputs in scenario_inputs:
+        by_name = {}
+        for i in inputs:
+            if i.name in by_name:
+                raise ValueError(f"two inputs named '{i.name}' in one scenario")
+            by_name[i.name] = i
+        rows.append([_abi_row(by_name[c], pool) for c in low.columns] + list(low.hidden))
+    return L.Job(low.limit_state, low.consts, L.make_inputs(rows), int(sim.n), int(sim.seed), bool(sim.strict),
+                 stream_id=stream_id, tables=pool.array())
+
+
+class Samples:
+    """Stands where the reference stores the n-row DataFrame of a scenario
+    (`additional_info[...][:samples]`, evaluate_node.jl:93-95). At 1e8+ samples per scenario the
+    frame cannot be materialised; it is replayed from the counter-based streams on demand."""
+
+    def __init__(self, job: L.Job, scenario: int, columns: List[str]):
+        self.job, self.scenario, self.columns = job, scenario, columns
+        self.shape = (job.n, len(columns))
+
+    def fetch(self, first: int = 0, n: int = 1000) -> Dict[str, np.ndarray]:
+        n = min(n, self.job.n - first)
+        ncols = min(len(self.columns), L.EBN_MAX_INPUTS) if self.job.limit_state == L.LS_POLYNOMIAL else self.job.d
+        X, g = L.sample_matrix(self.job, self.scenario, self.job.sample_offset + first, n, want_g=True, ncols=ncols)
+        out = {c: X[:, j] for j, c in enumerate(self.columns[:X.shape[1]])}
+        out["g"] = g
+        return out
+
+    def __len__(self):
+        return self.job.n
+
+
+def _is_imprecise(i) -> bool:
+    return isinstance(i, (Interval, ProbabilityBox))
+
+
+def pf_scenarios(models, performance, scenario_inputs, sim: CudaMonteCarlo):
+    """All scenarios of a node in one ebn_pf_batch call → (pf[S], std[S], [Samples])."""
+    low = lower(models, performance, [i.name for i in scenario_inputs[0]])
+    job = build_job(low, scenario_inputs, sim)
+    cnt, pf, var = L.pf_batch(job)
+    return pf, np.sqrt(var), [Samples(job, s, low.out_columns) for s in range(job.S)], cnt
+
+
+def probability_of_failure(models, performance, inputs, sim):
+    """UQ.jl signature, one scenario: (pf, std, samples) for Monte Carlo; `Interval`-like (lb, ub)
+    for DoubleLoop; ((lb, ub), info_lb, info_ub) for RandomSlicing."""
+    models = [models] if isinstance(models, Model) else list(models)
+    if isinstance(sim, CudaMonteCarlo):
+        if any(_is_imprecise(i) for i in inputs):
+            raise AssertionError("imprecise inputs need DoubleLoop or RandomSlicing")
+        pf, sd, smp, _ = pf_scenarios(models, performance, [inputs], sim)
+        return float(pf[0]), float(sd[0]), smp[0]
+    if isinstance(sim, CudaDoubleLoop):
+        return double_loop(models, performance, [inputs], sim)[0]
+    if isinstance(sim, CudaRandomSlicing):
+        return random_slicing(models, performance, [inputs], sim)[0]
+    raise TypeError(f"simulation {sim!r} has no device path (MonteCarlo, DoubleLoop and RandomSlicing do)")
+
+
+# ---- imprecise inputs ------------------------------------------------------------------------
+def _imprecise_dims(inputs) -> List[Tuple[int, int, float, float]]:
+    """(input position, parameter position or -1, lb, ub) per free coordinate of the outer loop."""
+    dims = []
+    for pos, i in enumerate(inputs):
+        if isinstance(i, Interval):
+            dims.append((pos, -1, float(i.lb), float(i.ub)))
+        elif isinstance(i, ProbabilityBox):
+            for k, p in enumerate(i.parameters):
+                dims.append((pos, k, float(p.lb), float(p.ub)))
+    return dims
+
+
+def _realise(inputs, dims, x) -> list:
+    """`map_to_precise`: an Interval becomes Parameter(x), a p-box RandomVariable(T(x...))."""
+    out = list(inputs)
+    pbox_vals: Dict[int, Dict[int, float]] = {}
+    for (pos, k, _, _), v in zip(dims, x):
+        if k < 0:
+            out[pos] = Parameter(float(v), inputs[pos].name)
+        else:
+            pbox_vals.setdefault(pos, {})[k] = float(v)
+    for pos, vals in pbox_vals.items():
+        pb = inputs[pos]
+        out[pos] = RandomVariable(pb.member([vals[k] for k in range(len(pb.parameters))]), pb.name)
+    return out
+
+
+def _eval_candidates(models, performance, scenario_inputs, dims_per_s, cands_per_s, sim: CudaMonteCarlo):
+    """pf of every (scenario, candidate) in ONE batch; candidates of a scenario share its Philox
+    stream (common random numbers), so pf is a deterministic function of the candidate."""
+    flat, stream, owner = [], [], []
+    for s, (inputs, dims, cands) in enumerate(zip(scenario_inputs, dims_per_s, cands_per_s)):
+        for x in cands:
+            flat.append(_realise(inputs, dims, x))
+            stream.append(s)
+            owner.append(s)
+    low = lower(models, performance, [i.name for i in flat[0]])
+    job = build_job(low, flat, sim, stream_id=np.array(stream, dtype=np.uint32))
+    _, pf, _ = L.pf_batch(job)
+    out, k = [], 0
+    for cands in cands_per_s:
+        out.append(pf[k:k + len(cands)])
+        k += len(cands)
+    return out
+
+
+def double_loop(models, performance, scenario_inputs, sim: CudaDoubleLoop) -> List[Tuple[float, float]]:
+    """UQ.jl DoubleLoop (A5): per scenario (pf_lb, pf_ub) over the imprecise box, all scenarios and
+    all outer candidates batched on the device."""
+    inner = sim.lb
+    dims_per_s = [_imprecise_dims(inp) for inp in scenario_inputs]
+    if any(not d for d in dims_per_s):
+        raise AssertionError("DoubleLoop needs at least one Interval / ProbabilityBox input")
+    S = len(scenario_inputs)
+    los = [np.array([d[2] for d in dims]) for dims in dims_per_s]
+    his = [np.array([d[3] for d in dims]) for dims in dims_per_s]
+    if sim.method == "grid":
+        cands = []
+        for lo, hi in zip(los, his):
+            axes = [np.linspace(a, b, sim.grid) for a, b in zip(lo, hi)]
+            cands.append([np.array(p) for p in itertools.product(*axes)])
+        pf = _eval_candidates(models, performance, scenario_inputs, dims_per_s, cands, inner)
+        return [(float(p.min()), float(p.max())) for p in pf]
+    # "optimise": compass search from the box midpoint (where the reference starts BOBYQA), both
+    # bounds and all scenarios advancing in lock-step; the vertices are always probed first.
+    best_lo = [None] * S
+    best_hi = [None] * S
+    x_lo = [0.5 * (a + b) for a, b in zip(los, his)]
+    x_hi = [0.5 * (a + b) for a, b in zip(los, his)]
+    step = [0.25 * (b - a) for a, b in zip(los, his)]
+    first = True
+    for _ in range(14):
+        cands = []
+        for s in range(S):
+            c = [x_lo[s], x_hi[s]]
+            for x0 in (x_lo[s], x_hi[s]):
+                for k in range(len(x0)):
+                    for sg in (-1.0, 1.0):
+                        y = x0.copy()
+                        y[k] = min(max(y[k] + sg * step[s][k], los[s][k]), his[s][k])
+                        c.append(y)
+            if first:
+                c += [np.array(v) for v in itertools.product(*zip(los[s], his[s]))]
+            cands.append(c)
+        pf = _eval_candidates(models, performance, scenario_inputs, dims_per_s, cands, inner)
+        moved = False
+        for s in range(S):
+            i_min, i_max = int(np.argmin(pf[s])), int(np.argmax(pf[s]))
+            if best_lo[s] is None or pf[s][i_min] < best_lo[s]:
+                moved |= best_lo[s] is not None
+                best_lo[s], x_lo[s] = float(pf[s][i_min]), cands[s][i_min].copy()
+            if best_hi[s] is None or pf[s][i_max] > best_hi[s]:
+                moved |= best_hi[s] is not None
+                best_hi[s], x_hi[s] = float(pf[s][i_max]), cands[s][i_max].copy()
+        if not moved and not first:
+            step = [0.5 * st for st in step]
+            if all(np.all(st <= 1e-3 * (b - a) + 1e-300) for st, a, b in zip(step, los, his)):
+                break
+        first = False
+    return list(zip(best_lo, best_hi))
+
+
+def _poly_monotone(models, performance, name: str) -> bool:
+    """True if every polynomial stage is affine in `name` with sign-definite coefficient, i.e. the
+    limit state is monotone in that column (sufficient condition, checked syntactically)."""
+    derived = {name}
+    for st in [m.func for m in models] + ([performance] if isinstance(performance, Poly) else []):
+        if not isinstance(st, Poly):
+            return False
+        for _, cols in st.terms:
+            hits = [c for c in cols if c in derived]
+            if len(hits) > 1 or (hits and len(cols) > 1):
+                return False
+    for m in models:
+        if any(c in derived for _, cols in m.func.terms for c in cols):
+            derived.add(m.name)
+    return True
+
+
+def random_slicing(models, performance, scenario_inputs, sim: CudaRandomSlicing):
+    """UQ.jl RandomSlicing (A6) for limit states monotone in each imprecise input: the per-sample
+    extremes over the input boxes are then attained at the box vertices, so
+    pf_lb / pf_ub are the extreme vertex probabilities (evaluated with common random numbers).
+    Returns [((lb, ub), (std_lb, Samples), (std_ub, Samples))] per scenario."""
+    inner = sim.lb
+    for inputs in scenario_inputs:
+        for i in inputs:
+            if _is_imprecise(i) and not _poly_monotone(models, performance, i.name):
+                raise UnsupportedModel(f"RandomSlicing on the device needs a limit state monotone in '{i.name}'")
+            if isinstance(i, ProbabilityBox) and len(i.parameters) > 1:
+                raise UnsupportedModel("RandomSlicing on the device supports p-boxes with one interval parameter")
+    dims_per_s = [_imprecise_dims(inp) for inp in scenario_inputs]
+    cands = [[np.array(v) for v in itertools.product(*[(d[2], d[3]) for d in dims])] for dims in dims_per_s]
+    pf = _eval_candidates(models, performance, scenario_inputs, dims_per_s, cands, inner)
+    out = []
+    n = inner.n
+    for p in pf:
+        lb, ub = float(p.min()), float(p.max())
+        out.append(((lb, ub), (math.sqrt(max(lb - lb * lb, 0) / n), None), (math.sqrt(max(ub - ub * ub, 0) / n), None)))
+    return out
+
+
+# ---- ContinuousFunctionalNode ------------------------------------------------------------------
+def output_histograms(models, scenario_inputs, sim: CudaMonteCarlo, edges: Optional[np.ndarray] = None):
+    """`sample` + `evaluate!` for a ContinuousFunctionalNode: per-scenario histogram and moments of
+    the last model's output. Without `edges`, a pilot call finds the output range."""
+    low = lower(models, None, [i.name for i in scenario_inputs[0]])
+    job = build_job(low, scenario_inputs, sim)
+    if edges is None:
+        pilot = L.Job(job.limit_state, job.consts, job.inputs, min(job.n, 1 << 16), job.seed, job.strict,
+                      tables=job.tables)
+        _, s1, s2 = L.hist_batch(pilot, np.array([0.0]))
+        m = s1 / pilot.n
+        sd = np.sqrt(np.maximum(s2 / pilot.n - m * m, 0.0))
+        lo, hi = float(np.min(m - 8 * sd)), float(np.max(m + 8 * sd))
+        if not hi > lo:
+            lo, hi = lo - 1.0, hi + 1.0
+        edges = np.linspace(lo, hi, min(HIST_BINS, L.EBN_MAX_EDGES))
+    counts, s1, s2 = L.hist_batch(job, edges)
+    return edges, counts, s1, s2, job, low

@@ -209,6 +209,11 @@ int ebn_eval_matrix(int limit_state, const double* consts, int n_consts,
  */
 int ebn_sample_matrix(const ebn_job_t* job, int scenario, int64_t first,
                       int64_t n, double* X, double* g_out);
+/* Same, with ncols >= d columns per sample: columns d.. are the model outputs the
+ * limit state defines (the stages of a polynomial program), i.e. the DataFrame
+ * UQ.jl holds after `evaluate!(models, samples)`. X is [n*ncols], ld = n. */
+int ebn_sample_matrix_ex(const ebn_job_t* job, int scenario, int64_t first,
+                         int64_t n, int ncols, double* X, double* g_out);
 
 /*
  * The static work partition of a job (host logic, needs no device): a work item

@@ -1,0 +1,361 @@
+"""GPU tests of `evaluate!` through the host mirror of the reference API — the reference's own
+hot-path tests restated (test/networks/ebn/evaluate/evaluate_node.jl, evaluate_net.jl,
+test/inference/variableselimination.jl:133-206, demo/straub_example.jl, demo/vehicle_suspension.jl),
+with the Monte Carlo running in libebncuda. Tolerances are the reference's (atol 0.02 … 0.2) or
+tighter where the value is analytic."""
+import math
+import warnings
+
+import numpy as np
+import pytest
+from scipy.special import ndtr
+
+pytestmark = pytest.mark.gpu
+
+INF = math.inf
+
+
+@pytest.fixture(scope="module")
+def E(ebn):
+    return ebn
+
+
+def _root(E, name, states, probs, params=None):
+    cpt = E.DiscreteConditionalProbabilityTable(name)
+    for s, p in zip(states, probs):
+        cpt[(name, s)] = p
+    return E.DiscreteNode(name, cpt, params or {})
+
+
+def _cont_root(E, name, dist, disc=None, kind="precise"):
+    cpt = E.ContinuousConditionalProbabilityTable(kind=kind)
+    cpt[()] = dist
+    return E.ContinuousNode(name, cpt, disc)
+
+
+def _ab_roots(E):
+    a = _root(E, "A", ["a1", "a2"], [0.5, 0.5], {"a1": [E.Parameter(1, "A")], "a2": [E.Parameter(2, "A")]})
+    return a, _cont_root(E, "B", E.Normal())
+
+
+def test_evaluate_discrete_functional_node(E):
+    """evaluate_node.jl:94-157."""
+    from ebn_b200 import evaluation as ev
+    a, b = _ab_roots(E)
+    sim = E.MonteCarlo(100_000)
+    f = E.DiscreteFunctionalNode("C", [E.Model(E.Poly([(1, ["A"]), (1, ["B"])]), "C")], E.Poly([(2, []), (-1, ["C"])]), sim)
+    net = E.EnhancedBayesianNetwork([a, b, f])
+    E.add_child(net, a, f)
+    E.add_child(net, b, f)
+    E.order(net)
+    out = ev._evaluate_node(net, f)
+    assert out.name == "C" and isinstance(out, E.DiscreteNode)
+    assert out.cpt.column("A") == ["a1", "a1", "a2", "a2"]
+    assert out.cpt.column("C") == ["C_fail", "C_safe", "C_fail", "C_safe"]
+    assert np.allclose(out.cpt.column("Π"), [0.16, 0.84, 0.5, 0.5], atol=0.02)
+    assert out.parameters == f.parameters
+    for key in (("a1",), ("a2",)):
+        info = out.additional_info[key]
+        assert info["samples"].shape == (sim.n, 3) and isinstance(info["cov"], float)
+    rows = out.additional_info[("a1",)]["samples"].fetch(0, 1000)
+    assert set(rows) == {"A", "B", "C", "g"} and np.all(rows["A"] == 1.0)
+    assert np.allclose(rows["g"], 2 - (rows["A"] + rows["B"]))
+    # pf and the replayed frame agree exactly: pf*n == #(g < 0) over the whole stream
+    allrows = out.additional_info[("a1",)]["samples"].fetch(0, sim.n)
+    assert int(np.sum(allrows["g"] < 0)) == round(out.cpt[{"A": "a1", "C": "C_fail"}] * sim.n)
+    # no discrete ancestor (evaluate_node.jl:123-139)
+    f2 = E.DiscreteFunctionalNode("C", [E.Model(E.Poly([(1, ["B"]), (1, [])]), "C")], E.Poly([(2, []), (-1, ["C"])]), sim)
+    net = E.EnhancedBayesianNetwork([b, f2])
+    E.add_child(net, b, f2)
+    E.order(net)
+    out = ev._evaluate_node(net, f2)
+    assert out.isroot() and out.cpt.column("C") == ["C_fail", "C_safe"]
+    assert np.allclose(out.cpt.column("Π"), [0.1587, 0.8413], atol=0.01)
+    assert ev._evaluate_node(net, f2, False).additional_info == {}
+
+
+def test_evaluate_continuous_functional_node(E):
+    """evaluate_node.jl:1-62: the evaluated node is a ContinuousNode; KDE replaced by a histogram."""
+    from ebn_b200 import evaluation as ev
+    a, b = _ab_roots(E)
+    sim = E.MonteCarlo(200_000)
+    disc = E.ApproximatedDiscretization([-1, 0, 1], 2)
+    cf = E.ContinuousFunctionalNode("C", [E.Model(E.Poly([(1, ["A"]), (1, ["B"])]), "C")], sim, disc)
+    net = E.EnhancedBayesianNetwork([a, b, cf])
+    E.add_child(net, a, cf)
+    E.add_child(net, b, cf)
+    E.order(net)
+    out = ev._evaluate_node(net, cf)
+    assert isinstance(out, E.ContinuousNode) and out.name == "C" and out.discretization == disc
+    assert out.cpt.column("A") == ["a1", "a2"]
+    d1, d2 = out.cpt.column("Π")
+    assert isinstance(d1, E.EmpiricalDistribution)
+    assert abs(d1.mean() - 1) < 0.01 and abs(d2.mean() - 2) < 0.01 and abs(d1.std() - 1) < 0.01
+    for x in (-0.5, 0.0, 1.0, 2.5):
+        assert abs(float(d1.cdf(x)) - ndtr(x - 1)) < 5e-3
+    assert out.additional_info[("a1",)]["samples"].shape == (sim.n, 3)
+    assert ev._evaluate_node(net, cf, False).additional_info == {}
+    # root case → ExactDiscretization (evaluate_node.jl:12-14,60)
+    cf2 = E.ContinuousFunctionalNode("C", [E.Model(E.Poly([(1, ["B"]), (1, [])]), "C")], sim, disc)
+    net = E.EnhancedBayesianNetwork([b, cf2])
+    E.add_child(net, b, cf2)
+    E.order(net)
+    out = ev._evaluate_node(net, cf2)
+    assert out.discretization == E.ExactDiscretization(disc.intervals) and out.isroot()
+    # imprecise parent → the reference's error (evaluate_node.jl:37, test :65-92)
+    r2 = _cont_root(E, "Bi", (0.1, 0.3), kind="interval")
+    cf3 = E.ContinuousFunctionalNode("C", [E.Model(E.Poly([(1, ["A"]), (1, ["Bi"])]), "C")], sim)
+    net = E.EnhancedBayesianNetwork([a, r2, cf3])
+    E.add_child(net, a, cf3)
+    E.add_child(net, r2, cf3)
+    E.order(net)
+    with pytest.raises(ValueError, match="No method for extracting failure probability p-box"):
+        ev._evaluate_node(net, cf3)
+
+
+def _imprecise_net(E, sim):
+    a = _root(E, "A", ["a1", "a2"], [0.5, 0.5], {"a1": [E.Parameter(1, "A")], "a2": [E.Parameter(2, "A")]})
+    b = _cont_root(E, "B", (0.10, 1.30), kind="interval")
+    p = _cont_root(E, "P", E.Uniform(-10, 10))
+    f = E.DiscreteFunctionalNode("C", [E.Model(E.Poly([(1, ["A"]), (1, ["B"]), (1, ["P"])]), "C")],
+                                 E.Poly([(2, []), (-1, ["C"])]), sim)
+    net = E.EnhancedBayesianNetwork([a, b, p, f])
+    for par in (a, b, p):
+        E.add_child(net, par, f)
+    E.order(net)
+    return net, f
+
+
+@pytest.mark.parametrize("method", ["optimise", "grid"])
+def test_double_loop_interval_parent(E, method):
+    """evaluate_node.jl:159-204: pf = (8 + A + B)/20 over B in [0.10, 1.30]."""
+    from ebn_b200 import evaluation as ev
+    net, f = _imprecise_net(E, E.DoubleLoop(E.MonteCarlo(100_000), method=method))
+    out = ev._evaluate_node(net, f)
+    assert not out.isprecise() and out.additional_info[("a1",)] == {} and out.additional_info[("a2",)] == {}
+    assert out.cpt.column("A") == ["a1", "a1", "a2", "a2"]
+    assert out.cpt.column("C") == ["C_fail", "C_safe", "C_fail", "C_safe"]
+    want = [(0.45191, 0.51868), (0.48132, 0.54809), (0.50418, 0.56792), (0.43208, 0.49582)]
+    for got, w in zip(out.cpt.column("Π"), want):
+        assert np.allclose(got, w, atol=0.2)       # the reference's tolerance
+    exact = [(0.455, 0.515), (0.485, 0.545), (0.505, 0.565), (0.435, 0.495)]
+    for got, w in zip(out.cpt.column("Π"), exact):
+        assert np.allclose(got, w, atol=0.006)     # analytic value, 3 SE at n = 1e5 is 0.0047
+
+
+def test_random_slicing_and_child_intervals(E):
+    """evaluate_node.jl:206-282."""
+    from ebn_b200 import evaluation as ev
+    sim = E.RandomSlicing(E.MonteCarlo(100_000))
+    net, f = _imprecise_net(E, sim)
+    out = ev._evaluate_node(net, f)
+    for key in (("a1",), ("a2",)):
+        lb, ub = out.additional_info[key]["lb"], out.additional_info[key]["ub"]
+        assert isinstance(lb[0], float) and isinstance(ub[0], float)
+    exact = [(0.455, 0.515), (0.485, 0.545), (0.505, 0.565), (0.435, 0.495)]
+    for got, w in zip(out.cpt.column("Π"), exact):
+        assert np.allclose(got, w, atol=0.006)
+    # child with interval rows per parent state (evaluate_node.jl:233-282)
+    a = _root(E, "A", ["a1", "a2"], [0.5, 0.5], {"a1": [E.Parameter(1, "A")], "a2": [E.Parameter(2, "A")]})
+    b = _cont_root(E, "B", E.Normal())
+    d = _root(E, "D", ["d1", "d2"], [0.5, 0.5], {"d1": [E.Parameter(1, "D")], "d2": [E.Parameter(2, "D")]})
+    cptc = E.ContinuousConditionalProbabilityTable(["A"], kind="interval")
+    cptc[("A", "a1")], cptc[("A", "a2")] = (0.1, 0.3), (0.7, 0.8)
+    c1 = E.ContinuousNode("C1", cptc)
+    fn = E.DiscreteFunctionalNode("F1", [E.Model(E.Poly([(1, ["D"]), (1, ["C1"]), (1, ["B"])]), "C2")],
+                                  E.Poly([(2, []), (-1, ["C2"])]), sim)
+    net = E.EnhancedBayesianNetwork([a, b, d, c1, fn])
+    E.add_child(net, a, c1)
+    for par in (b, d, c1):
+        E.add_child(net, par, fn)
+    E.order(net)
+    out = ev._evaluate_node(net, fn)
+    assert out.name == "F1"
+    assert out.cpt.column("A") == ["a1", "a1", "a2", "a2"] * 2
+    assert out.cpt.column("D") == ["d1"] * 4 + ["d2"] * 4
+    assert out.cpt.column("F1") == ["F1_fail", "F1_safe"] * 4
+    want = [(0.198, 0.2406), (0.759, 0.802), (0.371, 0.4248), (0.5752, 0.629), (0.537, 0.6224), (0.377, 0.463),
+            (0.749, 0.7869), (0.213, 0.251)]
+    for got, w in zip(out.cpt.column("Π"), want):
+        assert np.allclose(got, w, atol=0.2)
+    # analytic: pf = Phi(D + C1 - 2)
+    ex = {("d1", "a1"): (ndtr(-0.9), ndtr(-0.7)), ("d1", "a2"): (ndtr(-0.3), ndtr(-0.2)),
+          ("d2", "a1"): (ndtr(0.1), ndtr(0.3)), ("d2", "a2"): (ndtr(0.7), ndtr(0.8))}
+    for (dd, aa), w in ex.items():
+        assert np.allclose(out.cpt[{"D": dd, "A": aa, "F1": "F1_fail"}], w, atol=0.006)
+
+
+def test_evaluate_net_chain_and_error_messages(E):
+    """evaluate_net.jl: a continuous functional node with children is fused, one with a discretisation
+    is evaluated then discretised; wrong simulation type → the reference's two fixed messages."""
+    a, b = _ab_roots(E)
+    sim = E.MonteCarlo(20_000)
+    # B -> C1 (fused away) -> C2 (discretised: evaluated to a histogram, then split into C2_d + C2) -> F,
+    # the flow of test/inference/variableselimination.jl:207-284 (Straub with R4, R5 discretised)
+    c1 = E.ContinuousFunctionalNode("C1", [E.Model(E.Poly([(1, ["B"]), (1, [])]), "C1")], sim)
+    c2 = E.ContinuousFunctionalNode("C2", [E.Model(E.Poly([(1, ["C1"]), (0.5, ["B"])]), "C2")], sim,
+                                    E.ApproximatedDiscretization([0.0, 1.0, 2.0, 3.0], 1.5))
+    f = E.DiscreteFunctionalNode("F", [E.Model(E.Poly([(1, ["C2"]), (1, ["A"])]), "G")], E.Poly([(2.5, []), (-1, ["G"])]), sim)
+    net = E.EnhancedBayesianNetwork([a, b, c1, c2, f])
+    E.add_child(net, b, c1)
+    E.add_child(net, c1, c2)
+    E.add_child(net, b, c2)
+    E.add_child(net, c2, f)
+    E.add_child(net, a, f)
+    E.order(net)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        E.evaluate(net, True, False)
+    names = sorted(n.name for n in net.nodes)
+    assert names == ["A", "B", "C2", "C2_d", "F"] and all(not isinstance(n, (E.DiscreteFunctionalNode, E.ContinuousFunctionalNode)) for n in net.nodes)
+    c2d = net.node("C2_d")
+    assert c2d.isroot() and abs(sum(c2d.cpt.column("Π")) - 1) < 1e-9
+    # C2 = 1 + 1.5 B: P(C2 in [1, 2]) = Phi(2/3) - Phi(0)
+    assert abs(c2d.cpt[("C2_d", "[1.0, 2.0]")] - (ndtr(2 / 3) - 0.5)) < 0.012
+    fnode = net.node("F")
+    assert sorted(fnode.cpt.names[:-1]) == ["A", "C2_d"] and len(fnode.cpt.data) == 2 * 2 * len(c2d.states())
+    pf = {(r["A"], r["C2_d"]): r["Π"] for r in fnode.cpt.data if r["F"] == "F_fail"}
+    # g = 2.5 - (C2 + A). The evaluated C2 is a ROOT continuous node, so its bins carry
+    # truncated(EmpiricalDistribution, a, b) (discretize.jl:53-55), shipped to the device as inverse-CDF
+    # tables: with C2 ~ N(1, 1.5), P(C2 > 1.5 | [1, 2]) and P(C2 > 0.5 | [0, 1]) are analytic.
+    p_a1 = (ndtr(1 / 1.5) - ndtr(0.5 / 1.5)) / (ndtr(1 / 1.5) - 0.5)
+    p_a2 = (0.5 - ndtr(-0.5 / 1.5)) / (0.5 - ndtr(-1 / 1.5))
+    assert pf[("a1", "[2.0, 3.0]")] == 1.0 and pf[("a1", "[0.0, 1.0]")] == 0.0 and abs(pf[("a1", "[1.0, 2.0]")] - p_a1) < 0.02
+    assert pf[("a2", "[1.0, 2.0]")] == 1.0 and abs(pf[("a2", "[0.0, 1.0]")] - p_a2) < 0.02
+    assert all(not n.additional_info for n in net.nodes if isinstance(n, E.DiscreteNode))
+    # precise simulation with an imprecise parent (evaluate_net.jl:268-281)
+    net, f = _imprecise_net(E, E.MonteCarlo(100))
+    with pytest.raises(ValueError, match=r"has .* as simulation technique, but have \['B'\] as imprecise parent/s. "
+                                         "DoubleLoop or RandomSlicing technique must be employeed instead"):
+        E.evaluate(net)
+    # DoubleLoop without imprecise parents (evaluate_net.jl:218-266)
+    a, b = _ab_roots(E)
+    f = E.DiscreteFunctionalNode("C", [E.Model(E.Poly([(1, ["A"]), (1, ["B"])]), "C")], E.Poly([(2, []), (-1, ["C"])]),
+                                 E.DoubleLoop(E.MonteCarlo(100)))
+    net = E.EnhancedBayesianNetwork([a, b, f])
+    E.add_child(net, a, f)
+    E.add_child(net, b, f)
+    E.order(net)
+    with pytest.raises(ValueError, match="A prices simulation technique must be selected!"):
+        E.evaluate(net)
+    # a model with no device functor is an error, never a fallback
+    f = E.DiscreteFunctionalNode("C", [E.Model(lambda df: df.A + df.B, "C")], "C", E.MonteCarlo(100))
+    net = E.EnhancedBayesianNetwork([a, b, f])
+    E.add_child(net, a, f)
+    E.add_child(net, b, f)
+    E.order(net)
+    with pytest.raises(E.UnsupportedModel, match="no CPU fallback"):
+        E.evaluate(net)
+
+
+def straub_net(E, n):
+    """demo/straub_example.jl in the current API (test/inference/variableselimination.jl:133-206)."""
+    lam, zeta = E.distribution_parameters(150, 30, "LogNormal")
+    ur = _cont_root(E, "Uᵣ", E.Normal())
+    v = _cont_root(E, "V", E.Gamma(*E.distribution_parameters(60, 12, "Gamma")))
+    h = _cont_root(E, "H", E.Gumbel(*E.distribution_parameters(50, 20, "Gumbel")))
+    sim = E.MonteCarlo(n)
+    rs = [E.ContinuousFunctionalNode(f"R{i}", [E.Model(E.Catalogue("straub_capacity", (lam, zeta, 0.5477), ("Uᵣ",)), f"r{i}")], sim)
+          for i in range(1, 6)]
+    frame = E.DiscreteFunctionalNode(
+        "E", [E.Model(E.Catalogue("straub_frame", (), ("r1", "r2", "r3", "r4", "r5", "V", "H")), "G")], "G", sim)
+    net = E.EnhancedBayesianNetwork([ur, v, h] + rs + [frame])
+    for r in rs:
+        E.add_child(net, ur, r)
+        E.add_child(net, r, frame)
+    E.add_child(net, v, frame)
+    E.add_child(net, h, frame)
+    E.order(net)
+    return net
+
+
+def test_straub_end_to_end(E):
+    """demo/straub_example.jl:71: Π ≈ [0.026129, 0.973871] atol 0.01 at n = 10^6."""
+    net = straub_net(E, 10**6)
+    E.evaluate(net)
+    e = net.nodes[-1]
+    assert e.name == "E" and sorted(n.name for n in net.nodes) == ["E", "H", "Uᵣ", "V"]
+    assert np.allclose(e.cpt.column("Π"), [0.026129, 0.973871], atol=0.01)
+    assert abs(e.cpt.column("Π")[0] - 0.0258) < 0.001
+    bn = E.dispatch(net)
+    assert isinstance(bn, E.BayesianNetwork) and [n.name for n in bn.nodes] == ["E"]
+
+
+def vehicle_net(E, n, v_dist=None, sim=None):
+    """demo/vehicle_suspension.jl restated in the current API (the demo file itself is stale)."""
+    M, m, g = 3.2633, 0.8158, 981.0
+    consts = (M, m, g, (M * g) ** -1.5, (g * (M + m)) ** 0.877)
+    A = _root(E, "A", ["road", "offroad"], [0.7, 0.3],
+              {"road": [E.Parameter(0.15915, "A")], "offroad": [E.Parameter(0.8, "A")]})
+    b0 = _root(E, "b₀", ["normal_load", "over_load"], [0.7, 0.3],
+               {"normal_load": [E.Parameter(0.27, "b₀")], "over_load": [E.Parameter(0.5, "b₀")]})
+    if v_dist is None:
+        V = _cont_root(E, "V", E.Uniform(7, 12), E.ExactDiscretization([8.5, 9.5, 10.5, 11.5]))
+    else:
+        V = _cont_root(E, "V", v_dist, E.ExactDiscretization([8.5, 9.5, 10.5, 11.5]), kind="interval")
+    C = _cont_root(E, "C", E.Normal(431.7221, 10))
+    Ck = _cont_root(E, "Cₖ", E.Normal(1475.5503, 10))
+    K = _cont_root(E, "K", E.Normal(55.0406, 10))
+    from ebn_b200 import uq
+    model = E.Model(E.Catalogue("vehicle_suspension", consts, uq.VEHICLE_ARGS), "y")
+    node = E.DiscreteFunctionalNode("E", [model], "y", sim or E.MonteCarlo(n))
+    net = E.EnhancedBayesianNetwork([A, b0, V, C, Ck, K, node])
+    for p in (A, b0, V, C, Ck, K):
+        E.add_child(net, p, node)
+    E.order(net)
+    return net
+
+
+def test_vehicle_suspension_network(E):
+    """BASELINE config 2 through the node API: 20 scenarios, pf per BASELINE.md §2 / the oracle."""
+    net = vehicle_net(E, 4_000_000)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        E.evaluate(net, True, False)
+    e = net.node("E")
+    assert e.cpt.names == ["A", "b₀", "V_d", "E"] and len(e.cpt.data) == 40
+    pf = {(r["A"], r["b₀"], r["V_d"]): r["Π"] for r in e.cpt.data if r["E"] == "E_fail"}
+    want = {"[7.0, 8.5]": 0.0023, "[8.5, 9.5]": 0.0431, "[9.5, 10.5]": 0.2151, "[10.5, 11.5]": 0.5164, "[11.5, 12.0]": 0.7373}
+    for vbin, w in want.items():
+        got = pf[("offroad", "normal_load", vbin)]
+        assert abs(got - w) < 4 * math.sqrt(w * (1 - w) / 4e6) + 2e-4, (vbin, got, w)
+    others = [v for k, v in pf.items() if k[:2] != ("offroad", "normal_load")]
+    assert len(others) == 15 and all(abs(v - 5.2e-4) < 1e-4 for v in others)
+    for r in e.cpt.data:  # safe = 1 - fail exactly as the reference writes it (evaluate_node.jl:91-92)
+        if r["E"] == "E_safe":
+            assert r["Π"] == 1 - pf[(r["A"], r["b₀"], r["V_d"])]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bn = E.dispatch(net)
+    assert isinstance(bn, E.BayesianNetwork) and sorted(n.name for n in bn.nodes) == ["A", "E", "V_d", "b₀"]
+
+
+def test_vehicle_suspension_imprecise(E):
+    """BASELINE config 4 (demo/vehicle_suspension_imprecise.jl): V an interval (7, 13), discretised into
+    interval bins; DoubleLoop sweeps V over each bin. pf is monotone in V, so the bounds are the pf at
+    the bin ends — checked against precise runs with V fixed there."""
+    sim = E.DoubleLoop(E.MonteCarlo(400_000), method="grid", grid=9)
+    net = vehicle_net(E, 0, v_dist=(7, 13), sim=sim)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        E.evaluate(net, True, False)
+    e = net.node("E")
+    assert not e.isprecise() and len(e.cpt.data) == 40
+    got = {r["V_d"]: r["Π"] for r in e.cpt.data if r["E"] == "E_fail" and (r["A"], r["b₀"]) == ("offroad", "normal_load")}
+    assert set(got) == {"[7.0, 8.5]", "[8.5, 9.5]", "[9.5, 10.5]", "[10.5, 11.5]", "[11.5, 13.0]"}
+    from ebn_b200 import uq
+    M, m, g = 3.2633, 0.8158, 981.0
+    consts = (M, m, g, (M * g) ** -1.5, (g * (M + m)) ** 0.877)
+    model = E.Model(E.Catalogue("vehicle_suspension", consts, uq.VEHICLE_ARGS), "y")
+
+    def pf_at(v):
+        inputs = [E.Parameter(0.8, "A"), E.Parameter(0.27, "b₀"), E.Parameter(v, "V"),
+                  E.RandomVariable(E.Normal(431.7221, 10), "C"), E.RandomVariable(E.Normal(1475.5503, 10), "Cₖ"),
+                  E.RandomVariable(E.Normal(55.0406, 10), "K")]
+        return E.probability_of_failure(model, "y", inputs, E.MonteCarlo(400_000, seed=77))[0]
+
+    for name, (lo, hi) in {"[8.5, 9.5]": (8.5, 9.5), "[11.5, 13.0]": (11.5, 13.0)}.items():
+        lb, ub = got[name]
+        assert lb < ub and abs(lb - pf_at(lo)) < 0.005 and abs(ub - pf_at(hi)) < 0.005
+    bn = E.dispatch(net)
+    assert isinstance(bn, E.CredalNetwork)
