@@ -1,0 +1,210 @@
+# EBNCuda.jl — `ccall` wrapper over libebncuda.so (C ABI: include/ebncuda.h).
+#
+# Drop-in for the Monte Carlo hot path of EnhancedBayesianNetworks.jl. A functional node whose
+# `simulation` is a `CudaMonteCarlo` (a new `AbstractMonteCarlo` subtype) is evaluated by ONE call
+# into the library for all its scenarios instead of one UncertaintyQuantification.jl call per
+# scenario (reference src/networks/ebn/evaluation/evaluate_node.jl:79-95 and :22-33).
+#
+# NOT EXECUTED in the build environment of this repository (no Julia there, SURVEY.md F3): this
+# file is kept a thin, obviously-correct marshalling layer; everything it calls is exercised
+# through the same C ABI by the Python tests under tests/.
+#
+# Integration (see INTEGRATION.md): `include("cuda/EBNCuda.jl")` at the end of
+# src/EnhancedBayesianNetworks.jl, after networks/ebn/ebn.jl.
+
+module EBNCuda
+
+using ..EnhancedBayesianNetworks
+using ..EnhancedBayesianNetworks: AbstractNode, ContinuousNode, DiscreteNode, DiscreteFunctionalNode,
+    ContinuousFunctionalNode, EnhancedBayesianNetwork, Evidence, parents, discrete_ancestors, states,
+    _uq_inputs, DiscreteConditionalProbabilityTable, ContinuousConditionalProbabilityTable,
+    PreciseDiscreteProbability, PreciseContinuousInput, ExactDiscretization
+using UncertaintyQuantification
+using Distributions
+using DataFrames
+using Libdl
+
+export CudaMonteCarlo, CudaModel, ebn_init, ebn_shutdown
+
+const LIB = Ref{String}(get(ENV, "EBNCUDA_LIB", "libebncuda.so"))
+
+# ---- constants of include/ebncuda.h ------------------------------------------------------------
+const EBN_LS = Dict(:vehicle_suspension => 1, :straub_frame => 2, :hydrogen_radius => 3,
+    :polynomial => 4, :min_affine => 5)
+const IN_PARAM, IN_NORMAL, IN_LOGNORMAL, IN_UNIFORM, IN_GUMBEL, IN_GAMMA, IN_EXP_AFFINE, IN_TABULATED = 0:7
+
+# typedef struct ebn_input { int32 kind; int32 flags; double p[4]; double lo; double hi; }  (56 bytes)
+struct EbnInput
+    kind::Int32
+    flags::Int32
+    p::NTuple{4,Float64}
+    lo::Float64
+    hi::Float64
+end
+
+# typedef struct ebn_job (104 bytes); field order and widths as in the header
+struct EbnJob
+    limit_state::Int32
+    n_consts::Int32
+    consts::Ptr{Float64}
+    n_scenarios::Int32
+    n_inputs::Int32
+    inputs::Ptr{EbnInput}
+    n_per_scenario::Int64
+    seed::UInt64
+    strict::Int32
+    flags::UInt32
+    corr_chol::Ptr{Float64}
+    stream_id::Ptr{UInt32}
+    tables::Ptr{Float64}
+    n_tables::Int64
+    sample_offset::Int64
+    shard_rank::Int32
+    shard_world::Int32
+end
+
+@assert sizeof(EbnInput) == 56
+@assert sizeof(EbnJob) == 104
+
+last_error() = unsafe_string(ccall((:ebn_last_error, LIB[]), Cstring, ()))
+
+function check(rc::Integer)
+    if rc != 0
+        msg = last_error()
+        # evaluate! rewrites every exception of _evaluate_node into one of two fixed messages
+        # (evaluate_net.jl:16-24): log the real one before throwing.
+        @error "libebncuda: $msg (code $rc)"
+        error("libebncuda: $msg (code $rc)")
+    end
+    return nothing
+end
+
+"ebn_init: `devices` are CUDA ordinals; more than one → single-process multi-GPU with an NCCL all-reduce."
+function ebn_init(devices::Vector{Int}=Int[])
+    dev = Int32.(devices)
+    check(ccall((:ebn_init, LIB[]), Cint, (Ptr{Int32}, Cint), isempty(dev) ? C_NULL : dev, length(dev)))
+end
+ebn_shutdown() = check(ccall((:ebn_shutdown, LIB[]), Cint, ()))
+
+# ---- the plug-in point: a new AbstractMonteCarlo subtype ---------------------------------------
+"""
+    CudaMonteCarlo(n; seed=0x5EED0001, strict=false)
+
+Simulation object routing a functional node to libebncuda. `strict=true` evaluates the limit
+state with one IEEE operation per Julia operation (bit-exact `g`), the default contracts FMAs and
+hoists reciprocals (|Δg| ~ 1e-13, count differences only on ties).
+"""
+struct CudaMonteCarlo <: UncertaintyQuantification.AbstractMonteCarlo
+    n::Int
+    seed::UInt64
+    strict::Bool
+end
+CudaMonteCarlo(n::Integer; seed::Integer=0x5EED0001, strict::Bool=false) = CudaMonteCarlo(n, UInt64(seed), strict)
+
+"""
+    CudaModel(name, limit_state, consts, args)
+
+A `UQModel` naming a limit state compiled into the kernels (`:vehicle_suspension`, `:straub_frame`,
+`:polynomial`, ...). `args` are the DataFrame column names in the functor's argument order.
+Arbitrary closures cannot run on the GPU; there is no CPU fallback.
+"""
+struct CudaModel <: UncertaintyQuantification.UQModel
+    name::Symbol
+    limit_state::Symbol
+    consts::Vector{Float64}
+    args::Vector{Symbol}
+end
+
+# ---- marshalling: UQInput -> ebn_input_t --------------------------------------------------------
+abi(p::Parameter) = EbnInput(IN_PARAM, 0, (Float64(p.value), 0.0, 0.0, 0.0), -Inf, Inf)
+abi(rv::RandomVariable) = abi(rv.dist, -Inf, Inf)
+abi(d::Normal, lo, hi) = EbnInput(IN_NORMAL, 0, (d.μ, d.σ, 0.0, 0.0), lo, hi)
+abi(d::LogNormal, lo, hi) = EbnInput(IN_LOGNORMAL, 0, (d.μ, d.σ, 0.0, 0.0), lo, hi)
+abi(d::Uniform, lo, hi) = EbnInput(IN_UNIFORM, 0, (d.a, d.b, 0.0, 0.0), lo, hi)
+abi(d::Gumbel, lo, hi) = EbnInput(IN_GUMBEL, 0, (d.μ, d.θ, 0.0, 0.0), lo, hi)
+abi(d::Gamma, lo, hi) = (isinf(lo) && isinf(hi)) ? EbnInput(IN_GAMMA, 0, (d.α, d.θ, 0.0, 0.0), lo, hi) :
+                        error("truncated Gamma must be passed as an inverse-CDF table (EBN_IN_TABULATED)")
+abi(d::Truncated, lo, hi) = abi(d.untruncated, max(lo, something(d.lower, -Inf)), min(hi, something(d.upper, Inf)))
+# `±Exponential(λ) + c` built by _approximate (discretize.jl:83-91) is a LocationScale
+abi(d::Distributions.AffineDistribution{<:Any,<:Any,<:Exponential}, lo, hi) =
+    EbnInput(IN_EXP_AFFINE, 0, (d.ρ.θ, sign(d.σ), d.μ, 0.0), lo, hi)
+abi(x, args...) = error("marginal $(typeof(x)) has no device sampler")
+
+function input_matrix(scenario_inputs::Vector{<:Vector}, columns::Vector{Symbol}, hidden::Vector{EbnInput})
+    S = length(scenario_inputs)
+    d = length(columns) + length(hidden)
+    M = Vector{EbnInput}(undef, S * d)
+    for (s, inputs) in enumerate(scenario_inputs)
+        byname = Dict(i.name => i for i in inputs)
+        for (j, c) in enumerate(columns)
+            haskey(byname, c) || error("limit state needs input $c which the node's parents do not provide")
+            M[(s-1)*d+j] = abi(byname[c])
+        end
+        for (j, h) in enumerate(hidden)
+            M[(s-1)*d+length(columns)+j] = h
+        end
+    end
+    return M, S, d
+end
+
+# ---- one call for all scenarios -------------------------------------------------------------------
+"Returns (fail_count, pf, var) for every scenario; replaces S calls of `probability_of_failure`."
+function pf_batch(model::CudaModel, scenario_inputs::Vector{<:Vector}, sim::CudaMonteCarlo;
+    hidden::Vector{EbnInput}=EbnInput[])
+    M, S, d = input_matrix(scenario_inputs, model.args, hidden)
+    consts = model.consts
+    counts = zeros(Int64, S)
+    pf = zeros(Float64, S)
+    var = zeros(Float64, S)
+    GC.@preserve M consts begin
+        job = Ref(EbnJob(EBN_LS[model.limit_state], length(consts), pointer(consts), S, d, pointer(M), sim.n,
+            sim.seed, sim.strict ? 1 : 0, 0, C_NULL, C_NULL, C_NULL, 0, 0, 0, 1))
+        check(ccall((:ebn_pf_batch, LIB[]), Cint, (Ref{EbnJob}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+            job, counts, pf, var))
+    end
+    return counts, pf, var
+end
+
+hidden_inputs(m::CudaModel) = m.limit_state == :straub_frame ? fill(abi(Normal(), -Inf, Inf), 5) : EbnInput[]
+
+# UQ.jl-style single-scenario entry (demo/vehicle_suspension.jl:68)
+function UncertaintyQuantification.probability_of_failure(models::Union{CudaModel,Vector{CudaModel}},
+    performance::Function, inputs::Vector{<:UQInput}, sim::CudaMonteCarlo)
+    model = models isa Vector ? models[end] : models
+    _, pf, var = pf_batch(model, [inputs], sim; hidden=hidden_inputs(model))
+    return pf[1], sqrt(var[1]), DataFrame()
+end
+
+# ---- `_evaluate_node` specialised on the simulation type ------------------------------------------
+# Same scenario enumeration, marshalling and CPT write-back as evaluate_node.jl:41-122; only the
+# scenario loop is replaced by one library call.
+function EnhancedBayesianNetworks._evaluate_node(net::EnhancedBayesianNetwork,
+    node::DiscreteFunctionalNode{<:Any}, collect_samples::Bool, sim::CudaMonteCarlo)
+    ancestors = discrete_ancestors(net, node)
+    combos = sort(vec(collect(Iterators.product(states.(ancestors)...))))
+    owner(s) = (hits = filter(n -> s ∈ states(n), ancestors); isempty(hits) ? node.name : hits[1].name)
+    evidences = isempty(combos[1]) ? [Evidence()] : map(c -> Evidence(owner(s) => s for s in c), combos)
+    cpt_names = isempty(combos[1]) ? [node.name] : vcat([a.name for a in ancestors], node.name)
+    cpt = DiscreteConditionalProbabilityTable{PreciseDiscreteProbability}(cpt_names)
+    scen = map(ev -> mapreduce(p -> _uq_inputs(p, ev), vcat, parents(net, node)[3]; init=UQInput[]), evidences)
+    model = node.models[end]::CudaModel
+    _, pf, var = pf_batch(model, scen, sim; hidden=hidden_inputs(model))
+    info = Dict{AbstractVector{Symbol},Dict}()
+    for (s, ev) in enumerate(evidences)
+        fail_ev = copy(ev); fail_ev[node.name] = Symbol(string(node.name) * "_fail")
+        safe_ev = copy(ev); safe_ev[node.name] = Symbol(string(node.name) * "_safe")
+        cpt[fail_ev] = pf[s]
+        cpt[safe_ev] = 1 - pf[s]
+        if collect_samples
+            # the n-row DataFrame cannot be materialised at 1e8+ samples: empty frame, replay with
+            # ebn_sample_matrix if rows are needed (INTEGRATION.md "samples")
+            info[collect(values(ev))] = Dict(:cov => sqrt(var[s]), :samples => DataFrame())
+        end
+    end
+    return DiscreteNode(node.name, cpt, node.parameters, info)
+end
+
+# dispatch hook: called from _evaluate_node(net, node::DiscreteFunctionalNode, collect_samples)
+# when `node.simulation isa CudaMonteCarlo` (one-line patch in evaluate_node.jl, see INTEGRATION.md)
+
+end # module
