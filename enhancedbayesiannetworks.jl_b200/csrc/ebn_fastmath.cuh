@@ -78,9 +78,11 @@ __device__ __forceinline__ double sqrt_pos(double t) {
   double h = 0.5 * y;
   double r = fma(-g, h, 0.5);
   g = fma(g, r, g);
+#ifndef EBN_SQRT_ONE_STEP
   h = fma(h, r, h);
   r = fma(-g, h, 0.5);
   g = fma(g, r, g);
+#endif
   return g;
 }
 

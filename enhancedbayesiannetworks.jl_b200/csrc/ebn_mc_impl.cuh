@@ -25,6 +25,10 @@ namespace ebn {
 #endif
 constexpr int kThreads = EBN_THREADS;
 constexpr int kWarps = kThreads / 32;
+#ifndef EBN_UNROLL
+#define EBN_UNROLL 1
+#endif
+constexpr int kPairUnroll = EBN_UNROLL;  // pairs per trip of the static count loop
 
 // Compile-time sampling plans ------------------------------------------------
 template <int... K>
@@ -133,6 +137,7 @@ __device__ __forceinline__ unsigned static_count_loop(const typename LS::Ctx& ct
   int64_t q = q_begin + tid;
   Philox4 nxt[NC];
   static_gen<Plan>(nxt, (uint32_t)q, (uint32_t)((uint64_t)q >> 32), pc);
+#pragma unroll kPairUnroll
   for (; q < q_end; q += kThreads) {
     Philox4 cur[NC];
 #pragma unroll

@@ -103,3 +103,44 @@ def straub_row():
 def w2_straub(n: int = 10**6, seed: int = 0x5EED0002, strict: bool = False) -> L.Job:
     """W2 = BASELINE config 1: Straub frame, S=1."""
     return L.Job(L.LS_STRAUB_FRAME, straub_consts(), L.make_inputs([straub_row()]), n, seed, strict)
+
+
+def w3_straub_copula(n: int = 10**9, seed: int = 0x5EED0003, bits: int = 6, strict: bool = False) -> L.Job:
+    """W3 = BASELINE config 3: synthetic Straub-style EBN, 2^bits discrete-parent scenarios, the seven
+    continuous inputs (r1..r5 ~ LogNormal(lambda, zeta), V ~ Gamma, H ~ Gumbel) joined by a Gaussian
+    copula with equicorrelation rho^2 = 0.3 among the r's (which is exactly the dependence the
+    common factor u_r induces in demo/straub_example.jl:16-26, so scenario 0 reproduces Straub's pf).
+    Each binary parent shifts the Gumbel location (odd bits) or the Gamma mean (even bits) by 2 %.
+    Limit state: the frame's three mechanisms as a min of affine forms of (r1..r5, V, H)."""
+    from .distributions import Gamma, table_for
+    lam, zeta = lognormal_params(150.0, 30.0)
+    d = 7
+    R = np.eye(d)
+    R[:5, :5] = STRAUB_RHO**2
+    np.fill_diagonal(R, 1.0)
+    chol = np.linalg.cholesky(R)
+    rows, tables, off = [], [], 0
+    for s in range(1 << bits):
+        mean_v, mean_h = 60.0, 50.0
+        for b in range(bits):
+            if (s >> b) & 1:
+                if b % 2:
+                    mean_h *= 1.02
+                else:
+                    mean_v *= 1.02
+        a, th = gamma_params(mean_v, 0.2 * mean_v)
+        mu, beta = gumbel_params(mean_h, 0.4 * mean_h)
+        q = table_for(Gamma(a, th), -INF, INF, 8193)   # Gamma under a copula is shipped tabulated
+        tables.append(q)
+        row = [(L.IN_LOGNORMAL, lam, zeta, 0, 0, -INF, INF)] * 5
+        row.append((L.IN_TABULATED, float(off), float(len(q)), 0, 0, -INF, INF))
+        row.append((L.IN_GUMBEL, mu, beta, 0, 0, -INF, INF))
+        off += len(q)
+        rows.append(row)
+    #            c0  r1 r2 r3 r4 r5  V   H
+    k = np.array([3.0,
+                  0, 1, 1, 0, 1, 1, 0, -5,      # g1 = r1 + r2 + r4 + r5 - 5h
+                  0, 0, 1, 2, 1, 0, -5, 0,      # g2 = r2 + 2 r3 + r4 - 5v
+                  0, 1, 0, 2, 2, 1, -5, -5.0])  # g3 = r1 + 2 r3 + 2 r4 + r5 - 5h - 5v
+    return L.Job(L.LS_MIN_AFFINE, k, L.make_inputs(rows), n, seed, strict, corr_chol=chol,
+                 tables=np.concatenate(tables))

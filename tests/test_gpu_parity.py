@@ -400,6 +400,104 @@ def test_errors(ebn):
 
 
 # ---------------------------------------------------------------------------
+# 7b. Gaussian copula (BASELINE config 3; UQ.jl JointDistribution + GaussianCopula)
+# ---------------------------------------------------------------------------
+COPULA_ROW = [
+    (0, 2.0, 0, 0, 0, -INF, INF),             # Parameter (identity row/col in L)
+    (1, 1.0, 2.0, 0, 0, -INF, INF),           # Normal
+    (2, 0.3, 0.25, 0, 0, -INF, INF),          # LogNormal
+    (3, 7.0, 12.0, 0, 0, -INF, INF),          # Uniform
+    (4, 41.0, 15.6, 0, 0, -INF, INF),         # Gumbel
+    (6, 2.0, 1.0, 3.0, 0, -INF, INF),         # 3 + Exponential(2)
+    (1, 0.0, 1.0, 0, 0, -1.0, 2.0),           # truncated Normal
+    (7, 0.0, 5.0, 0, 0, -INF, INF),           # tabulated
+]
+
+
+def _corr_chol(d, rho, fixed=(0,)):
+    R = np.full((d, d), rho)
+    np.fill_diagonal(R, 1.0)
+    for j in fixed:
+        R[j, :] = 0.0
+        R[:, j] = 0.0
+        R[j, j] = 1.0
+    return R, np.linalg.cholesky(R)
+
+
+def test_gaussian_copula_sampler_and_count(ebn):
+    from scipy import stats
+    d = len(COPULA_ROW)
+    R, Lc = _corr_chol(d, 0.3)
+    R2, Lc2 = _corr_chol(d, -0.1)
+    inputs = ebn.make_inputs([COPULA_ROW, COPULA_ROW])
+    n = 200_000
+    k = np.array([1.0, -75.0] + [1.0] * d)
+    job = ebn.Job(ebn._lib.LS_MIN_AFFINE, k, inputs, n=n, seed=99, strict=True, tables=TABLE,
+                  corr_chol=np.stack([Lc, Lc2]))
+    cnt, pf, _ = ebn.pf_batch(job)
+    for s, (Rs, Ls) in enumerate([(R, Lc), (R2, Lc2)]):
+        X = ebn.sample_matrix(job, s, 0, n)
+        ref = replay.copula_sample_matrix(inputs[s], Ls, s, 99, 0, n, tables=TABLE)
+        err = np.max(np.abs(X - ref) / np.maximum(np.abs(ref), 1.0), axis=0)
+        assert np.all(err < 1e-9), err
+        assert int(cnt[s]) == ocpu.eval_matrix(ocpu.LS_MIN_AFFINE, k, X)
+        # the dependence structure: normal scores of the marginals correlate like R
+        Z = stats.norm.ppf((stats.rankdata(X[:, 1:7], axis=0) - 0.5) / n)
+        C = np.corrcoef(Z.T)
+        assert np.max(np.abs(C - Rs[1:7, 1:7])) < 0.01
+        assert np.all(X[:, 0] == 2.0) and X[:, 6].min() >= -1.0 and X[:, 6].max() <= 2.0
+    assert 0 < cnt[0] < n and cnt[0] != cnt[1]
+    # one shared factor for all scenarios (EBN_JOB_COPULA_SHARED) == the same factor per scenario
+    job_sh = ebn.Job(ebn._lib.LS_MIN_AFFINE, k, inputs, n=n, seed=99, strict=True, tables=TABLE, corr_chol=Lc)
+    job_ps = ebn.Job(ebn._lib.LS_MIN_AFFINE, k, inputs, n=n, seed=99, strict=True, tables=TABLE,
+                     corr_chol=np.stack([Lc, Lc]))
+    assert np.array_equal(ebn.pf_batch(job_sh)[0], ebn.pf_batch(job_ps)[0])
+    # marginals keep their laws under the copula
+    Xs = ebn.sample_matrix(job_sh, 0, 0, n)
+    for j, dist in {1: stats.norm(1, 2), 3: stats.uniform(7, 5), 4: stats.gumbel_r(41.0, 15.6), 5: stats.expon(3, 2)}.items():
+        assert stats.kstest(Xs[:, j], dist.cdf).pvalue > 1e-4, j
+    # a factor that is not a Cholesky factor of a correlation matrix is rejected
+    bad = Lc.copy()
+    bad[2, 2] = 2.0
+    with pytest.raises(ebn.EbnError, match="EBN_EINVAL.*diagonal"):
+        ebn.pf_batch(ebn.Job(ebn._lib.LS_MIN_AFFINE, k, inputs, n=n, seed=99, tables=TABLE, corr_chol=bad))
+    # Gamma under a copula must come tabulated
+    rows = [[(5, 25.0, 2.4, 0, 0, -INF, INF), (1, 0.0, 1.0, 0, 0, -INF, INF)]]
+    with pytest.raises(ebn.EbnError, match="EBN_EMARGINAL.*TABULATED"):
+        ebn.pf_batch(ebn.Job(ebn._lib.LS_MIN_AFFINE, np.array([1.0, 0.0, 1.0, 1.0]), ebn.make_inputs(rows), n=100,
+                             corr_chol=np.eye(2)))
+
+
+def test_w3_straub_copula_and_w5_grid(ebn):
+    """BASELINE configs 3 and 5 at test size."""
+    from ebn_b200 import workloads as W
+    n = 1_000_000
+    job = W.w3_straub_copula(n=n, bits=3, strict=True)
+    cnt, pf, var = ebn.pf_batch(job)
+    assert job.S == 8
+    # scenario 0 has Straub's dependence structure exactly: same pf as the straub_frame functor
+    ref_cnt, ref_pf, ref_var = ebn.pf_batch(W.w2_straub(n=n))
+    assert abs(pf[0] - ref_pf[0]) < 3 * math.sqrt(var[0] + ref_var[0]) + 3e-4   # + table interpolation
+    assert abs(pf[0] - 0.026129) < 0.01
+    assert pf[0b101] > pf[0] and pf[0b010] > pf[0]      # heavier loads fail more often
+    for s in (0, 5):
+        X = ebn.sample_matrix(job, s, 0, 100_000)
+        ref = replay.copula_sample_matrix(job.inputs[s], job.corr_chol, s, job.seed, 0, 100_000, tables=job.tables)
+        assert np.max(np.abs(X - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-9
+    X = ebn.sample_matrix(job, 3, 0, n)
+    assert int(cnt[3]) == ocpu.eval_matrix(ocpu.LS_MIN_AFFINE, job.consts, X)
+    # W5: 1024 scenarios on the (A, b0) grid; pf grows with A and falls with b0
+    j5 = W.w5_vehicle_grid(n=200_000, strict=True)
+    c5, p5, _ = ebn.pf_batch(j5)
+    assert j5.S == 1024 and ebn.last_stats()["specialised"] == 1
+    G = p5.reshape(32, 32)
+    assert G[31, 0] > 0.5 and G[0, 31] < 1e-3 and np.all(np.diff(G[:, 0]) > -0.01) and np.all(np.diff(G[31, :]) < 0.01)
+    for s in (0, 517, 1023):
+        X = ebn.sample_matrix(j5, s, 0, 200_000)
+        assert int(c5[s]) == ocpu.eval_matrix(ocpu.LS_VEHICLE, j5.consts, X)
+
+
+# ---------------------------------------------------------------------------
 # 8. committed golden fixtures (tests/golden/, made by make_golden.py)
 # ---------------------------------------------------------------------------
 def test_golden_fixtures(ebn):

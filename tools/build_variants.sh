@@ -3,9 +3,10 @@
 # enhancedbayesiannetworks.jl_b200/tune/. Usage: tools/build_variants.sh "256,4 128,6 ..."
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
+mkdir -p $ROOT/enhancedbayesiannetworks.jl_b200/tune
 for v in $1; do
   T=${v%,*}; B=${v#*,}
-  D=/tmp/ebn_variant_${T}_${B}
+  D=/tmp/ebn_variant_${T}_${B}${SUFFIX}
   rm -rf $D && mkdir -p $D/pkg/csrc $D/include && cp $ROOT/enhancedbayesiannetworks.jl_b200/csrc/*.cu* $ROOT/enhancedbayesiannetworks.jl_b200/csrc/*.h $ROOT/enhancedbayesiannetworks.jl_b200/csrc/*.inc $ROOT/enhancedbayesiannetworks.jl_b200/csrc/Makefile $D/pkg/csrc/ && cp $ROOT/include/ebncuda.h $D/include/
   (cd $D/pkg/csrc && make -j8 EXTRA="-DEBN_THREADS=$T -DEBN_MIN_BLOCKS=$B $EXTRA_FLAGS" OUT=$ROOT/enhancedbayesiannetworks.jl_b200/tune/libebncuda_${T}_${B}${SUFFIX}.so > /dev/null 2>&1) &
 done
