@@ -238,8 +238,11 @@ int canonicalise(const ebn_input_t& in, bool copula, DevInput& o, int s, int j,
       o.kind = DK_GAMMA_MT;
       o.a = in.p[0];
       o.b = in.p[1];
-      o.c = 0.0;
-      o.d = 1.0;
+      {  // Marsaglia-Tsang constants: d = shape' - 1/3, c = 1/sqrt(9 d), shape' = shape (+1 if < 1)
+        const double sh = in.p[0] < 1.0 ? in.p[0] + 1.0 : in.p[0];
+        o.c = sh - 1.0 / 3.0;
+        o.d = 1.0 / sqrt(9.0 * o.c);
+      }
       return EBN_OK;
     }
     case EBN_IN_TABULATED: {

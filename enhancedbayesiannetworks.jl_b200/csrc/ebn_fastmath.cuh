@@ -24,22 +24,30 @@ struct FastMathConst {
   double cosc[10];
   double ln1p[5];   // -1/2, 1/3, -1/4, 1/5, -1/6  (negated for -ln)
   double ln2;
+  double expc[4];   // 1/2, 1/6, 1/24, 1/120
+  double inv_ln2_64, ln2_64_hi, ln2_64_lo;
 };
 __constant__ FastMathConst kFm = {
     {EBN_SIN_COEFS},
     {EBN_COS_COEFS},
     {0.5, -0.33333333333333331483, 0.25, -0.2000000000000000111, 0.16666666666666665741},
     0.69314718055994528623,
+    {0.5, 0.16666666666666665741, 0.041666666666666664354, 0.0083333333333333332177},
+    92.332482616893656877,          // 64/ln2
+    0x1.62e42fef00000p-7,           // ln2/64, high 33 bits (n * hi is exact for |n| < 2^20)
+    0x1.473de6af278edp-40,          // ln2/64 - high part
 };
 
 // Shared-memory copy of the log table (per-lane random index: shared memory,
 // not the constant cache, which serialises divergent addresses).
 struct FastMathSmem {
   double2 logtab[128];
+  double exptab[64];
 };
 
 __device__ __forceinline__ void fastmath_init(FastMathSmem& sm, int tid, int nthreads) {
   for (int i = tid; i < 128; i += nthreads) sm.logtab[i] = kLogTab[i];
+  for (int i = tid; i < 64; i += nthreads) sm.exptab[i] = kExpTab[i];
 }
 
 // -ln(u) for a normal double u in (0,1).
@@ -68,6 +76,45 @@ __device__ __forceinline__ double neg_log01(double u, const FastMathSmem& sm) {
   const double r2 = r * r;
   const double base = fma(ned, kFm.ln2, t.y);   // -e*ln2 + ln(rc)
   return fma(r2, p, base - r);                   // ... - r + r^2*(...)
+}
+
+// -ln(t) for any positive normal double t (the exponent may have either sign).
+__device__ __forceinline__ double neg_log_pos(double t, const FastMathSmem& sm) {
+  const int hi = __double2hiint(t);
+  const int lo = __double2loint(t);
+  const int ne = 1023 - (hi >> 20);
+  const int mhi = (hi & 0x000FFFFF) | 0x3FF00000;
+  const int idx = (hi >> 13) & 0x7F;
+  const double m = __hiloint2double(mhi, lo);
+  const double2 tb = sm.logtab[idx];
+  const double r = fma(m, tb.x, -1.0);
+  // signed int -> double: bias by 2^31 inside the 2^52+2^51 magic
+  const double ned = __hiloint2double(0x43380000, ne ^ (int)0x80000000) - 6755401588539392.0;
+  double p = fma(r, kFm.ln1p[4], kFm.ln1p[3]);
+  p = fma(r, p, kFm.ln1p[2]);
+  p = fma(r, p, kFm.ln1p[1]);
+  p = fma(r, p, kFm.ln1p[0]);
+  const double r2 = r * r;
+  const double base = fma(ned, kFm.ln2, tb.y);
+  return fma(r2, p, base - r);
+}
+
+// exp(x) for |x| < 700 (no overflow/underflow handling: the callers exponentiate
+// log-normal scores). x = (64 k + j) ln2/64 + r, |r| <= ln2/128:
+//   exp(x) = 2^k * 2^(j/64) * (1 + r + r^2/2 + ... + r^5/120),  ~1 ulp.
+__device__ __forceinline__ double exp_fast(double x, const FastMathSmem& sm) {
+  const double t = fma(x, kFm.inv_ln2_64, 6755399441055744.0);   // round to nearest integer n
+  const int n = __double2loint(t);
+  const double nd = t - 6755399441055744.0;
+  double r = fma(-nd, kFm.ln2_64_hi, x);
+  r = fma(-nd, kFm.ln2_64_lo, r);
+  const double s = sm.exptab[n & 63];
+  double p = fma(r, kFm.expc[3], kFm.expc[2]);
+  p = fma(r, p, kFm.expc[1]);
+  p = fma(r, p, kFm.expc[0]);
+  p = fma(r * r, p, r);                 // e^r - 1
+  const double y = fma(s, p, s);
+  return __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
 }
 
 // sqrt(t) for t in [2^-60, 2^60]: MUFU.RSQ64H seed + two coupled Newton steps.

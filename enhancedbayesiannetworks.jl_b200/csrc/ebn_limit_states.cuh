@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "../../include/ebncuda.h"
+#include "ebn_fastmath.cuh"
 
 namespace ebn {
 
@@ -52,13 +53,14 @@ struct VehicleSuspension {
   static constexpr int XCAP = 6; // columns held per sample
   static constexpr int NC = 5;
   static constexpr bool HAS_FAILS = !Ops::strict;  // sign-only test in fast mode
+  static constexpr int MIN_BLOCKS = 3;             // blocks of 256 threads per SM (register budget 80)
   struct Ctx {
     double M, m, gg, pow_a, pow_b;     // strict
     double pim, mM, iM, imM, immM, mpM, Mg;
     double k1, k2, k3, k4;             // fast
     double thr2, c3;                   // fast, sign-only
   };
-  __device__ static void setup(Ctx& c, const double* k, int, int) {
+  __device__ static void setup(Ctx& c, const double* k, int, int, const FastMathSmem*) {
     const double M = k[0], m = k[1], g = k[2];
     c.M = M;
     c.m = m;
@@ -157,13 +159,19 @@ template <class Ops>
 struct StraubFrame {
   static constexpr int ID = EBN_LS_STRAUB_FRAME;
   static constexpr bool HAS_FAILS = false;
+#ifndef EBN_STRAUB_BLOCKS
+#define EBN_STRAUB_BLOCKS 2
+#endif
+  static constexpr int MIN_BLOCKS = EBN_STRAUB_BLOCKS;
   static constexpr int D = 8;
   static constexpr int XCAP = 8;
   static constexpr int NC = 3;
   struct Ctx {
     double lambda, rz, sd;
+    const FastMathSmem* fm;
   };
-  __device__ static void setup(Ctx& c, const double* k, int, int) {
+  __device__ static void setup(Ctx& c, const double* k, int, int, const FastMathSmem* fm) {
+    c.fm = fm;
     const double lambda = k[0], zeta = k[1], rho = k[2];
     c.lambda = lambda;
     c.rz = __dmul_rn(rho, zeta);  // rho * zeta (then * u_r)
@@ -175,7 +183,10 @@ struct StraubFrame {
     const double mu = Ops::add(c.lambda, Ops::mul(c.rz, ur));
     double r[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) r[i] = exp(Ops::add(mu, Ops::mul(c.sd, x[3 + i])));
+    for (int i = 0; i < 5; ++i) {
+      const double a = Ops::add(mu, Ops::mul(c.sd, x[3 + i]));
+      r[i] = Ops::strict ? exp(a) : exp_fast(a, *c.fm);   // strict: libdevice exp (< 1 ulp, like Julia's)
+    }
     const double h5 = Ops::mul(5.0, h), v5 = Ops::mul(5.0, v);
     const double g1 = Ops::sub(Ops::add(Ops::add(Ops::add(r[0], r[1]), r[3]), r[4]), h5);
     const double g2 = Ops::sub(Ops::add(Ops::add(r[1], Ops::mul(2.0, r[2])), r[3]), v5);
@@ -196,11 +207,12 @@ template <class Ops>
 struct HydrogenRadius {
   static constexpr int ID = EBN_LS_HYDROGEN_RADIUS;
   static constexpr bool HAS_FAILS = false;
+  static constexpr int MIN_BLOCKS = 3;
   static constexpr int D = 4;
   static constexpr int XCAP = 4;
   static constexpr int NC = 0;
   struct Ctx {};
-  __device__ static void setup(Ctx&, const double*, int, int) {}
+  __device__ static void setup(Ctx&, const double*, int, int, const FastMathSmem*) {}
   __device__ __forceinline__ static double eval(const Ctx&, const double* x) {
     const double sc = x[0];
     if (sc == 1.0) return Ops::sub(x[1], x[2]);
@@ -219,6 +231,7 @@ template <class Ops>
 struct PolynomialProgram {
   static constexpr int ID = EBN_LS_POLYNOMIAL;
   static constexpr bool HAS_FAILS = false;
+  static constexpr int MIN_BLOCKS = 3;
   static constexpr int D = -1;  // variadic
   static constexpr int XCAP = EBN_MAX_INPUTS;
   static constexpr int NC = -1;
@@ -226,7 +239,7 @@ struct PolynomialProgram {
     const double* prog;
     int d;
   };
-  __device__ static void setup(Ctx& c, const double* k, int, int d) {
+  __device__ static void setup(Ctx& c, const double* k, int, int d, const FastMathSmem*) {
     c.prog = k;
     c.d = d;
   }
@@ -261,6 +274,7 @@ template <class Ops>
 struct MinAffine {
   static constexpr int ID = EBN_LS_MIN_AFFINE;
   static constexpr bool HAS_FAILS = false;
+  static constexpr int MIN_BLOCKS = 3;
   static constexpr int D = -1;
   static constexpr int XCAP = EBN_MAX_INPUTS;
   static constexpr int NC = -1;
@@ -268,7 +282,7 @@ struct MinAffine {
     const double* k;
     int d;
   };
-  __device__ static void setup(Ctx& c, const double* k, int, int d) {
+  __device__ static void setup(Ctx& c, const double* k, int, int d, const FastMathSmem*) {
     c.k = k;
     c.d = d;
   }

@@ -174,7 +174,7 @@ __device__ __forceinline__ int find_bin(const double* edges, int nedges, double 
 
 // MODE 0: failure count. MODE 1: histogram + moments of the output.
 template <class LS, class Plan, int MODE>
-__global__ void __launch_bounds__(kThreads, EBN_MIN_BLOCKS) mc_kernel(const McParams p) {
+__global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McParams p) {
   constexpr int XCAP = LS::XCAP;
   __shared__ FastMathSmem s_fm;
   __shared__ DevInput s_plan[EBN_MAX_INPUTS];
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, EBN_MIN_BLOCKS) mc_kernel(const McPa
   unsigned int* s_bins = reinterpret_cast<unsigned int*>(s_dyn + sizeof(double) * (MODE == 1 ? p.nedges : 0));
 
   typename LS::Ctx ctx;
-  LS::setup(ctx, p.consts, p.n_consts, p.d);
+  LS::setup(ctx, p.consts, p.n_consts, p.d, &s_fm);
 
   const int tid = threadIdx.x;
   fastmath_init(s_fm, tid, kThreads);
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
   __shared__ DevInput s_plan[EBN_MAX_INPUTS];
   __shared__ double s_chol[std::is_same<Plan, CopulaPlan>::value ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
   typename LS::Ctx ctx;
-  LS::setup(ctx, p.consts, p.n_consts, p.d);
+  LS::setup(ctx, p.consts, p.n_consts, p.d, &s_fm);
   fastmath_init(s_fm, threadIdx.x, kThreads);
   if (threadIdx.x < p.d) s_plan[threadIdx.x] = p.plan[(int64_t)scenario * p.d + threadIdx.x];
   if (std::is_same<Plan, CopulaPlan>::value) {
@@ -363,8 +363,11 @@ __global__ void __launch_bounds__(kThreads) matrix_kernel(const double* consts, 
                                                           double* g_out) {
   constexpr int XCAP = LS::XCAP;
   __shared__ unsigned int s_red[kWarps];
+  __shared__ FastMathSmem s_fm;
   typename LS::Ctx ctx;
-  LS::setup(ctx, consts, n_consts, d);
+  LS::setup(ctx, consts, n_consts, d, &s_fm);
+  fastmath_init(s_fm, threadIdx.x, kThreads);
+  __syncthreads();
   unsigned int cnt = 0;
   for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < n;
        r += (int64_t)gridDim.x * kThreads) {

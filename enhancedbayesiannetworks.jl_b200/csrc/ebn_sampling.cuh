@@ -78,14 +78,21 @@ struct DynWords {
 // e of input j reads its own Philox call, counter word 3 =
 // 0x80000000 | j<<16 | e<<15 | t: normal from (w0,w1,w2) (first Box-Muller
 // output), acceptance uniform from w3. The boost uniform is call t = 0x7fff.
+// in.c = d = shape' - 1/3 and in.d = c = 1/sqrt(9 d) are precomputed on the host.
+static __device__ __noinline__ double gamma_boost(const DevInput& in, const PairCtr& pc,
+                                                  uint32_t base) {
+  const Philox4 w = philox4x32_10(pc.qlo, pc.qhi, pc.stream, base | 0x7FFFu, pc.k0, pc.k1);
+  return pow(u52w(w.w0, w.w1), 1.0 / in.a);
+}
+
 static __device__ __noinline__ double gamma_mt(const DevInput& in, const PairCtr& pc, uint32_t j,
                                                uint32_t e, const FastMathSmem& sm) {
   const double shape = in.a;
-  const double a = shape < 1.0 ? shape + 1.0 : shape;
-  const double dd = a - 1.0 / 3.0;
-  const double cc = 1.0 / sqrt(9.0 * dd);
+  const double dd = in.c;
+  const double cc = in.d;
   const uint32_t base = 0x80000000u | (j << 16) | (e << 15);
   double v = 1.0;
+#pragma unroll 1
   for (uint32_t t = 0; t < 64u; ++t) {
     const Philox4 w = philox4x32_10(pc.qlo, pc.qhi, pc.stream, base | t, pc.k0, pc.k1);
     double z, z_unused;
@@ -96,13 +103,10 @@ static __device__ __noinline__ double gamma_mt(const DevInput& in, const PairCtr
     const double u = u32w(w.w3);
     const double z2 = z * z;
     if (u < 1.0 - 0.0331 * z2 * z2) break;
-    if (log(u) < 0.5 * z2 + dd * (1.0 - v + log(v))) break;
+    if (-neg_log01(u, sm) < 0.5 * z2 + dd * (1.0 - v - neg_log_pos(v, sm))) break;
   }
   double x = dd * v;
-  if (shape < 1.0) {
-    const Philox4 w = philox4x32_10(pc.qlo, pc.qhi, pc.stream, base | 0x7FFFu, pc.k0, pc.k1);
-    x *= pow(u52w(w.w0, w.w1), 1.0 / shape);
-  }
+  if (shape < 1.0) x *= gamma_boost(in, pc, base);
   return x * in.b;
 }
 
@@ -120,11 +124,12 @@ __device__ __forceinline__ double table_quantile(const DevInput& in, const doubl
 // x = Q(u') for the inverse-CDF kinds, u' = c + u*d already mapped into the
 // truncation window.
 template <int KIND>
-__device__ __forceinline__ double icdf(const DevInput& in, const double* tables, double u) {
+__device__ __forceinline__ double icdf(const DevInput& in, const double* tables,
+                                       const FastMathSmem& sm, double u) {
   const double up = fma(u, in.d, in.c);
   if (KIND == DK_NORMAL_ICDF) return fma(normcdfinv(up), in.b, in.a);
-  if (KIND == DK_LOGNORMAL_ICDF) return exp(fma(normcdfinv(up), in.b, in.a));
-  if (KIND == DK_GUMBEL) return in.a - in.b * log(-log(up));
+  if (KIND == DK_LOGNORMAL_ICDF) return exp_fast(fma(normcdfinv(up), in.b, in.a), sm);
+  if (KIND == DK_GUMBEL) return fma(in.b, neg_log_pos(neg_log01(up, sm), sm), in.a);  // a - b ln(-ln u)
   if (KIND == DK_EXP_AFFINE) return in.a - in.b * log1p(-up);
   return table_quantile(in, tables, up);
 }
@@ -147,15 +152,15 @@ __device__ __forceinline__ void draw_pair(const DevInput& in, const WS& ws, cons
     x0 = fma(z0, in.b, in.a);
     x1 = fma(z1, in.b, in.a);
     if (KIND == DK_LOGNORMAL_BM) {
-      x0 = exp(x0);
-      x1 = exp(x1);
+      x0 = exp_fast(x0, sm);
+      x1 = exp_fast(x1, sm);
     }
   } else if (KIND == DK_GAMMA_MT) {
     x0 = gamma_mt(in, pc, j, 0u, sm);
     x1 = gamma_mt(in, pc, j, 1u, sm);
   } else {
-    x0 = icdf<KIND>(in, tables, u52w(ws.template w<0>(), ws.template w<1>()));
-    x1 = icdf<KIND>(in, tables, u52w(ws.template w<2>(), ws.template w<3>()));
+    x0 = icdf<KIND>(in, tables, sm, u52w(ws.template w<0>(), ws.template w<1>()));
+    x1 = icdf<KIND>(in, tables, sm, u52w(ws.template w<2>(), ws.template w<3>()));
   }
 }
 
@@ -225,32 +230,32 @@ static __device__ __noinline__ void draw_pair_copula(const DevInput* plan, const
         a1 = fma(z1, in.b, in.a);
         break;
       case DK_LOGNORMAL_BM:
-        a0 = exp(fma(z0, in.b, in.a));
-        a1 = exp(fma(z1, in.b, in.a));
+        a0 = exp_fast(fma(z0, in.b, in.a), sm);
+        a1 = exp_fast(fma(z1, in.b, in.a), sm);
         break;
       case DK_UNIFORM:
         a0 = fma(phi_clamped(z0), in.b, in.a);
         a1 = fma(phi_clamped(z1), in.b, in.a);
         break;
       case DK_NORMAL_ICDF:
-        a0 = icdf<DK_NORMAL_ICDF>(in, tables, phi_clamped(z0));
-        a1 = icdf<DK_NORMAL_ICDF>(in, tables, phi_clamped(z1));
+        a0 = icdf<DK_NORMAL_ICDF>(in, tables, sm, phi_clamped(z0));
+        a1 = icdf<DK_NORMAL_ICDF>(in, tables, sm, phi_clamped(z1));
         break;
       case DK_LOGNORMAL_ICDF:
-        a0 = icdf<DK_LOGNORMAL_ICDF>(in, tables, phi_clamped(z0));
-        a1 = icdf<DK_LOGNORMAL_ICDF>(in, tables, phi_clamped(z1));
+        a0 = icdf<DK_LOGNORMAL_ICDF>(in, tables, sm, phi_clamped(z0));
+        a1 = icdf<DK_LOGNORMAL_ICDF>(in, tables, sm, phi_clamped(z1));
         break;
       case DK_GUMBEL:
-        a0 = icdf<DK_GUMBEL>(in, tables, phi_clamped(z0));
-        a1 = icdf<DK_GUMBEL>(in, tables, phi_clamped(z1));
+        a0 = icdf<DK_GUMBEL>(in, tables, sm, phi_clamped(z0));
+        a1 = icdf<DK_GUMBEL>(in, tables, sm, phi_clamped(z1));
         break;
       case DK_EXP_AFFINE:
-        a0 = icdf<DK_EXP_AFFINE>(in, tables, phi_clamped(z0));
-        a1 = icdf<DK_EXP_AFFINE>(in, tables, phi_clamped(z1));
+        a0 = icdf<DK_EXP_AFFINE>(in, tables, sm, phi_clamped(z0));
+        a1 = icdf<DK_EXP_AFFINE>(in, tables, sm, phi_clamped(z1));
         break;
       default:  // DK_TABLE (Gamma under a copula is tabulated by the caller)
-        a0 = icdf<DK_TABLE>(in, tables, phi_clamped(z0));
-        a1 = icdf<DK_TABLE>(in, tables, phi_clamped(z1));
+        a0 = icdf<DK_TABLE>(in, tables, sm, phi_clamped(z0));
+        a1 = icdf<DK_TABLE>(in, tables, sm, phi_clamped(z1));
         break;
     }
     x0[j] = a0;

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) comp(unsigned long long* out, const doubl
   __syncthreads();
   using LS = VehicleSuspension<FastOps>;
   typename LS::Ctx ctx;
-  LS::setup(ctx, consts, 5, 6);
+  LS::setup(ctx, consts, 5, 6, &s_fm);
   unsigned cnt = 0;
   const long long q0 = ((long long)blockIdx.x * 256 + threadIdx.x) * pairs_per_thread;
   for (long long q = q0; q < q0 + pairs_per_thread; ++q) {
