@@ -173,7 +173,7 @@ int canonicalise(const ebn_input_t& in, bool copula, DevInput& o, int s, int j,
       o.kind = DK_UNIFORM;
       o.a = a;
       o.b = b - a;
-      o.c = 0.0;
+      o.c = a - (b - a) * (1.0 - 0x1p-33);  // x = fma(d, b, c) for the raw [1,2) double d
       o.d = 1.0;
       return EBN_OK;
     }

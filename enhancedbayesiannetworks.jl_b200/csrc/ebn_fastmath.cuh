@@ -20,8 +20,8 @@ namespace ebn {
 #include "ebn_fastmath_tables.inc"
 
 struct FastMathConst {
-  double sinc[9];
-  double cosc[10];
+  double sinc[7];
+  double cosc[8];
   double ln1p[5];   // -1/2, 1/3, -1/4, 1/5, -1/6  (negated for -ln)
   double ln2;
   double expc[4];   // 1/2, 1/6, 1/24, 1/120
@@ -148,12 +148,12 @@ __device__ __forceinline__ double rcp_normal(double x) {
 // sqrt(2)*(sin, cos) of the first-quadrant angle (pi/2)*(v + 1/2).
 __device__ __forceinline__ void sincos_quadrant(double v, double& cps, double& cms) {
   const double w = v * v;
-  double s = fma(w, kFm.sinc[7], kFm.sinc[6]);
-  double c = fma(w, kFm.cosc[8], kFm.cosc[7]);
+  double s = fma(w, kFm.sinc[6], kFm.sinc[5]);
+  double c = fma(w, kFm.cosc[7], kFm.cosc[6]);
 #pragma unroll
-  for (int i = 5; i >= 0; --i) s = fma(w, s, kFm.sinc[i]);
+  for (int i = 4; i >= 0; --i) s = fma(w, s, kFm.sinc[i]);
 #pragma unroll
-  for (int i = 6; i >= 0; --i) c = fma(w, c, kFm.cosc[i]);
+  for (int i = 5; i >= 0; --i) c = fma(w, c, kFm.cosc[i]);
   s *= v;
   cps = c + s;
   cms = c - s;
@@ -165,20 +165,55 @@ __device__ __forceinline__ void sincos_quadrant(double v, double& cps, double& c
 //   signs   bits 31 and 30 of w1
 // z0 = s0*R*sin(phi), z1 = s1*R*cos(phi) with R = sqrt(-2 ln u), phi uniform in (0, pi/2):
 // a uniformly random direction, so (z0, z1) are independent standard normals.
-__device__ __forceinline__ void box_muller_words(uint32_t w0, uint32_t w1, uint32_t w2,
-                                                 const FastMathSmem& sm, double& z0, double& z1) {
+//
+// Split in two so that the count loop can software-pipeline it: the FRONT end (integer bit
+// placement, the table load and the two fp64 operations that consume it) runs one pair ahead,
+// next to the Philox rounds, and hides the shared-memory latency; the BACK end is pure fp64.
+struct BmFront {
+  double r;       // m*rc - 1 of the -ln(u) reduction
+  double base;    // -e*ln2 + ln(rc)
+  uint32_t w1;    // sign bits
+  uint32_t w2;    // angle word
+};
+
+__device__ __forceinline__ BmFront box_muller_front(uint32_t w0, uint32_t w1, uint32_t w2,
+                                                    const FastMathSmem& sm) {
   // Mask-only bit placement (one LOP3 per word half, no shifts: the integer ALU is the
   // scarce pipe next to the fp64 pipe): the low 20 bits of a word become the high mantissa bits.
   const double u = __hiloint2double((int)((w1 & 0x000FFFFFu) | 0x3FF00000u), (int)w0) - 0x1.fffffffffffffp-1;
-  const double v = __hiloint2double((int)((w2 & 0x000FFFFFu) | 0x3FF00000u), (int)(w2 & 0xFFF00000u)) -
-                   (1.5 - 0x1p-33);  // [-1/2, 1/2), centred
-  const double rr = sqrt_pos(neg_log01(u, sm));  // sqrt(-ln u) = R / sqrt(2)
+  const int hi = __double2hiint(u);
+  const int ne = 1023 - (hi >> 20);
+  const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(u));
+  const double2 t = sm.logtab[(hi >> 13) & 0x7F];
+  BmFront f;
+  f.r = fma(m, t.x, -1.0);
+  f.base = fma(__hiloint2double(0x43380000, ne) - 6755399441055744.0, kFm.ln2, t.y);
+  f.w1 = w1;
+  f.w2 = w2;
+  return f;
+}
+
+__device__ __forceinline__ void box_muller_back(const BmFront& f, double& z0, double& z1) {
+  const double r = f.r;
+  double p = fma(r, kFm.ln1p[4], kFm.ln1p[3]);
+  p = fma(r, p, kFm.ln1p[2]);
+  p = fma(r, p, kFm.ln1p[1]);
+  p = fma(r, p, kFm.ln1p[0]);
+  const double t = fma(r * r, p, f.base - r);          // -ln u
+  const double v = __hiloint2double((int)((f.w2 & 0x000FFFFFu) | 0x3FF00000u), (int)(f.w2 & 0xFFF00000u)) -
+                   (1.5 - 0x1p-33);                     // [-1/2, 1/2), centred
+  const double rr = sqrt_pos(t);                        // sqrt(-ln u) = R / sqrt(2)
   double cps, cms;
   sincos_quadrant(v, cps, cms);
   const double a = rr * cps;  // R*sin(phi)
   const double b = rr * cms;  // R*cos(phi)
-  z0 = __hiloint2double(__double2hiint(a) ^ (int)(w1 & 0x80000000u), __double2loint(a));
-  z1 = __hiloint2double(__double2hiint(b) ^ (int)((w1 << 1) & 0x80000000u), __double2loint(b));
+  z0 = __hiloint2double(__double2hiint(a) ^ (int)(f.w1 & 0x80000000u), __double2loint(a));
+  z1 = __hiloint2double(__double2hiint(b) ^ (int)((f.w1 << 1) & 0x80000000u), __double2loint(b));
+}
+
+__device__ __forceinline__ void box_muller_words(uint32_t w0, uint32_t w1, uint32_t w2,
+                                                 const FastMathSmem& sm, double& z0, double& z1) {
+  box_muller_back(box_muller_front(w0, w1, w2, sm), z0, z1);
 }
 
 }  // namespace ebn

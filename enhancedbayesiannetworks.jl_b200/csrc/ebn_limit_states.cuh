@@ -53,7 +53,10 @@ struct VehicleSuspension {
   static constexpr int XCAP = 6; // columns held per sample
   static constexpr int NC = 5;
   static constexpr bool HAS_FAILS = !Ops::strict;  // sign-only test in fast mode
-  static constexpr int MIN_BLOCKS = 3;             // blocks of 256 threads per SM (register budget 80)
+#ifndef EBN_VEHICLE_BLOCKS
+#define EBN_VEHICLE_BLOCKS 2
+#endif
+  static constexpr int MIN_BLOCKS = EBN_VEHICLE_BLOCKS;  // blocks of 256 threads per SM: 128 registers, no spills; throughput is issue-bound, not occupancy-bound
   struct Ctx {
     double M, m, gg, pow_a, pow_b;     // strict
     double pim, mM, iM, imM, immM, mpM, Mg;

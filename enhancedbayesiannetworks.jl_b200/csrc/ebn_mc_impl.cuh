@@ -119,12 +119,36 @@ __device__ __forceinline__ bool sample_fails(const typename LS::Ctx& ctx, double
   }
 }
 
-// Count loop of one work item for a static plan, software-pipelined: the Philox
-// words of the NEXT pair are generated while the current pair goes through the
-// fp64 transforms and the limit state. The integer stream (ALU / IMAD.WIDE) and
-// the fp64 stream then sit in the same basic block and ptxas interleaves them;
-// without this, warps convoy through an all-integer phase and an all-fp64 phase
-// and the two pipes never overlap (profiles/r01_b_*, tools/microbench).
+// Front / back halves of a static plan (see InState).
+template <class Plan, int J>
+struct FrontAll {
+  __device__ __forceinline__ static void run(const Philox4* ph, const FastMathSmem& sm, InState* st) {
+    if constexpr (J < Plan::n) {
+      StaticWords<static_word_offset<Plan, J>()> ws{ph};
+      st[J] = draw_front<Plan::kinds[J]>(ws, sm);
+      FrontAll<Plan, J + 1>::run(ph, sm, st);
+    }
+  }
+};
+template <class Plan, int J>
+struct BackAll {
+  __device__ __forceinline__ static void run(const DevInput* sp, const InState* st, const PairCtr& pc,
+                                             const double* tables, const FastMathSmem& sm,
+                                             double* x0, double* x1) {
+    if constexpr (J < Plan::n) {
+      draw_back<Plan::kinds[J]>(sp[J], st[J], pc, (uint32_t)J, tables, sm, x0[J], x1[J]);
+      BackAll<Plan, J + 1>::run(sp, st, pc, tables, sm, x0, x1);
+    }
+  }
+};
+
+// Count loop of one work item for a static plan, software-pipelined: the Philox words of the
+// NEXT pair are generated and pushed through the front end of every input (bit placement,
+// table loads) while the current pair goes through the fp64 back end and the limit state.
+// The integer stream (ALU / IMAD.WIDE) and the fp64 stream then sit in the same basic block and
+// ptxas interleaves them; without this, warps convoy through an all-integer phase and an
+// all-fp64 phase (profiles/r01_b_*, tools/microbench), and the shared-memory latency of the
+// log table is exposed.
 // CHECK = the item touches the [first, last) boundary and samples must be masked.
 template <class LS, class Plan, bool CHECK>
 __device__ __forceinline__ unsigned static_count_loop(const typename LS::Ctx& ctx,
@@ -135,19 +159,27 @@ __device__ __forceinline__ unsigned static_count_loop(const typename LS::Ctx& ct
   constexpr int NC = static_calls<Plan>() > 0 ? static_calls<Plan>() : 1;
   unsigned cnt = 0;
   int64_t q = q_begin + tid;
-  Philox4 nxt[NC];
-  static_gen<Plan>(nxt, (uint32_t)q, (uint32_t)((uint64_t)q >> 32), pc);
+  InState nxt[Plan::n];
+  {
+    Philox4 ph[NC];
+    static_gen<Plan>(ph, (uint32_t)q, (uint32_t)((uint64_t)q >> 32), pc);
+    FrontAll<Plan, 0>::run(ph, sm, nxt);
+  }
 #pragma unroll kPairUnroll
   for (; q < q_end; q += kThreads) {
-    Philox4 cur[NC];
+    InState cur[Plan::n];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) cur[c] = nxt[c];
-    const int64_t qn = q + kThreads;  // prefetch (one surplus generation per item and thread)
-    static_gen<Plan>(nxt, (uint32_t)qn, (uint32_t)((uint64_t)qn >> 32), pc);
+    for (int j = 0; j < Plan::n; ++j) cur[j] = nxt[j];
+    {  // prefetch (one surplus generation per item and thread)
+      const int64_t qn = q + kThreads;
+      Philox4 ph[NC];
+      static_gen<Plan>(ph, (uint32_t)qn, (uint32_t)((uint64_t)qn >> 32), pc);
+      FrontAll<Plan, 0>::run(ph, sm, nxt);
+    }
     pc.qlo = (uint32_t)q;
     pc.qhi = (uint32_t)((uint64_t)q >> 32);
     double x0[XCAP], x1[XCAP];
-    DrawAll<Plan, XCAP, 0>::run(r_plan, cur, pc, p.tables, sm, x0, x1);
+    BackAll<Plan, 0>::run(r_plan, cur, pc, p.tables, sm, x0, x1);
     const unsigned f0 = sample_fails<LS>(ctx, x0) ? 1u : 0u;
     const unsigned f1 = sample_fails<LS>(ctx, x1) ? 1u : 0u;
     if (CHECK) {

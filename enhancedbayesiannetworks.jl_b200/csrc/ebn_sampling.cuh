@@ -40,6 +40,11 @@ __device__ __forceinline__ double u32w(uint32_t w) {
   return __hiloint2double((int)((w & 0x000FFFFFu) | 0x3FF00000u), (int)(w & 0xFFF00000u)) - (1.0 - 0x1p-33);
 }
 
+// the [1,2) double behind U32(w), before the offset is removed
+__device__ __forceinline__ double u32w_raw(uint32_t w) {
+  return __hiloint2double((int)((w & 0x000FFFFFu) | 0x3FF00000u), (int)(w & 0xFFF00000u));
+}
+
 // Word sources -----------------------------------------------------------------
 // Static: all Philox calls of the pair are made up front, words are picked with
 // compile-time indices (registers only).
@@ -134,21 +139,45 @@ __device__ __forceinline__ double icdf(const DevInput& in, const double* tables,
   return table_quantile(in, tables, up);
 }
 
-// Draws input j for both samples of a pair. KIND is a DevKind, WS a word source
-// positioned at the input's first word.
+// Per-input state between the front end (word consumption, one pair ahead in the pipelined
+// loop) and the back end (fp64 transform) of a draw. Unused members are dead code per kind.
+struct InState {
+  uint32_t w0, w1, w2, w3;
+  BmFront bm;
+};
+
 template <int KIND, class WS>
-__device__ __forceinline__ void draw_pair(const DevInput& in, const WS& ws, const PairCtr& pc,
+__device__ __forceinline__ InState draw_front(const WS& ws, const FastMathSmem& sm) {
+  InState st;
+  if (KIND == DK_UNIFORM) {
+    st.w0 = ws.template w<0>();
+    st.w1 = ws.template w<1>();
+  } else if (KIND == DK_NORMAL_BM || KIND == DK_LOGNORMAL_BM) {
+    st.bm = box_muller_front(ws.template w<0>(), ws.template w<1>(), ws.template w<2>(), sm);
+  } else if (KIND != DK_CONST && KIND != DK_GAMMA_MT) {
+    st.w0 = ws.template w<0>();
+    st.w1 = ws.template w<1>();
+    st.w2 = ws.template w<2>();
+    st.w3 = ws.template w<3>();
+  }
+  return st;
+}
+
+template <int KIND>
+__device__ __forceinline__ void draw_back(const DevInput& in, const InState& st, const PairCtr& pc,
                                           uint32_t j, const double* tables,
                                           const FastMathSmem& sm, double& x0, double& x1) {
   if (KIND == DK_CONST) {
     x0 = in.a;
     x1 = in.a;
   } else if (KIND == DK_UNIFORM) {
-    x0 = fma(u32w(ws.template w<0>()), in.b, in.a);
-    x1 = fma(u32w(ws.template w<1>()), in.b, in.a);
+    // x = a + b*U32(w) with U32(w) = d - (1 - 2^-33), d in [1,2): folded into one FMA, the
+    // host stores c = a - b*(1 - 2^-33)
+    x0 = fma(u32w_raw(st.w0), in.b, in.c);
+    x1 = fma(u32w_raw(st.w1), in.b, in.c);
   } else if (KIND == DK_NORMAL_BM || KIND == DK_LOGNORMAL_BM) {
     double z0, z1;
-    box_muller_words(ws.template w<0>(), ws.template w<1>(), ws.template w<2>(), sm, z0, z1);
+    box_muller_back(st.bm, z0, z1);
     x0 = fma(z0, in.b, in.a);
     x1 = fma(z1, in.b, in.a);
     if (KIND == DK_LOGNORMAL_BM) {
@@ -159,9 +188,18 @@ __device__ __forceinline__ void draw_pair(const DevInput& in, const WS& ws, cons
     x0 = gamma_mt(in, pc, j, 0u, sm);
     x1 = gamma_mt(in, pc, j, 1u, sm);
   } else {
-    x0 = icdf<KIND>(in, tables, sm, u52w(ws.template w<0>(), ws.template w<1>()));
-    x1 = icdf<KIND>(in, tables, sm, u52w(ws.template w<2>(), ws.template w<3>()));
+    x0 = icdf<KIND>(in, tables, sm, u52w(st.w0, st.w1));
+    x1 = icdf<KIND>(in, tables, sm, u52w(st.w2, st.w3));
   }
+}
+
+// Draws input j for both samples of a pair. KIND is a DevKind, WS a word source
+// positioned at the input's first word.
+template <int KIND, class WS>
+__device__ __forceinline__ void draw_pair(const DevInput& in, const WS& ws, const PairCtr& pc,
+                                          uint32_t j, const double* tables,
+                                          const FastMathSmem& sm, double& x0, double& x1) {
+  draw_back<KIND>(in, draw_front<KIND>(ws, sm), pc, j, tables, sm, x0, x1);
 }
 
 // Runtime (warp-uniform) dispatch on the kind; the generic, slower path.
