@@ -31,11 +31,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# FP64-pipe instructions per sample of the W1 kernel: (DFMA 107 + DMUL 32 + DADD 18) warp
+# FP64-pipe instructions per sample of the W1 kernel: (DFMA 101.2 + DMUL 32.0 + DADD 16.1) warp
 # instructions per sample PAIR executed in the hot loop, from the ncu source page of
-# profiles/r01_c_* (= sm__inst_executed_pipe_fp64), i.e. 78.5 per sample. See DESIGN.md
+# profiles/r01_f_* (= sm__inst_executed_pipe_fp64), i.e. 74.65 per sample. See DESIGN.md
 # "Roofline". The SURVEY's ceiling for this figure is 339; the first version executed 151.5.
-F_ALG_W1 = 78.5
+F_ALG_W1 = 74.65
+# dram__bytes_read.sum + dram__bytes_write.sum of one mc_kernel launch (ncu --set full,
+# profiles/r01_f_ncu_full_w1_n1e7_summary.txt): 38.9 KB read, 0 B written — the plan and tables.
+DRAM_TRAFFIC_BYTES_PER_LAUNCH = 38912
 METRIC = "limit_state_mc_samples_per_sec"
 UNIT = "samples/s"
 
@@ -118,8 +121,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": "W1 vehicle_suspension S=20 (bounded CPU sample)",
-                                        "n_per_scenario": n},
+        "data": "synthetic", "config": {"workload": "W1 vehicle_suspension (BASELINE configs[1]): S=20 scenarios, bounded CPU "
+                                                    f"sample of {n} samples per scenario per step",
+                                        "n_per_scenario": n, "scenarios": 20},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Julia+UQ.jl (not runnable here); this is the oracle's structural C port",
@@ -242,7 +246,8 @@ def main():
             "clocks": clocks,
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": DRAM_TRAFFIC_BYTES_PER_LAUNCH,
+                "traffic_unit": "bytes per launch (ncu, n=1e7 launch; algorithmic traffic is O(S) descriptors)",
                 "fp64_slots_per_sample": F_ALG_W1,
                 "peak_source": "measured in this run by ebn_peak_fp64 (independent DFMA chains, burst); "
                                "MEASURED_PEAKS.json has no FP64 entry",
