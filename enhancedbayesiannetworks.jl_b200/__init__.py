@@ -24,6 +24,6 @@ from .nodes import (DiscreteConditionalProbabilityTable, ContinuousConditionalPr
                     ContinuousNode, DiscreteFunctionalNode, ContinuousFunctionalNode, Model, Poly, Catalogue,
                     CudaMonteCarlo, MonteCarlo, CudaDoubleLoop, DoubleLoop, CudaRandomSlicing, RandomSlicing)
 from .network import (EnhancedBayesianNetwork, BayesianNetwork, CredalNetwork, add_child, order, parents,  # noqa: F401
-                      children, discrete_ancestors)
+                      children, discrete_ancestors, markov_blanket, markov_envelope)
 from .uq import probability_of_failure, UnsupportedModel  # noqa: F401
-from .evaluation import evaluate, reduce, dispatch  # noqa: F401
+from .evaluation import evaluate, reduce, dispatch, evaluate_with_envelopes  # noqa: F401

@@ -319,3 +319,38 @@ def dispatch(net):
             return BayesianNetwork(net.nodes, net.topology_dict, net.adj_matrix)
         return CredalNetwork(net.nodes, net.topology_dict, net.adj_matrix)
     return net
+
+
+# ---------------------------------------------------------------------------------------------
+# evaluate_with_envelopes (evaluate_net.jl:34-40, :68-95)
+# ---------------------------------------------------------------------------------------------
+def _add_root2envelope(net, envelope):
+    envelope = list(envelope)
+    while True:
+        missing = []
+        for n in envelope:
+            for p in parents(net, n)[2]:
+                if not any(p is e for e in envelope) and not any(p is m for m in missing):
+                    missing.append(p)
+        if not missing:
+            return envelope
+        envelope += missing
+
+
+def _build_envelope_edges(net, envelope):
+    sub = EnhancedBayesianNetwork(envelope)
+    for n in envelope:
+        for p in parents(net, n)[2]:
+            if any(p is e for e in envelope):
+                add_child(sub, p, n)
+    order(sub)
+    return sub
+
+
+def evaluate_with_envelopes(net):
+    """One sub-network per Markov envelope, each evaluated on its own."""
+    from .network import markov_envelope
+    subs = [_build_envelope_edges(net, _add_root2envelope(net, env)) for env in markov_envelope(net)]
+    for s in subs:
+        evaluate(s)
+    return subs

@@ -201,3 +201,59 @@ class BayesianNetwork:
 
 class CredalNetwork(BayesianNetwork):
     """All-discrete network with at least one imprecise node (src/networks/cn/credalnet.jl)."""
+
+
+# ---- Markov blankets / envelopes (src/networks/ebn/enhancedbn.jl:63-118) -----------------------
+def markov_blanket(net, x) -> Tuple[List[int], List[str], List]:
+    """Parents, children and the children's other parents of a node (enhancedbn.jl:63-74)."""
+    idx = _index(net, x)
+    rev = {v: k for k, v in net.topology_dict.items()}
+    blanket: List[int] = []
+    for ch in children(net, idx)[0]:
+        blanket += parents(net, ch)[0]
+        blanket.append(ch)
+    blanket += parents(net, idx)[0]
+    indices = []
+    for i in blanket:
+        if i != idx and i not in indices:
+            indices.append(i)
+    names = [rev[i] for i in indices]
+    return indices, names, [n for n in net.nodes if n.name in names]
+
+
+def _get_markov_group(net, node) -> List:
+    """Closure of a continuous node under "continuous members of the Markov blanket"
+    (enhancedbn.jl:86-96)."""
+    def grow(lst):
+        out = list(lst)
+        for n in lst:
+            for m in markov_blanket(net, node)[2]:
+                if isinstance(m, AbstractContinuousNode) and not any(m is o for o in out):
+                    out.append(m)
+        return out
+    cur = [node]
+    new = grow(cur)
+    while {n.name for n in new} != {n.name for n in cur}:
+        cur, new = new, grow(new)
+    return new
+
+
+def markov_envelope(net) -> List[List]:
+    """Groups of nodes that have to be evaluated together (enhancedbn.jl:98-118)."""
+    cont = [n for n in net.nodes if isinstance(n, AbstractContinuousNode)]
+    envelopes = []
+    for c in cont:
+        env = []
+        for x in _get_markov_group(net, c):
+            for m in markov_blanket(net, x)[2] + [x]:
+                if not any(m is o for o in env):
+                    env.append(m)
+        envelopes.append(env)
+    envelopes.sort(key=len, reverse=True)
+    final = []
+    while envelopes:
+        head, rest = envelopes[0], envelopes[1:]
+        names = {n.name for n in head}
+        envelopes = [e for e in rest if any(n.name not in names for n in e)]
+        final.append(head)
+    return final

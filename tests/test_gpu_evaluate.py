@@ -359,3 +359,51 @@ def test_vehicle_suspension_imprecise(E):
         assert lb < ub and abs(lb - pf_at(lo)) < 0.005 and abs(ub - pf_at(hi)) < 0.005
     bn = E.dispatch(net)
     assert isinstance(bn, E.CredalNetwork)
+
+
+def test_evaluate_with_envelopes(E):
+    """evaluate_net.jl:93-216: two independent components (the Straub frame with a discrete parent M of V,
+    and a small second frame sharing M) are split into Markov envelopes and evaluated separately."""
+    lam, zeta = E.distribution_parameters(150, 30, "LogNormal")
+    a, th = E.distribution_parameters(60, 12, "Gamma")
+    ur = _cont_root(E, "Uᵣ", E.Normal())
+    m = _root(E, "M", ["new", "old"], [0.5, 0.5])
+    cptv = E.ContinuousConditionalProbabilityTable(["M"])
+    cptv[("M", "new")], cptv[("M", "old")] = E.Gamma(a, th), E.Gamma(a - 1, 2.4)
+    v = E.ContinuousNode("V", cptv)
+    h = _cont_root(E, "H", E.Gumbel(*E.distribution_parameters(50, 20, "Gumbel")))
+    sim = E.MonteCarlo(200_000)
+    rs = [E.ContinuousFunctionalNode(f"R{i}", [E.Model(E.Catalogue("straub_capacity", (lam, zeta, 0.5477), ("Uᵣ",)), f"r{i}")], sim)
+          for i in range(1, 6)]
+    frame = E.DiscreteFunctionalNode(
+        "E", [E.Model(E.Catalogue("straub_frame", (), ("r1", "r2", "r3", "r4", "r5", "V", "H")), "G")], "G", sim)
+    # second component: L | M and R9 feeding a second frame
+    cptl = E.ContinuousConditionalProbabilityTable(["M"])
+    cptl[("M", "new")], cptl[("M", "old")] = E.Normal(1, 1), E.Normal(2, 1)
+    L = E.ContinuousNode("L", cptl)
+    r9 = _cont_root(E, "R9", E.Normal(4, 1))
+    frame2 = E.DiscreteFunctionalNode("E2", [E.Model(E.Poly([(1, ["R9"]), (-1, ["L"])]), "G2")], "G2", sim)
+    net = E.EnhancedBayesianNetwork([ur, m, v, h] + rs + [frame, L, r9, frame2])
+    E.add_child(net, m, v)
+    for r in rs:
+        E.add_child(net, ur, r)
+        E.add_child(net, r, frame)
+    E.add_child(net, v, frame)
+    E.add_child(net, h, frame)
+    E.add_child(net, m, L)
+    E.add_child(net, L, frame2)
+    E.add_child(net, r9, frame2)
+    E.order(net)
+    envs = E.markov_envelope(net)
+    assert len(envs) == 2
+    assert {n.name for n in envs[0]} == {"Uᵣ", "M", "V", "H", "R1", "R2", "R3", "R4", "R5", "E"}   # evaluate_net.jl:197
+    assert {n.name for n in envs[1]} == {"L", "R9", "E2", "M"}                                      # :205
+    subs = E.evaluate_with_envelopes(net)
+    assert [sorted(n.name for n in s.nodes) for s in subs] == [["E", "H", "M", "Uᵣ", "V"], ["E2", "L", "M", "R9"]]
+    assert not any(isinstance(n, (E.DiscreteFunctionalNode, E.ContinuousFunctionalNode)) for s in subs for n in s.nodes)
+    e = subs[0].node("E")
+    assert e.cpt.names == ["M", "E"] and abs(e.cpt[{"M": "new", "E": "E_fail"}] - 0.0258) < 0.003
+    assert e.cpt[{"M": "old", "E": "E_fail"}] < e.cpt[{"M": "new", "E": "E_fail"}]      # lighter vertical load
+    e2 = subs[1].node("E2")
+    assert abs(e2.cpt[{"M": "new", "E2": "E2_fail"}] - ndtr(-3 / math.sqrt(2))) < 0.002
+    assert abs(e2.cpt[{"M": "old", "E2": "E2_fail"}] - ndtr(-2 / math.sqrt(2))) < 0.004
