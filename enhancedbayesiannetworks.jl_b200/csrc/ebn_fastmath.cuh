@@ -133,17 +133,6 @@ __device__ __forceinline__ double sqrt_pos(double t) {
   return g;
 }
 
-// 1/x for normal x, |x| in [2^-500, 2^500]: MUFU.RCP64H seed + two Newton steps.
-__device__ __forceinline__ double rcp_normal(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
-}
-
 // (cos a + sin a, cos a - sin a) for a = (pi/2)*v, v in [-1/2, 1/2):
 // sqrt(2)*(sin, cos) of the first-quadrant angle (pi/2)*(v + 1/2).
 __device__ __forceinline__ void sincos_quadrant(double v, double& cps, double& cms) {

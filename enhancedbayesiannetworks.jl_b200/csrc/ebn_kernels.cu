@@ -7,9 +7,6 @@ namespace ebn {
 #ifndef EBN_THREADS
 #define EBN_THREADS 256
 #endif
-#ifndef EBN_MIN_BLOCKS
-#define EBN_MIN_BLOCKS 3
-#endif
 constexpr int kThreads = EBN_THREADS;
 
 // Fixed-order reduction of the per-item moment partials: one thread per
