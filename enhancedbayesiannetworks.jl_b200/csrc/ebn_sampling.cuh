@@ -84,34 +84,53 @@ struct DynWords {
 // 0x80000000 | j<<16 | e<<15 | t: normal from (w0,w1,w2) (first Box-Muller
 // output), acceptance uniform from w3. The boost uniform is call t = 0x7fff.
 // in.c = d = shape' - 1/3 and in.d = c = 1/sqrt(9 d) are precomputed on the host.
-static __device__ __noinline__ double gamma_boost(const DevInput& in, const PairCtr& pc,
-                                                  uint32_t base) {
-  const Philox4 w = philox4x32_10(pc.qlo, pc.qhi, pc.stream, base | 0x7FFFu, pc.k0, pc.k1);
-  return pow(u52w(w.w0, w.w1), 1.0 / in.a);
+// One Marsaglia-Tsang attempt: returns true and v = (1 + c z)^3 when accepted.
+__device__ __forceinline__ bool gamma_attempt(double dd, double cc, uint32_t qlo, uint32_t qhi,
+                                              uint32_t stream, uint32_t slot, uint32_t k0,
+                                              uint32_t k1, const FastMathSmem& sm, double& v) {
+  const Philox4 w = philox4x32_10(qlo, qhi, stream, slot, k0, k1);
+  double z, z_unused;
+  box_muller_words(w.w0, w.w1, w.w2, sm, z, z_unused);
+  const double t1 = fma(cc, z, 1.0);
+  v = t1 * t1 * t1;
+  const double u = u32w(w.w3);
+  const double z2 = z * z;
+  // squeeze, then the exact test; both evaluated branch-free (in a warp some lane needs
+  // the logarithms almost always), t1 <= 0 gives NaN/false below and is rejected explicitly
+  const bool squeeze = u < fma(-0.0331 * z2, z2, 1.0);
+  const bool exact = -neg_log01(u, sm) < fma(dd, 1.0 - v - neg_log_pos(fmax(v, 0x1p-1000), sm), 0.5 * z2);
+  return t1 > 0.0 && (squeeze || exact);
 }
 
-static __device__ __noinline__ double gamma_mt(const DevInput& in, const PairCtr& pc, uint32_t j,
-                                               uint32_t e, const FastMathSmem& sm) {
-  const double shape = in.a;
-  const double dd = in.c;
-  const double cc = in.d;
-  const uint32_t base = 0x80000000u | (j << 16) | (e << 15);
+// Slow path (about 0.3 % of the samples at shape 25): attempts 1..63, all arguments by value
+// so that nothing lives in local memory.
+static __device__ __noinline__ double gamma_retry(double dd, double cc, uint32_t qlo, uint32_t qhi,
+                                                  uint32_t stream, uint32_t base, uint32_t k0,
+                                                  uint32_t k1, const FastMathSmem* sm) {
   double v = 1.0;
 #pragma unroll 1
-  for (uint32_t t = 0; t < 64u; ++t) {
-    const Philox4 w = philox4x32_10(pc.qlo, pc.qhi, pc.stream, base | t, pc.k0, pc.k1);
-    double z, z_unused;
-    box_muller_words(w.w0, w.w1, w.w2, sm, z, z_unused);
-    const double t1 = 1.0 + cc * z;
-    if (t1 <= 0.0) continue;
-    v = t1 * t1 * t1;
-    const double u = u32w(w.w3);
-    const double z2 = z * z;
-    if (u < 1.0 - 0.0331 * z2 * z2) break;
-    if (-neg_log01(u, sm) < 0.5 * z2 + dd * (1.0 - v - neg_log_pos(v, sm))) break;
-  }
-  double x = dd * v;
-  if (shape < 1.0) x *= gamma_boost(in, pc, base);
+  for (uint32_t t = 1; t < 64u; ++t)
+    if (gamma_attempt(dd, cc, qlo, qhi, stream, base | t, k0, k1, *sm, v)) break;
+  return v;
+}
+
+static __device__ __noinline__ double gamma_boost(double shape, uint32_t qlo, uint32_t qhi,
+                                                  uint32_t stream, uint32_t base, uint32_t k0,
+                                                  uint32_t k1) {
+  const Philox4 w = philox4x32_10(qlo, qhi, stream, base | 0x7FFFu, k0, k1);
+  return pow(u52w(w.w0, w.w1), 1.0 / shape);
+}
+
+// in.c = d = shape' - 1/3 and in.d = c = 1/sqrt(9 d) are precomputed on the host. The first
+// attempt is inlined (no call, no spills); rejected lanes go to gamma_retry.
+__device__ __forceinline__ double gamma_mt(const DevInput& in, const PairCtr& pc, uint32_t j,
+                                           uint32_t e, const FastMathSmem& sm) {
+  const uint32_t base = 0x80000000u | (j << 16) | (e << 15);
+  double v;
+  if (!gamma_attempt(in.c, in.d, pc.qlo, pc.qhi, pc.stream, base, pc.k0, pc.k1, sm, v))
+    v = gamma_retry(in.c, in.d, pc.qlo, pc.qhi, pc.stream, base, pc.k0, pc.k1, &sm);
+  double x = in.c * v;
+  if (in.a < 1.0) x *= gamma_boost(in.a, pc.qlo, pc.qhi, pc.stream, base, pc.k0, pc.k1);
   return x * in.b;
 }
 
