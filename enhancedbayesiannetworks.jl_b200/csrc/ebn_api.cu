@@ -556,6 +556,17 @@ int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, i
       mp.edges = (const double*)dv.edges.p;
       mp.partial = (double*)dv.partial.p;
       mp.nedges = nedges;
+      if (nedges >= 3) {  // equally spaced edges (the grid the host mirror uses) get the direct index
+        const double h = (edges[nedges - 1] - edges[0]) / (nedges - 1);
+        bool uni = h > 0.0 && std::isfinite(h);
+        for (int i = 1; uni && i < nedges; ++i)
+          if (fabs(edges[i] - (edges[0] + i * h)) > 1e-9 * h) uni = false;
+        if (uni) {
+          mp.hist_uniform = 1;
+          mp.hist_e0 = edges[0];
+          mp.hist_inv_h = 1.0 / h;
+        }
+      }
       cf[k] = dv.sums.p;
     }
     if ((rc = grid_for(dv, job, P, mode, dyn, mp.local_items, &blocks[k]))) return rc;

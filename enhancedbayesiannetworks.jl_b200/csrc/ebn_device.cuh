@@ -61,6 +61,8 @@ struct McParams {
   uint32_t k0, k1;
   int32_t chol_shared;
   int32_t ncols;  // replay: columns written per sample (d inputs + model outputs)
+  int32_t hist_uniform;  // HIST: edges are equally spaced -> direct bin index + exact fix-up
+  double hist_e0, hist_inv_h;
 };
 
 }  // namespace ebn

@@ -189,6 +189,18 @@ __device__ __forceinline__ unsigned static_count_loop(const typename LS::Ctx& ct
   return cnt;
 }
 
+// Equally spaced edges: a direct index from one FMA, then an exact fix-up against the real
+// edges (at most a step or two), so the result is identical to the binary search.
+__device__ __forceinline__ int find_bin_uniform(const double* edges, int nedges, double y,
+                                                double e0, double inv_h) {
+  if (!(y == y)) return nedges;
+  const double pos = (y - e0) * inv_h;
+  int b = pos < 0.0 ? 0 : (pos >= (double)nedges ? nedges : (int)pos + 1);
+  while (b > 0 && y < edges[b - 1]) --b;
+  while (b < nedges && edges[b] <= y) ++b;
+  return b;
+}
+
 __device__ __forceinline__ int find_bin(const double* edges, int nedges, double y) {
   // number of edges <= y  (NaN -> nedges)
   if (!(y == y)) return nedges;
@@ -279,12 +291,16 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
       } else {
         const double g0 = LS::eval(ctx, x0);
         const double g1 = LS::eval(ctx, x1);
+        const int b0 = p.hist_uniform ? find_bin_uniform(s_edges, p.nedges, g0, p.hist_e0, p.hist_inv_h)
+                                      : find_bin(s_edges, p.nedges, g0);
+        const int b1 = p.hist_uniform ? find_bin_uniform(s_edges, p.nedges, g1, p.hist_e0, p.hist_inv_h)
+                                      : find_bin(s_edges, p.nedges, g1);
         if (v0) {
-          atomicAdd(&s_bins[find_bin(s_edges, p.nedges, g0)], 1u);
+          atomicAdd(&s_bins[b0], 1u);
           if (g0 == g0) { sum += g0; sumsq = fma(g0, g0, sumsq); }
         }
         if (v1) {
-          atomicAdd(&s_bins[find_bin(s_edges, p.nedges, g1)], 1u);
+          atomicAdd(&s_bins[b1], 1u);
           if (g1 == g1) { sum += g1; sumsq = fma(g1, g1, sumsq); }
         }
       }

@@ -357,6 +357,12 @@ def test_hist_batch_matches_numpy_on_replayed_samples(ebn):
         want = np.bincount(np.searchsorted(edges, y, side="right"), minlength=len(edges) + 1)
         assert np.array_equal(counts[s], want), s
         assert abs(s1[s] - y.sum()) < 1e-6 * n and abs(s2[s] - (y * y).sum()) < 1e-6 * n
+    # equally spaced edges take the direct-index path; bins must be identical to a search
+    for ue in (np.linspace(-2.0, 6.0, 81), np.linspace(0.3, 0.9, 1025), np.array([0.0, 1.0, 2.0])):
+        cu, _, _ = ebn.hist_batch(job, ue)
+        X = ebn.sample_matrix(job, 1, 0, n)
+        y = X[:, 0] + X[:, 1]
+        assert np.array_equal(cu[1], np.bincount(np.searchsorted(ue, y, side="right"), minlength=len(ue) + 1))
     # same call twice → identical moments (fixed-order reduction)
     counts2, s1b, s2b = ebn.hist_batch(job, edges)
     assert np.array_equal(counts, counts2) and np.array_equal(s1, s1b) and np.array_equal(s2, s2b)
