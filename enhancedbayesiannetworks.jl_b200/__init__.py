@@ -18,7 +18,7 @@ from ._lib import (EbnError, Job, INPUT_DTYPE, make_inputs, pf_batch, hist_batch
                    sample_matrix, peak_fp64, last_stats, init, shutdown, device_count)
 from .distributions import (Normal, LogNormal, Uniform, Gumbel, Gamma, Exponential, Truncated, truncated,  # noqa: F401
                             Tabulated, EmpiricalDistribution, distribution_parameters, Parameter,
-                            RandomVariable, Interval, ProbabilityBox)
+                            RandomVariable, Interval, ProbabilityBox, GaussianCopula, JointDistribution)
 from .nodes import (DiscreteConditionalProbabilityTable, ContinuousConditionalProbabilityTable,  # noqa: F401
                     ExactDiscretization, ApproximatedDiscretization, UnamedProbabilityBox, DiscreteNode,
                     ContinuousNode, DiscreteFunctionalNode, ContinuousFunctionalNode, Model, Poly, Catalogue,

@@ -384,3 +384,36 @@ class ProbabilityBox:
         import itertools
         vals = [float(self.member(v).cdf(x)) for v in itertools.product(*[(p.lb, p.ub) for p in self.parameters])]
         return min(vals), max(vals)
+
+
+@dataclass(frozen=True)
+class GaussianCopula:
+    """UQ.jl `GaussianCopula(R)`: R is the correlation matrix of the normal scores."""
+    correlation: Tuple[Tuple[float, ...], ...]
+
+    def __init__(self, correlation):
+        R = np.asarray(correlation, dtype=float)
+        if R.ndim != 2 or R.shape[0] != R.shape[1] or not np.allclose(R, R.T) or not np.allclose(np.diag(R), 1.0):
+            raise ValueError("GaussianCopula needs a symmetric correlation matrix with unit diagonal")
+        np.linalg.cholesky(R)  # raises if not positive definite
+        object.__setattr__(self, "correlation", tuple(map(tuple, R.tolist())))
+
+
+@dataclass(frozen=True)
+class JointDistribution:
+    """UQ.jl `JointDistribution(marginals, copula)`: z = L eps, u = Phi(z),
+    x_j = quantile(marginal_j, u_j). The reference's node API never builds one; it is
+    accepted wherever a list of UQ inputs is (probability_of_failure)."""
+    marginals: Tuple[RandomVariable, ...]
+    copula: GaussianCopula
+
+    def __init__(self, marginals, copula):
+        marginals = tuple(marginals)
+        if len(marginals) != len(copula.correlation):
+            raise ValueError("one marginal per row of the correlation matrix")
+        object.__setattr__(self, "marginals", marginals)
+        object.__setattr__(self, "copula", copula)
+
+    @property
+    def name(self):
+        return tuple(m.name for m in self.marginals)

@@ -17,8 +17,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib as L
-from .distributions import (INF, Interval, NeedsTable, Normal, Parameter, ProbabilityBox, RandomVariable,
-                            Truncated, table_for)
+from .distributions import (INF, Gamma, Interval, JointDistribution, NeedsTable, Normal, Parameter,
+                            ProbabilityBox, RandomVariable, Truncated, table_for)
 from .nodes import Catalogue, CudaDoubleLoop, CudaMonteCarlo, CudaRandomSlicing, Model, Poly
 
 VEHICLE_ARGS = ("A", "b₀", "V", "C", "Cₖ", "K")
@@ -139,18 +139,59 @@ def _abi_row(inp, pool: _TablePool) -> tuple:
     raise TypeError(f"input {inp} is imprecise: use DoubleLoop or RandomSlicing")
 
 
+def _flatten(inputs):
+    """Expands JointDistribution inputs; returns (flat inputs, {name: (group id, position)}, copulas)."""
+    flat, where, copulas = [], {}, []
+    for i in inputs:
+        if isinstance(i, JointDistribution):
+            g = len(copulas)
+            copulas.append(np.asarray(i.copula.correlation))
+            for k, m in enumerate(i.marginals):
+                flat.append(m)
+                where[m.name] = (g, k)
+        else:
+            flat.append(i)
+    return flat, where, copulas
+
+
+def input_names(inputs) -> List[str]:
+    return [i.name for i in _flatten(inputs)[0]]
+
+
 def build_job(low: Lowered, scenario_inputs: Sequence[Sequence], sim: CudaMonteCarlo, stream_id=None) -> L.Job:
     pool = _TablePool()
-    rows = []
+    rows, chols = [], []
+    d = len(low.columns) + len(low.hidden)
+    any_copula = False
     for inputs in scenario_inputs:
+        flat, where, copulas = _flatten(inputs)
         by_name = {}
-        for i in inputs:
+        for i in flat:
             if i.name in by_name:
                 raise ValueError(f"two inputs named '{i.name}' in one scenario")
             by_name[i.name] = i
-        rows.append([_abi_row(by_name[c], pool) for c in low.columns] + list(low.hidden))
+        row = []
+        for c in low.columns:
+            inp = by_name[c]
+            if copulas and isinstance(inp, RandomVariable) and isinstance(inp.dist, Gamma):
+                # no closed-form quantile on the device: Gamma under a copula is shipped tabulated
+                off, n = pool.add(table_for(inp.dist, -INF, INF, 8193))
+                row.append((L.IN_TABULATED, float(off), float(n), 0.0, 0.0, -INF, INF))
+            else:
+                row.append(_abi_row(inp, pool))
+        rows.append(row + list(low.hidden))
+        if copulas:
+            any_copula = True
+            R = np.eye(d)
+            for a, ca in enumerate(low.columns):
+                for b, cb in enumerate(low.columns):
+                    if ca in where and cb in where and where[ca][0] == where[cb][0]:
+                        R[a, b] = copulas[where[ca][0]][where[ca][1], where[cb][1]]
+            chols.append(np.linalg.cholesky(R))
+        else:
+            chols.append(np.eye(d))
     return L.Job(low.limit_state, low.consts, L.make_inputs(rows), int(sim.n), int(sim.seed), bool(sim.strict),
-                 stream_id=stream_id, tables=pool.array())
+                 stream_id=stream_id, tables=pool.array(), corr_chol=np.stack(chols) if any_copula else None)
 
 
 class Samples:
@@ -180,7 +221,7 @@ def _is_imprecise(i) -> bool:
 
 def pf_scenarios(models, performance, scenario_inputs, sim: CudaMonteCarlo):
     """All scenarios of a node in one ebn_pf_batch call → (pf[S], std[S], [Samples])."""
-    low = lower(models, performance, [i.name for i in scenario_inputs[0]])
+    low = lower(models, performance, input_names(scenario_inputs[0]))
     job = build_job(low, scenario_inputs, sim)
     cnt, pf, var = L.pf_batch(job)
     return pf, np.sqrt(var), [Samples(job, s, low.out_columns) for s in range(job.S)], cnt
@@ -239,7 +280,7 @@ def _eval_candidates(models, performance, scenario_inputs, dims_per_s, cands_per
             flat.append(_realise(inputs, dims, x))
             stream.append(s)
             owner.append(s)
-    low = lower(models, performance, [i.name for i in flat[0]])
+    low = lower(models, performance, input_names(flat[0]))
     job = build_job(low, flat, sim, stream_id=np.array(stream, dtype=np.uint32))
     _, pf, _ = L.pf_batch(job)
     out, k = [], 0
@@ -349,7 +390,7 @@ def random_slicing(models, performance, scenario_inputs, sim: CudaRandomSlicing)
 def output_histograms(models, scenario_inputs, sim: CudaMonteCarlo, edges: Optional[np.ndarray] = None):
     """`sample` + `evaluate!` for a ContinuousFunctionalNode: per-scenario histogram and moments of
     the last model's output. Without `edges`, a pilot call finds the output range."""
-    low = lower(models, None, [i.name for i in scenario_inputs[0]])
+    low = lower(models, None, input_names(scenario_inputs[0]))
     job = build_job(low, scenario_inputs, sim)
     if edges is None:
         pilot = L.Job(job.limit_state, job.consts, job.inputs, min(job.n, 1 << 16), job.seed, job.strict,

@@ -407,3 +407,35 @@ def test_evaluate_with_envelopes(E):
     e2 = subs[1].node("E2")
     assert abs(e2.cpt[{"M": "new", "E2": "E2_fail"}] - ndtr(-3 / math.sqrt(2))) < 0.002
     assert abs(e2.cpt[{"M": "old", "E2": "E2_fail"}] - ndtr(-2 / math.sqrt(2))) < 0.004
+
+
+def test_joint_distribution_gaussian_copula(E):
+    """UQ.jl `JointDistribution(marginals, GaussianCopula(R))` as a probability_of_failure input
+    (BASELINE config 3): five log-normal capacities with equicorrelated scores
+    (rho^2 = 0.3) reproduce the common-factor dependence of demo/straub_example.jl:16-26, so the pf
+    equals the Straub frame's."""
+    lam, zeta = E.distribution_parameters(150, 30, "LogNormal")
+    R = np.full((5, 5), 0.5477**2)
+    np.fill_diagonal(R, 1.0)
+    caps = E.JointDistribution([E.RandomVariable(E.LogNormal(lam, zeta), f"r{i}") for i in range(1, 6)],
+                               E.GaussianCopula(R))
+    v = E.RandomVariable(E.Gamma(*E.distribution_parameters(60, 12, "Gamma")), "V")
+    h = E.RandomVariable(E.Gumbel(*E.distribution_parameters(50, 20, "Gumbel")), "H")
+    g1 = E.Model(E.Poly([(1, ["r1"]), (1, ["r2"]), (1, ["r4"]), (1, ["r5"]), (-5, ["H"])]), "g1")
+    g2 = E.Model(E.Poly([(1, ["r2"]), (2, ["r3"]), (1, ["r4"]), (-5, ["V"])]), "g2")
+    g3 = E.Model(E.Poly([(1, ["r1"]), (2, ["r3"]), (2, ["r4"]), (1, ["r5"]), (-5, ["H"]), (-5, ["V"])]), "g3")
+    n = 1_000_000
+    pfs = [E.probability_of_failure([g], g.name, [caps, v, h], E.MonteCarlo(n, seed=5))[0] for g in (g1, g2, g3)]
+    # each mechanism alone fails less often than their minimum; the frame pf (0.0258) is bounded by the union
+    assert all(0 < p < 0.03 for p in pfs) and sum(pfs) > 0.0258 - 0.002
+    # the min of the three through the min_affine catalogue entry, same inputs → Straub's pf
+    k = [3.0, 0, 1, 1, 0, 1, 1, 0, -5, 0, 0, 1, 2, 1, 0, -5, 0, 0, 1, 0, 2, 2, 1, -5, -5.0]
+    frame = E.Model(E.Catalogue("min_affine", k, ("r1", "r2", "r3", "r4", "r5", "V", "H")), "G")
+    pf, sd, _ = E.probability_of_failure(frame, "G", [caps, v, h], E.MonteCarlo(n, seed=5))
+    assert abs(pf - 0.0258) < 4 * sd + 5e-4
+    # independent capacities (identity copula) give a different, smaller pf: the dependence matters
+    ind = E.JointDistribution(caps.marginals, E.GaussianCopula(np.eye(5)))
+    pf_ind = E.probability_of_failure(frame, "G", [ind, v, h], E.MonteCarlo(n, seed=5))[0]
+    assert pf_ind < pf - 0.003
+    with pytest.raises(ValueError, match="correlation matrix"):
+        E.GaussianCopula([[1.0, 0.5], [0.4, 1.0]])
