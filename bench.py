@@ -140,6 +140,9 @@ def main():
     ap.add_argument("--n-per-scenario", type=float, default=1e8, help="per GPU (weak scaling)")
     ap.add_argument("--cpu-n", type=int, default=5_000_000, help="CPU arm: samples per scenario per step")
     ap.add_argument("--strict", action="store_true", help="Julia-order limit state (no FMA contraction)")
+    ap.add_argument("--workload", default="w1", choices=["w1", "w5"],
+                    help="w1: BASELINE configs[1] (default, weak scaling); w5: configs[4], 1024 scenarios x "
+                         "--n-per-scenario samples in total, sharded over the ranks (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -172,8 +175,15 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ebn_b200._lib.comm_init_rank(uid[0], rank, world)
 
-    n_per_scenario = int(args.n_per_scenario) * world  # weak scaling: per-GPU work fixed
-    job = W.w1_vehicle(n=n_per_scenario, strict=args.strict)
+    if args.workload == "w5":
+        n_per_scenario = int(args.n_per_scenario)      # strong scaling: total work fixed
+        job = W.w5_vehicle_grid(n=n_per_scenario, strict=args.strict)
+        wl_name = f"W5 vehicle_suspension grid (BASELINE configs[4]): S=1024 scenarios x {n_per_scenario:.3g} samples"
+    else:
+        n_per_scenario = int(args.n_per_scenario) * world  # weak scaling: per-GPU work fixed
+        job = W.w1_vehicle(n=n_per_scenario, strict=args.strict)
+        wl_name = ("W1 vehicle_suspension (BASELINE configs[1]): S=20 scenarios x "
+                   f"{n_per_scenario:.3g} samples, seed 0x5EED0001")
     job.shard_rank, job.shard_world = rank, world
     total_samples = job.S * n_per_scenario
 
@@ -231,11 +241,10 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.workload == "w5" else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": "W1 vehicle_suspension (BASELINE configs[1]): S=20 scenarios x "
-                            f"{n_per_scenario:.3g} samples, seed 0x5EED0001",
+                "workload": wl_name,
                 "n_per_scenario": n_per_scenario, "scenarios": job.S, "strict_fp": bool(args.strict),
                 "parallelism": f"(scenario,chunk) items round-robin over {world} rank(s); NCCL int64 all-reduce",
                 "l2": "256 MiB flush written between timed iterations; inputs are O(KB) descriptors",

@@ -53,19 +53,41 @@ class _CPT:
         self.names: List[str] = [names] if isinstance(names, str) else list(names)
         self.data: List[Dict[str, Any]] = []
 
-    # cpt[evidence] = value  (cpts.jl:81-102)
+    # cpt[evidence] = value  (cpts.jl:81-102). The reference subsets the DataFrame per call
+    # (O(S) each, O(S^2) per node — SURVEY.md §8f row 4); here a hash index over the key columns
+    # makes the write-back O(1) per row.
+    def _key(self, ev) -> tuple:
+        return tuple(ev[n] for n in self.names)
+
+    def _reindex(self):
+        self._index = {tuple(r[n] for n in self.names): r for r in self.data}
+        self._index_rows, self._index_names = len(self.data), tuple(self.names)
+
     def __setitem__(self, key, value):
         ev = self._as_evidence(key)
         if set(ev) != set(self.names):
             raise ValueError(f"Cannot set index with {list(ev)} into a CPT initialized with {self.names}")
-        for row in self.data:
-            if all(row[k] == v for k, v in ev.items()):
-                row[PI] = value
-                return
-        self.data.append({**{n: ev[n] for n in self.names}, PI: value})
+        if getattr(self, "_index_rows", -1) != len(self.data) or getattr(self, "_index_names", None) != tuple(self.names):
+            self._reindex()
+        k = self._key(ev)
+        row = self._index.get(k)
+        if row is not None:
+            row[PI] = value
+            return
+        row = {**{n: ev[n] for n in self.names}, PI: value}
+        self.data.append(row)
+        self._index[k] = row
+        self._index_rows = len(self.data)
 
     def __getitem__(self, key):
         ev = self._as_evidence(key)
+        if set(ev) == set(self.names):
+            if getattr(self, "_index_rows", -1) != len(self.data) or getattr(self, "_index_names", None) != tuple(self.names):
+                self._reindex()
+            row = self._index.get(self._key(ev))
+            if row is None:
+                raise KeyError(f"index not find in the CPT {self}")
+            return row[PI]
         hits = [r for r in self.data if all(r.get(k) == v for k, v in ev.items())]
         if not hits:
             raise KeyError(f"index not find in the CPT {self}")
@@ -92,7 +114,9 @@ class _CPT:
         return [r for r in self.data if all(r[k] == v for k, v in ev.items())]
 
     def __eq__(self, other):
-        return type(self) is type(other) and self.names == other.names and self.data == other.data \
+        return type(self) is type(other) and self.names == other.names and \
+            [{k: r[k] for k in self.names + [PI]} for r in self.data] == \
+            [{k: r[k] for k in other.names + [PI]} for r in other.data] \
             and getattr(self, "precise", None) == getattr(other, "precise", None)
 
     def __repr__(self):
@@ -207,8 +231,11 @@ def _verify_probabilities(cpt: DiscreteConditionalProbabilityTable, name: str):
                 raise ValueError(f"probabilities must be lower or equal than 1: {p}")
         if not cpt.precise and r[PI][0] > r[PI][1]:
             raise ValueError(f"interval probabilities must have a lower bound smaller than upper bound. {cpt.data}")
-    for sc in (cpt.scenarios(name) or [{}]):
-        rows = cpt.subset(sc)
+    groups: Dict[tuple, list] = {}
+    others = [n for n in cpt.names if n != name]
+    for r in cpt.data:
+        groups.setdefault(tuple(r[n] for n in others), []).append(r)
+    for rows in groups.values():
         if cpt.precise:
             tot = sum(r[PI] for r in rows)
             if tot != 1:
