@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -481,6 +482,10 @@ int grid_for(Dev& dv, const ebn_job_t* job, const Prepared& P, int mode, size_t 
   int per_sm = 0;
   CU(ls_vtable(job->limit_state)->occupancy(job->strict ? 1 : 0, P.plan_class, mode, dyn, &per_sm));
   if (per_sm < 1) return fail(EBN_ECUDA, "kernel does not fit on an SM (dyn smem %zu)", dyn);
+  if (const char* cap = getenv("EBN_BLOCKS_PER_SM")) {  // tuning experiments only
+    const int c = atoi(cap);
+    if (c >= 1 && c < per_sm) per_sm = c;
+  }
   int64_t b = (int64_t)dv.sms * per_sm;
   if (b > local_items) b = local_items;
   if (b < 1) b = 1;

@@ -117,20 +117,17 @@ __device__ __forceinline__ double exp_fast(double x, const FastMathSmem& sm) {
   return __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
 }
 
-// sqrt(t) for t in [2^-60, 2^60]: MUFU.RSQ64H seed + two coupled Newton steps.
+// sqrt(t) for t in [2^-60, 2^60]: MUFU.RSQ64H seed y ~ t^-1/2 (relative error e0 ~ 2^-20),
+// then one third-order correction: with a = t*y and e = 1 - a*y,
+//   sqrt(t) = a / sqrt(1 - e) = a * (1 + e/2 + 3 e^2/8 + O(e^3)),   truncation 5 e^3/16 < 2^-58.
+// Five fp64 operations (two coupled Newton steps need seven).
 __device__ __forceinline__ double sqrt_pos(double t) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
-  double g = t * y;
-  double h = 0.5 * y;
-  double r = fma(-g, h, 0.5);
-  g = fma(g, r, g);
-#ifndef EBN_SQRT_ONE_STEP
-  h = fma(h, r, h);
-  r = fma(-g, h, 0.5);
-  g = fma(g, r, g);
-#endif
-  return g;
+  const double a = t * y;
+  const double e = fma(-a, y, 1.0);
+  const double c = fma(e, 0.375, 0.5);
+  return fma(a * e, c, a);
 }
 
 // (cos a + sin a, cos a - sin a) for a = (pi/2)*v, v in [-1/2, 1/2):
