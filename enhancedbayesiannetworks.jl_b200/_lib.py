@@ -26,6 +26,8 @@ LS_STRAUB_FRAME = 2
 LS_HYDROGEN_RADIUS = 3
 LS_POLYNOMIAL = 4
 LS_MIN_AFFINE = 5
+LS_STRAUB_FRAME_R45 = 6
+LS_STRAUB_CAPACITY = 7
 
 IN_PARAM = 0
 IN_NORMAL = 1

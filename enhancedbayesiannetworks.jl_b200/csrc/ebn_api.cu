@@ -277,6 +277,8 @@ const LsInfo kLs[] = {
     {EBN_LS_HYDROGEN_RADIUS, "hydrogen_radius", 4, 0},
     {EBN_LS_POLYNOMIAL, "polynomial", -1, -1},
     {EBN_LS_MIN_AFFINE, "min_affine", -1, -1},
+    {EBN_LS_STRAUB_FRAME_R45, "straub_frame_r45", 8, 3},
+    {EBN_LS_STRAUB_CAPACITY, "straub_capacity", 2, 3},
 };
 const LsInfo* ls_info(int id) {
   for (const auto& l : kLs)

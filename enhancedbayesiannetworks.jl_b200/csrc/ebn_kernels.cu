@@ -57,16 +57,21 @@ LsVTable vt_straub();
 LsVTable vt_hydrogen();
 LsVTable vt_polynomial();
 LsVTable vt_min_affine();
+LsVTable vt_straub_r45();
+LsVTable vt_straub_capacity();
 
 const LsVTable* ls_vtable(int limit_state) {
   static const LsVTable v1 = vt_vehicle(), v2 = vt_straub(), v3 = vt_hydrogen(),
-                        v4 = vt_polynomial(), v5 = vt_min_affine();
+                        v4 = vt_polynomial(), v5 = vt_min_affine(), v6 = vt_straub_r45(),
+                        v7 = vt_straub_capacity();
   switch (limit_state) {
     case EBN_LS_VEHICLE_SUSPENSION: return &v1;
     case EBN_LS_STRAUB_FRAME: return &v2;
     case EBN_LS_HYDROGEN_RADIUS: return &v3;
     case EBN_LS_POLYNOMIAL: return &v4;
     case EBN_LS_MIN_AFFINE: return &v5;
+    case EBN_LS_STRAUB_FRAME_R45: return &v6;
+    case EBN_LS_STRAUB_CAPACITY: return &v7;
   }
   return nullptr;
 }

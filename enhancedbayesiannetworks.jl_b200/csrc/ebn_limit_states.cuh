@@ -202,6 +202,67 @@ struct StraubFrame {
 };
 
 // ---------------------------------------------------------------------------
+// Straub frame with R4, R5 as observed columns — test/inference/variableselimination.jl:207-217
+// (`frame_model.(df.r1, df.r2, df.r3, df.R4, df.R5, df.V, df.H)`).
+// x = (Ur, V, H, R4, R5, e1, e2, e3); consts = (lambda, zeta, rho).
+// ---------------------------------------------------------------------------
+template <class Ops>
+struct StraubFrameR45 {
+  static constexpr int ID = EBN_LS_STRAUB_FRAME_R45;
+  static constexpr bool HAS_FAILS = false;
+  static constexpr int MIN_BLOCKS = 2;
+  static constexpr int D = 8;
+  static constexpr int XCAP = 8;
+  static constexpr int NC = 3;
+  using Ctx = typename StraubFrame<Ops>::Ctx;
+  __device__ static void setup(Ctx& c, const double* k, int a, int b, const FastMathSmem* fm) {
+    StraubFrame<Ops>::setup(c, k, a, b, fm);
+  }
+  __device__ __forceinline__ static double eval(const Ctx& c, const double* x) {
+    const double ur = x[0], v = x[1], h = x[2];
+    const double mu = Ops::add(c.lambda, Ops::mul(c.rz, ur));
+    double r[5];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double a = Ops::add(mu, Ops::mul(c.sd, x[5 + i]));
+      r[i] = Ops::strict ? exp(a) : exp_fast(a, *c.fm);
+    }
+    r[3] = x[3];
+    r[4] = x[4];
+    const double h5 = Ops::mul(5.0, h), v5 = Ops::mul(5.0, v);
+    const double g1 = Ops::sub(Ops::add(Ops::add(Ops::add(r[0], r[1]), r[3]), r[4]), h5);
+    const double g2 = Ops::sub(Ops::add(Ops::add(r[1], Ops::mul(2.0, r[2])), r[3]), v5);
+    const double g3 = Ops::sub(
+        Ops::sub(Ops::add(Ops::add(Ops::add(r[0], Ops::mul(2.0, r[2])), Ops::mul(2.0, r[3])), r[4]),
+                 h5),
+        v5);
+    return Ops::min(Ops::min(g1, g2), g3);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// One plastic moment capacity — demo/straub_example.jl:16-26 (`plastic_moment_capacities`).
+// x = (Ur, e); consts = (lambda, zeta, rho); value r.
+// ---------------------------------------------------------------------------
+template <class Ops>
+struct StraubCapacity {
+  static constexpr int ID = EBN_LS_STRAUB_CAPACITY;
+  static constexpr bool HAS_FAILS = false;
+  static constexpr int MIN_BLOCKS = 3;
+  static constexpr int D = 2;
+  static constexpr int XCAP = 2;
+  static constexpr int NC = 3;
+  using Ctx = typename StraubFrame<Ops>::Ctx;
+  __device__ static void setup(Ctx& c, const double* k, int a, int b, const FastMathSmem* fm) {
+    StraubFrame<Ops>::setup(c, k, a, b, fm);
+  }
+  __device__ __forceinline__ static double eval(const Ctx& c, const double* x) {
+    const double a = Ops::add(Ops::add(c.lambda, Ops::mul(c.rz, x[0])), Ops::mul(c.sd, x[1]));
+    return Ops::strict ? exp(a) : exp_fast(a, *c.fm);
+  }
+};
+
+// ---------------------------------------------------------------------------
 // Hydrogen — reference demo/Hydrogen_new/ebn.jl:98-111 (`hyram_performance`).
 // x = (scenario, r_operators, burn_r_C_3th, explosion_r_C). The two radii come
 // from HyRAM, which is not in the reference repository; here they are inputs.

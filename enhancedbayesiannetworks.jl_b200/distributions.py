@@ -317,7 +317,12 @@ def table_for(dist: Distribution, lo: float, hi: float, npts: int = 4097) -> np.
     lo, hi = max(lo, a), min(hi, b)
     Fl, Fh = float(dist.cdf(lo)), float(dist.cdf(hi))
     if not Fh > Fl:
-        raise ValueError(f"{dist} has no mass in [{lo}, {hi}]")
+        # A window the (histogram) distribution gives no mass to, e.g. an outer bin no sample of a
+        # ContinuousFunctionalNode fell into. The reference's KDE has a positive tail there; the bin has
+        # probability 0 in the discretised parent, so any proper law on the window serves: uniform.
+        if not (np.isfinite(lo) and np.isfinite(hi)):
+            raise ValueError(f"{dist} has no mass in [{lo}, {hi}]")
+        return np.linspace(lo, hi, npts)
     eps = 1e-12
     u = np.linspace(0.0, 1.0, npts)
     p = np.clip(Fl + u * (Fh - Fl), eps if not np.isfinite(lo) else Fl, 1 - eps if not np.isfinite(hi) else Fh)

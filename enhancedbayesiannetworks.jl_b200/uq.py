@@ -91,16 +91,30 @@ def lower(models: Sequence[Model], performance, input_names: Sequence[str]) -> L
         raise UnsupportedModel("a Catalogue chain cannot be followed by a polynomial performance")
     ls = last.func.limit_state
     if ls == "straub_frame":
+        # demo/straub_example.jl after transmission: the capacity models r1..r5 (each with its own
+        # in-model randn → one hidden standard-normal input) followed by the frame model. With R4, R5
+        # discretised (test/inference/variableselimination.jl:207-217) only r1..r3 are fused and the
+        # frame reads the R4, R5 columns.
         caps = cats[:-1]
-        if len(caps) != 5 or any(c.func.limit_state != "straub_capacity" for c in caps):
-            raise UnsupportedModel("straub_frame expects the five straub_capacity models r1..r5 before it")
-        consts = np.array(caps[0].func.consts)
+        if any(c.func.limit_state != "straub_capacity" for c in caps) or len(last.func.args) != 7:
+            raise UnsupportedModel("straub_frame expects straub_capacity models before it and 7 arguments")
+        consts = np.array(caps[0].func.consts) if caps else np.array(last.func.consts)
+        made = [c.name for c in caps]
+        r_args, (v_arg, h_arg) = list(last.func.args[:5]), last.func.args[5:]
         ur = caps[0].func.args[0]
-        order = [ur] + [a for a in last.func.args if a not in [c.name for c in caps]]
-        hidden = [Normal(0.0, 1.0).abi()] * 5
-        cols = order
+        if all(a in made for a in r_args):
+            ls, cols = "straub_frame", [ur, v_arg, h_arg]
+        elif all(a in made for a in r_args[:3]) and not any(a in made for a in r_args[3:]):
+            ls, cols = "straub_frame_r45", [ur, v_arg, h_arg, r_args[3], r_args[4]]
+        else:
+            raise UnsupportedModel("straub_frame supports r1..r5 (or r1..r3) produced by straub_capacity models")
+        hidden = [Normal(0.0, 1.0).abi()] * sum(a in made for a in r_args)
     elif ls == "straub_capacity":
-        raise UnsupportedModel("straub_capacity models are only supported fused into straub_frame")
+        if len(cats) != 1:
+            raise UnsupportedModel("straub_capacity evaluates one capacity; chains end in straub_frame")
+        consts = np.array(last.func.consts)
+        cols = [last.func.args[0]]
+        hidden = [Normal(0.0, 1.0).abi()]
     else:
         consts = np.array(last.func.consts)
         if len(cats) != 1:

@@ -66,7 +66,16 @@ enum {
   EBN_LS_POLYNOMIAL = 4,
   /* min over several affine forms  g = min_k (c_k0 + sum_j c_kj x_j).
    * consts (K, then K rows of 1+d coefficients). d = n_inputs of the job.     */
-  EBN_LS_MIN_AFFINE = 5
+  EBN_LS_MIN_AFFINE = 5,
+  /* Straub frame with R4 and R5 observed (test/inference/variableselimination.jl:207-284: R4, R5
+   * are discretised continuous functional nodes, so the frame reads their columns directly).
+   * inputs (Ur, V, H, R4, R5, e1, e2, e3); consts (lambda, zeta, rho).                     */
+  EBN_LS_STRAUB_FRAME_R45 = 6,
+  /* One plastic moment capacity r = exp(lambda + rho*zeta*u_r + sqrt((1-rho^2) zeta^2) * e)
+   * (demo/straub_example.jl:16-26) — the model of a ContinuousFunctionalNode R_i that is
+   * evaluated on its own (histogram path). inputs (Ur, e); consts (lambda, zeta, rho).
+   * As a limit state its value is r itself.                                              */
+  EBN_LS_STRAUB_CAPACITY = 7
 };
 
 /*

@@ -88,6 +88,31 @@ static double g_straub(const double *x, const double *k) {
   return jl_min(jl_min(g1, g2), g3);
 }
 
+/* test/inference/variableselimination.jl:207-217: the frame with R4, R5 read as columns.
+ * x = (Ur, V, H, R4, R5, e1, e2, e3). */
+static double g_straub_r45(const double *x, const double *k) {
+  const double ur = x[0], v = x[1], h = x[2];
+  const double lambda = k[0], zeta = k[1], rho = k[2];
+  const double normal_mu = lambda + (rho * zeta) * ur;
+  const double normal_std = sqrt((1.0 - rho * rho) * (zeta * zeta));
+  double r[5];
+  for (int i = 0; i < 3; ++i) r[i] = exp(normal_mu + normal_std * x[5 + i]);
+  r[3] = x[3];
+  r[4] = x[4];
+  const double g1 = (((r[0] + r[1]) + r[3]) + r[4]) - 5.0 * h;
+  const double g2 = ((r[1] + 2.0 * r[2]) + r[3]) - 5.0 * v;
+  const double g3 = ((((r[0] + 2.0 * r[2]) + 2.0 * r[3]) + r[4]) - 5.0 * h) - 5.0 * v;
+  return jl_min(jl_min(g1, g2), g3);
+}
+
+/* demo/straub_example.jl:16-26 (plastic_moment_capacities): x = (Ur, e). */
+static double g_straub_capacity(const double *x, const double *k) {
+  const double lambda = k[0], zeta = k[1], rho = k[2];
+  const double normal_mu = lambda + (rho * zeta) * x[0];
+  const double normal_std = sqrt((1.0 - rho * rho) * (zeta * zeta));
+  return exp(normal_mu + normal_std * x[1]);
+}
+
 /* demo/Hydrogen_new/ebn.jl:98-108 (hyram_performance). */
 static double g_hydrogen(const double *x) {
   if (x[0] == 1.0) return x[1] - x[2];
@@ -134,6 +159,8 @@ static double limit_state(int ls, const double *consts, double *x, int d) {
     case EBN_LS_HYDROGEN_RADIUS: return g_hydrogen(x);
     case EBN_LS_POLYNOMIAL: return g_polynomial(x, d, consts);
     case EBN_LS_MIN_AFFINE: return g_min_affine(x, d, consts);
+    case EBN_LS_STRAUB_FRAME_R45: return g_straub_r45(x, consts);
+    case EBN_LS_STRAUB_CAPACITY: return g_straub_capacity(x, consts);
   }
   return NAN;
 }

@@ -439,3 +439,57 @@ def test_joint_distribution_gaussian_copula(E):
     assert pf_ind < pf - 0.003
     with pytest.raises(ValueError, match="correlation matrix"):
         E.GaussianCopula([[1.0, 0.5], [0.4, 1.0]])
+
+
+def test_straub_with_evidence_posterior(E):
+    """test/inference/variableselimination.jl:207-284: R4 and R5 are continuous functional nodes with
+    21 cut points each (22 bins after the support ends are added); they are evaluated to histograms,
+    discretised, and the frame node is evaluated for all 22 x 22 scenarios with
+    truncated(EmpiricalDistribution) capacities. The reference then asserts
+    P(E | R4 in [140,150], R5 in [90.01,100.01]) ≈ [0.035, 0.965] (atol 0.05) — with both parents
+    observed that posterior is the CPT row itself."""
+    lam, zeta = E.distribution_parameters(150, 30, "LogNormal")
+    ur = _cont_root(E, "Uᵣ", E.Normal())
+    v = _cont_root(E, "V", E.Gamma(*E.distribution_parameters(60, 12, "Gamma")))
+    h = _cont_root(E, "H", E.Gumbel(*E.distribution_parameters(50, 20, "Gumbel")))
+    n2 = 2000
+    sim = E.MonteCarlo(n2)
+    cap = lambda i: E.Model(E.Catalogue("straub_capacity", (lam, zeta, 0.5477), ("Uᵣ",)), f"r{i}")
+    rs = [E.ContinuousFunctionalNode(f"R{i}", [cap(i)], sim) for i in (1, 2, 3)]
+    # collect(range(50, 250, 21)) / collect(range(50.01, 250.01, 21)): Julia's ranges give the exact decimals
+    d1 = E.ApproximatedDiscretization([50.0 + 10 * i for i in range(21)], 1)
+    d2 = E.ApproximatedDiscretization([round(50.01 + 10 * i, 2) for i in range(21)], 1)
+    r4 = E.ContinuousFunctionalNode("R4", [cap(4)], sim, d1)
+    r5 = E.ContinuousFunctionalNode("R5", [cap(5)], sim, d2)
+    frame = E.DiscreteFunctionalNode(
+        "E", [E.Model(E.Catalogue("straub_frame", (), ("r1", "r2", "r3", "R4", "R5", "V", "H")), "G")], "G", sim)
+    net = E.EnhancedBayesianNetwork([ur, v, h] + rs + [r4, r5, frame])
+    for r in rs + [r4, r5]:
+        E.add_child(net, ur, r)
+        E.add_child(net, r, frame)
+    E.add_child(net, v, frame)
+    E.add_child(net, h, frame)
+    E.order(net)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        E.evaluate(net, True, False)
+    assert sorted(n.name for n in net.nodes) == ["E", "H", "R4", "R4_d", "R5", "R5_d", "Uᵣ", "V"]
+    e = net.node("E")
+    assert sorted(e.cpt.names[:-1]) == ["R4_d", "R5_d"]
+    n4, n5 = len(net.node("R4_d").states()), len(net.node("R5_d").states())
+    assert n4 >= 20 and n5 >= 20 and len(e.cpt.data) == 2 * n4 * n5
+    post = e.cpt[{"R4_d": "[140.0, 150.0]", "R5_d": "[90.01, 100.01]", "E": "E_fail"}]
+    assert abs(post - 0.035) < 0.05 and abs((1 - post) - 0.965) < 0.05          # the reference's assertion
+    # bin probabilities of R4_d follow LogNormal(lambda, zeta): P(140 < R4 < 150)
+    from scipy.stats import lognorm
+    p_bin = lognorm(zeta, scale=math.exp(lam)).cdf(150) - lognorm(zeta, scale=math.exp(lam)).cdf(140)
+    assert abs(net.node("R4_d").cpt[("R4_d", "[140.0, 150.0]")] - p_bin) < 0.03   # n = 2000
+    # weak capacities fail more often than strong ones
+    lo = e.cpt[{"R4_d": "[60.0, 70.0]", "R5_d": "[60.01, 70.01]", "E": "E_fail"}]
+    hi = e.cpt[{"R4_d": "[200.0, 210.0]", "R5_d": "[200.01, 210.01]", "E": "E_fail"}]
+    assert lo > post > hi
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        E.reduce(net)
+    assert sorted(n.name for n in net.nodes) == ["E", "R4_d", "R5_d"]          # adjacency :263-267
+    assert net.adj_matrix.sum() == 2 and net.adj_matrix[:, net.topology_dict["E"]].sum() == 2

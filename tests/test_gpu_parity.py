@@ -103,6 +103,26 @@ def test_eval_matrix_straub(ebn):
     assert 0 < want_cnt < len(X)
 
 
+def test_eval_matrix_straub_variants(ebn):
+    """The frame with observed R4/R5 and the single capacity against the oracle (same exp tolerance)."""
+    from ebn_b200 import workloads as W
+    rng = np.random.default_rng(31)
+    n = 100_000
+    k = W.straub_consts()
+    X = np.column_stack([rng.normal(0, 1, n), rng.gamma(25.0, 2.4, n), rng.gumbel(41.0, 15.6, n),
+                         rng.lognormal(k[0], k[1], (n, 2)), rng.normal(0, 1, (n, 3))])
+    for strict in (True, False):
+        want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_STRAUB_R45, k, X, want_g=True)
+        got_cnt, got_g = ebn.eval_matrix(ebn._lib.LS_STRAUB_FRAME_R45, k, X, strict=strict, want_g=True)
+        assert np.max(np.abs(got_g - want_g)) < 1e-9 and abs(got_cnt - want_cnt) <= np.sum(np.abs(want_g) < 1e-9)
+        assert 0 < want_cnt < n
+        want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_STRAUB_CAPACITY, k, X[:, [0, 5]], want_g=True)
+        got_cnt, got_g = ebn.eval_matrix(ebn._lib.LS_STRAUB_CAPACITY, k, X[:, [0, 5]], strict=strict, want_g=True)
+        assert np.max(np.abs(got_g / want_g - 1)) < 1e-14 and got_cnt == 0 == want_cnt
+    # exp_fast against the correctly rounded value: a few ulp over the lognormal range
+    assert np.max(np.abs(got_g / np.exp(k[0] + k[2] * k[1] * X[:, 0] + np.sqrt((1 - k[2] ** 2) * k[1] ** 2) * X[:, 5]) - 1)) < 1e-14
+
+
 def test_eval_matrix_polynomial_and_min_affine_bit_exact(ebn):
     rng = np.random.default_rng(4)
     X = rng.normal(0.5, 1.0, (100_000, 2))

@@ -273,6 +273,11 @@ def test_lowering_model_chains():
     frame = E.Model(E.Catalogue("straub_frame", (), ("r1", "r2", "r3", "r4", "r5", "V", "H")), "G")
     low = uq.lower(caps + [frame], "G", ["H", "Uᵣ", "V"])
     assert low.limit_state == E._lib.LS_STRAUB_FRAME and low.columns == ["Uᵣ", "V", "H"] and len(low.hidden) == 5
+    frame45 = E.Model(E.Catalogue("straub_frame", (), ("r1", "r2", "r3", "R4", "R5", "V", "H")), "G")
+    low = uq.lower(caps[:3] + [frame45], "G", ["H", "R4", "R5", "Uᵣ", "V"])
+    assert low.limit_state == E._lib.LS_STRAUB_FRAME_R45 and low.columns == ["Uᵣ", "V", "H", "R4", "R5"] and len(low.hidden) == 3
+    low = uq.lower(caps[3:4], None, ["Uᵣ"])
+    assert low.limit_state == E._lib.LS_STRAUB_CAPACITY and low.columns == ["Uᵣ"] and len(low.hidden) == 1
 
 
 def test_distributions_host_side():
