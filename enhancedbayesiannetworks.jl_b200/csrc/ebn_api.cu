@@ -608,8 +608,6 @@ int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, i
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, dv.ev0, dv.ev1));
     if (ms > kms) kms = ms;
-    // samples done by this device: every pair of its items, clipped to [first,last)
-    my_samples += 0;
   }
   CU(cudaSetDevice(d0.id));
   if (mode == 1) {
@@ -618,8 +616,7 @@ int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, i
       if (sumsq_out) sumsq_out[s] = sums[(size_t)S + s];
     }
   }
-  // samples processed by this process = its share of items (approximately
-  // n*S/world; exact accounting by items)
+  // samples processed by this process: its share of the work items
   {
     const int64_t total_items = P.items_per_scenario * S;
     int64_t mine = 0;

@@ -30,7 +30,7 @@ const LIB = Ref{String}(get(ENV, "EBNCUDA_LIB", "libebncuda.so"))
 
 # ---- constants of include/ebncuda.h ------------------------------------------------------------
 const EBN_LS = Dict(:vehicle_suspension => 1, :straub_frame => 2, :hydrogen_radius => 3,
-    :polynomial => 4, :min_affine => 5)
+    :polynomial => 4, :min_affine => 5, :straub_frame_r45 => 6, :straub_capacity => 7)
 const IN_PARAM, IN_NORMAL, IN_LOGNORMAL, IN_UNIFORM, IN_GUMBEL, IN_GAMMA, IN_EXP_AFFINE, IN_TABULATED = 0:7
 
 # typedef struct ebn_input { int32 kind; int32 flags; double p[4]; double lo; double hi; }  (56 bytes)
@@ -165,7 +165,9 @@ function pf_batch(model::CudaModel, scenario_inputs::Vector{<:Vector}, sim::Cuda
     return counts, pf, var
 end
 
-hidden_inputs(m::CudaModel) = m.limit_state == :straub_frame ? fill(abi(Normal(), -Inf, Inf), 5) : EbnInput[]
+# the in-model `rand(Normal(...))` draws of the Straub capacities travel as hidden N(0,1) inputs
+const N_HIDDEN = Dict(:straub_frame => 5, :straub_frame_r45 => 3, :straub_capacity => 1)
+hidden_inputs(m::CudaModel) = fill(abi(Normal(), -Inf, Inf), get(N_HIDDEN, m.limit_state, 0))
 
 # UQ.jl-style single-scenario entry (demo/vehicle_suspension.jl:68)
 function UncertaintyQuantification.probability_of_failure(models::Union{CudaModel,Vector{CudaModel}},
