@@ -96,7 +96,10 @@ def cpu_reference_run(n_per_scenario: int, threads: int):
     job = W.w1_vehicle(n=n_per_scenario)
     inp = job.inputs.view(ocpu.INPUT_DTYPE)
     t0 = time.perf_counter()
-    cnt = ocpu.pf_batch(ocpu.LS_VEHICLE, job.consts, inp, n_per_scenario, seed=12345, threads=threads, block=0)
+    # columns are materialised like UQ.jl's `sample` does, in blocks of at most 5e6 rows so that all
+    # host threads together stay within a few GB
+    cnt = ocpu.pf_batch(ocpu.LS_VEHICLE, job.consts, inp, n_per_scenario, seed=12345, threads=threads,
+                        block=min(n_per_scenario, 5_000_000))
     dt = time.perf_counter() - t0
     return job.S * n_per_scenario / dt, dt, cnt
 
@@ -138,7 +141,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-per-scenario", type=float, default=1e8, help="per GPU (weak scaling)")
-    ap.add_argument("--cpu-n", type=int, default=5_000_000, help="CPU arm: samples per scenario per step")
+    ap.add_argument("--cpu-n", type=int, default=50_000_000,
+                    help="CPU arm: samples per scenario per step (20 scenarios; ~10 s on 16 cores)")
     ap.add_argument("--strict", action="store_true", help="Julia-order limit state (no FMA contraction)")
     ap.add_argument("--workload", default="w1", choices=["w1", "w5"],
                     help="w1: BASELINE configs[1] (default, weak scaling); w5: configs[4], 1024 scenarios x "
