@@ -396,8 +396,8 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
       }
     }
     P.plan_class = PLAN_COPULA;
-  } else if (static_plan_matches(job->limit_state, P.plan.data(), S, d)) {
-    P.plan_class = PLAN_STATIC;
+  } else if (const int which = static_plan_matches(job->limit_state, P.plan.data(), S, d)) {
+    P.plan_class = which == 1 ? PLAN_STATIC : PLAN_STATIC2;
   }
   P.world = jw * (ndev_override > 0 ? ndev_override : (int)g.devs.size());
   P.first = job->sample_offset;
@@ -630,7 +630,7 @@ int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, i
   g.stats.samples = my_samples;
   g.stats.launches = (int)nd * (mode == 1 ? 2 : 1);
   g.stats.devices = (int)nd;
-  g.stats.specialised = P.plan_class == PLAN_STATIC;
+  g.stats.specialised = P.plan_class == PLAN_STATIC || P.plan_class == PLAN_STATIC2;
   return EBN_OK;
 }
 

@@ -76,13 +76,20 @@ const LsVTable* ls_vtable(int limit_state) {
   return nullptr;
 }
 
-bool static_plan_matches(int limit_state, const DevInput* plan, int S, int d) {
+int static_plan_matches(int limit_state, const DevInput* plan, int S, int d) {
   const LsVTable* v = ls_vtable(limit_state);
-  if (!v || !v->static_kinds || v->n_static != d) return false;
-  for (int s = 0; s < S; ++s)
-    for (int j = 0; j < d; ++j)
-      if (plan[(int64_t)s * d + j].kind != v->static_kinds[j]) return false;
-  return true;
+  if (!v) return 0;
+  const int* kinds[2] = {v->static_kinds, v->static_kinds2};
+  const int n[2] = {v->n_static, v->n_static2};
+  for (int which = 0; which < 2; ++which) {
+    if (!kinds[which] || n[which] != d) continue;
+    bool ok = true;
+    for (int s = 0; s < S && ok; ++s)
+      for (int j = 0; j < d; ++j)
+        if (plan[(int64_t)s * d + j].kind != kinds[which][j]) { ok = false; break; }
+    if (ok) return which + 1;
+  }
+  return 0;
 }
 
 cudaError_t moments_launch(const double* partial, int64_t local_items, int64_t items_per_scenario,

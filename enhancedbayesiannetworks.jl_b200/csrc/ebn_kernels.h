@@ -9,10 +9,11 @@
 
 namespace ebn {
 
-enum PlanClass { PLAN_DYNAMIC = 0, PLAN_STATIC = 1, PLAN_COPULA = 2 };
+enum PlanClass { PLAN_DYNAMIC = 0, PLAN_STATIC = 1, PLAN_COPULA = 2, PLAN_STATIC2 = 3 };
 
 int threads_per_block();
-bool static_plan_matches(int limit_state, const DevInput* plan, int S, int d);
+// 0: no compile-time plan matches every scenario; 1 / 2: the limit state's first / second plan does.
+int static_plan_matches(int limit_state, const DevInput* plan, int S, int d);
 
 // Launchers of one limit state (filled by its translation unit).
 struct LsVTable {
@@ -26,6 +27,8 @@ struct LsVTable {
                         cudaStream_t st);
   const int* static_kinds;  // compile-time sampling plan, if the limit state has one
   int n_static;
+  const int* static_kinds2;  // an optional second one
+  int n_static2;
 };
 const LsVTable* ls_vtable(int limit_state);
 

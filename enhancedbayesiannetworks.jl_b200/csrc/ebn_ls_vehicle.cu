@@ -4,5 +4,11 @@
 namespace ebn {
 // vehicle suspension W1/W5: (A, b0) Parameters, V uniform (a truncated uniform is
 // again uniform), C, Ck, K untruncated normals.
-LsVTable vt_vehicle() { return LsLaunch<VehicleSuspension, StaticPlan<DK_CONST, DK_CONST, DK_UNIFORM, DK_NORMAL_BM, DK_NORMAL_BM, DK_NORMAL_BM>>::vtable(); }
+// Second plan: V a Parameter as well — what the imprecise outer loop (DoubleLoop over an interval V,
+// demo/vehicle_suspension_imprecise.jl) and `probability_of_failure` with a fixed V produce.
+LsVTable vt_vehicle() {
+  return LsLaunch<VehicleSuspension,
+                  StaticPlan<DK_CONST, DK_CONST, DK_UNIFORM, DK_NORMAL_BM, DK_NORMAL_BM, DK_NORMAL_BM>,
+                  StaticPlan<DK_CONST, DK_CONST, DK_CONST, DK_NORMAL_BM, DK_NORMAL_BM, DK_NORMAL_BM>>::vtable();
+}
 }  // namespace ebn

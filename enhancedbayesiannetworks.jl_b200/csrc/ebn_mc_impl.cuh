@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(kThreads) matrix_kernel(const double* consts, 
 // per-limit-state table of launchers (one translation unit per limit state so
 // the build parallelises)
 // ---------------------------------------------------------------------------
-template <template <class> class LST, class SPlan>
+template <template <class> class LST, class SPlan, class SPlan2 = NoStaticPlan>
 struct LsLaunch {
   template <class LS, class Plan>
   static cudaError_t occ2(int mode, size_t dyn, int* out) {
@@ -465,6 +465,9 @@ struct LsLaunch {
     if constexpr (SPlan::is_static) {
       if (plan_class == PLAN_STATIC) return occ2<LS, SPlan>(mode, dyn, out);
     }
+    if constexpr (SPlan2::is_static) {
+      if (plan_class == PLAN_STATIC2) return occ2<LS, SPlan2>(mode, dyn, out);
+    }
     return occ2<LS, DynamicPlan>(mode, dyn, out);
   }
   template <class LS>
@@ -474,6 +477,9 @@ struct LsLaunch {
     if constexpr (SPlan::is_static) {
       if (plan_class == PLAN_STATIC) return launch2<LS, SPlan>(mode, p, blocks, dyn, st);
     }
+    if constexpr (SPlan2::is_static) {
+      if (plan_class == PLAN_STATIC2) return launch2<LS, SPlan2>(mode, p, blocks, dyn, st);
+    }
     return launch2<LS, DynamicPlan>(mode, p, blocks, dyn, st);
   }
   template <class LS>
@@ -482,6 +488,9 @@ struct LsLaunch {
     if (plan_class == PLAN_COPULA) return replay2<LS, CopulaPlan>(p, scenario, n, X, g, blocks, st);
     if constexpr (SPlan::is_static) {
       if (plan_class == PLAN_STATIC) return replay2<LS, SPlan>(p, scenario, n, X, g, blocks, st);
+    }
+    if constexpr (SPlan2::is_static) {
+      if (plan_class == PLAN_STATIC2) return replay2<LS, SPlan2>(p, scenario, n, X, g, blocks, st);
     }
     return replay2<LS, DynamicPlan>(p, scenario, n, X, g, blocks, st);
   }
@@ -521,6 +530,13 @@ struct LsLaunch {
     } else {
       v.static_kinds = nullptr;
       v.n_static = 0;
+    }
+    if constexpr (SPlan2::is_static) {
+      v.static_kinds2 = SPlan2::kinds;
+      v.n_static2 = SPlan2::n;
+    } else {
+      v.static_kinds2 = nullptr;
+      v.n_static2 = 0;
     }
     return v;
   }

@@ -65,6 +65,26 @@ def w5_vehicle_grid(n: int = 10**10, seed: int = 0x5EED0005, side: int = 32, str
     return L.Job(L.LS_VEHICLE_SUSPENSION, vehicle_consts(), L.make_inputs(rows), n, seed, strict)
 
 
+def w4_vehicle_fixed_v(v_values, n: int = 10**6, seed: int = 0x5EED0004, strict: bool = False,
+                       crn: bool = True) -> L.Job:
+    """W4 = BASELINE config 4, the inner estimator of the imprecise vehicle net
+    (demo/vehicle_suspension_imprecise.jl): every (A, b0) state x every outer-loop value of V, with V
+    entering as a Parameter (evaluate_node.jl:104-117 -> UQ.jl DoubleLoop). `crn` gives all V values
+    of one (A, b0) state the same stream (common random numbers across the outer loop)."""
+    rows, streams = [], []
+    k = 0
+    for A in (0.8, 0.15915):
+        for b0 in (0.27, 0.5):
+            for v in v_values:
+                row = _veh_row(A, b0, -INF, INF)
+                row[2] = (L.IN_PARAM, float(v), 0, 0, 0, -INF, INF)
+                rows.append(row)
+                streams.append(k if crn else len(streams))
+            k += 1
+    return L.Job(L.LS_VEHICLE_SUSPENSION, vehicle_consts(), L.make_inputs(rows), n, seed, strict,
+                 stream_id=np.asarray(streams, dtype=np.uint32))
+
+
 # demo/straub_example.jl:5-24 — distribution_parameters(mean, std, Dist)
 STRAUB_RHO = 0.5477
 

@@ -263,6 +263,34 @@ def test_fused_count_equals_oracle_on_replayed_matrix_straub(ebn):
     assert abs(pf[0] - 0.026129) < 0.01
 
 
+def test_fused_count_equals_oracle_vehicle_fixed_v_plan(ebn):
+    """Second compile-time plan of the vehicle limit state (V a Parameter): the inner estimator of the
+    imprecise net's DoubleLoop. Counts match the oracle on the replayed matrix, the V column is the
+    parameter itself, and common random numbers make the vertices of one state share C, Ck, K."""
+    from ebn_b200 import workloads as W
+    n = 200_001
+    vs = [7.0, 9.5, 12.0]
+    job = W.w4_vehicle_fixed_v(vs, n=n, strict=True)
+    cnt, pf, _ = ebn.pf_batch(job)
+    assert ebn.last_stats()["specialised"] == 1
+    mats = {}
+    for s in (0, 1, 2, 5, job.S - 1):
+        X = ebn.sample_matrix(job, s, 0, n)
+        mats[s] = X
+        assert np.all(X[:, 2] == vs[s % 3])
+        assert int(cnt[s]) == ocpu.eval_matrix(ocpu.LS_VEHICLE, job.consts, X), s
+    assert np.array_equal(mats[0][:, 3:], mats[1][:, 3:]) and np.array_equal(mats[0][:, 3:], mats[2][:, 3:])
+    assert not np.array_equal(mats[0][:, 3:], mats[5][:, 3:])
+    # same streams through the runtime-dispatched plan (a mixed job cannot use a compile-time plan)
+    rows = [list(map(tuple, [(int(c["kind"]), *c["p"], c["lo"], c["hi"]) for c in job.inputs[s]])) for s in range(3)]
+    rows.append(W._veh_row(0.8, 0.27, 7.0, 8.5))
+    mixed = ebn.Job(job.limit_state, job.consts, ebn.make_inputs(rows), n=n, seed=job.seed, strict=True,
+                    stream_id=np.array([0, 0, 0, 7], dtype=np.uint32))
+    cnt_dyn, _, _ = ebn.pf_batch(mixed)
+    assert ebn.last_stats()["specialised"] == 0
+    assert np.array_equal(cnt_dyn[:3], cnt[:3])
+
+
 def test_fused_dynamic_plan_all_kinds(ebn):
     """Generic (runtime-dispatched) sampling plan: fused count == oracle on the replayed matrix."""
     inputs = ebn.make_inputs([ALL_KINDS_ROW, ALL_KINDS_ROW[::-1][1:] + [ALL_KINDS_ROW[-1]]])

@@ -33,6 +33,7 @@ run("W1 vehicle (strict: Julia-order g, 6 div + sqrt)", W.w1_vehicle(n=10**8, st
 run("W2 Straub frame S=1", W.w2_straub(n=10**9))
 run("W3 Straub-style copula, 64 scenarios", W.w3_straub_copula(n=2 * 10**7))
 run("W5 vehicle grid, 1024 scenarios", W.w5_vehicle_grid(n=4 * 10**6))
+run("W4 vehicle, V fixed: 4 states x 25 outer-loop values", W.w4_vehicle_fixed_v(np.linspace(7, 12, 25), n=2 * 10**7))
 j = W.w1_vehicle(n=10**8)
 j.inputs[:, 3]["lo"] = 400.0   # truncated normals: inverse-CDF path through the generic plan
 run("W1 with C truncated at 400 (generic plan)", j)
