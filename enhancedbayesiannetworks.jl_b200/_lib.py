@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EBN_LIB", os.path.join(_HERE, "libebncuda.so"))  # EBN_LIB: tuning builds only
 
 # ---- constants mirrored from include/ebncuda.h ------------------------------
-EBN_ABI_VERSION = 1
+EBN_ABI_VERSION = 2
 EBN_MAX_INPUTS = 16
 EBN_MAX_EDGES = 1025
 
@@ -28,6 +28,11 @@ LS_POLYNOMIAL = 4
 LS_MIN_AFFINE = 5
 LS_STRAUB_FRAME_R45 = 6
 LS_STRAUB_CAPACITY = 7
+LS_EXPRESSION = 8
+
+# expression program opcodes (EBN_OP_*)
+(OP_INPUT, OP_PARAM, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_ABS, OP_SQRT, OP_EXP, OP_LOG,
+ OP_SIN, OP_COS, OP_MIN, OP_MAX, OP_POW, OP_POWI, OP_LT, OP_SELECT, OP_STORE) = range(21)
 
 IN_PARAM = 0
 IN_NORMAL = 1
@@ -40,9 +45,12 @@ IN_TABULATED = 7
 
 JOB_COPULA_SHARED = 1
 JOB_PARTIAL = 2
+JOB_JIT_PLAN = 4
+JOB_NO_JIT_PLAN = 8
 
 ERROR_NAMES = {0: "EBN_OK", -1: "EBN_EINVAL", -2: "EBN_ELIMITSTATE", -3: "EBN_EMARGINAL",
-               -4: "EBN_ECUDA", -5: "EBN_ENCCL", -6: "EBN_ENODEV", -7: "EBN_ENOMEM", -8: "EBN_ESTATE"}
+               -4: "EBN_ECUDA", -5: "EBN_ENCCL", -6: "EBN_ENODEV", -7: "EBN_ENOMEM", -8: "EBN_ESTATE",
+               -9: "EBN_EJIT"}
 
 INPUT_DTYPE = np.dtype(
     [("kind", "<i4"), ("flags", "<i4"), ("p", "<f8", (4,)), ("lo", "<f8"), ("hi", "<f8")]
@@ -65,7 +73,7 @@ class EbnStats(C.Structure):
     _fields_ = [
         ("kernel_ms", C.c_double), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
         ("samples", C.c_int64), ("launches", C.c_int32), ("devices", C.c_int32),
-        ("specialised", C.c_int32), ("reserved", C.c_int32),
+        ("specialised", C.c_int32), ("jit_compiles", C.c_int32),
     ]
 
 
@@ -76,6 +84,7 @@ EXPORTS = [
     "ebn_nccl_unique_id", "ebn_comm_init_rank", "ebn_comm_destroy", "ebn_pf_batch",
     "ebn_hist_batch", "ebn_eval_matrix", "ebn_sample_matrix", "ebn_sample_matrix_ex", "ebn_peak_fp64", "ebn_last_stats",
     "ebn_partition", "ebn_last_error", "ebn_limit_state_id", "ebn_limit_state_name", "ebn_limit_state_arity",
+    "ebn_jit_available", "ebn_expression_check", "ebn_expression_source", "ebn_jit_compile",
 ]
 
 
@@ -119,6 +128,11 @@ def load():
     L.ebn_limit_state_name.restype = C.c_char_p
     L.ebn_limit_state_name.argtypes = [C.c_int]
     L.ebn_limit_state_arity.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ebn_jit_available.restype = C.c_int
+    L.ebn_expression_check.argtypes = [dp, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.ebn_expression_source.restype = C.c_int64
+    L.ebn_expression_source.argtypes = [dp, C.c_int, C.c_int, C.c_char_p, C.c_int64]
+    L.ebn_jit_compile.argtypes = [C.POINTER(EbnJob), C.c_int, i64p]
     if L.ebn_abi_version() != EBN_ABI_VERSION:
         raise RuntimeError("libebncuda.so ABI version mismatch")
     _lib = L
@@ -219,6 +233,7 @@ class Job:
     shard_rank: int = 0
     shard_world: int = 1
     partial: bool = False          # EBN_JOB_PARTIAL: this shard's counts only
+    jit_plan: Optional[bool] = None  # True: EBN_JOB_JIT_PLAN, False: EBN_JOB_NO_JIT_PLAN, None: library decides
 
     def __post_init__(self):
         self.consts = np.ascontiguousarray(self.consts, dtype=np.float64).ravel()
@@ -253,6 +268,8 @@ class Job:
         j.seed = self.seed & 0xFFFFFFFFFFFFFFFF
         j.strict = 1 if self.strict else 0
         j.flags = JOB_PARTIAL if self.partial else 0
+        if self.jit_plan is not None:
+            j.flags |= JOB_JIT_PLAN if self.jit_plan else JOB_NO_JIT_PLAN
         if self.corr_chol is not None:
             j.corr_chol = self.corr_chol.ctypes.data
             if self.corr_chol.ndim == 2:
@@ -336,7 +353,40 @@ def peak_fp64(seconds: float = 0.25) -> float:
 def last_stats() -> dict:
     st = EbnStats()
     _check(load().ebn_last_stats(C.byref(st)))
-    return {k: getattr(st, k) for k, _ in EbnStats._fields_ if k != "reserved"}
+    return {k: getattr(st, k) for k, _ in EbnStats._fields_}
+
+
+def jit_available() -> bool:
+    """ebn_jit_available: can kernels be compiled at run time (libnvrtc loadable)? Needs no GPU."""
+    return bool(load().ebn_jit_available())
+
+
+def expression_check(consts, d: int) -> int:
+    """ebn_expression_check → number of columns (d + stored model outputs). Raises on a bad program."""
+    consts = np.ascontiguousarray(consts, dtype=np.float64).ravel()
+    ncol = C.c_int(0)
+    _check(load().ebn_expression_check(_dp(consts) if consts.size else None, consts.size, d, C.byref(ncol)))
+    return ncol.value
+
+
+def expression_source(consts, d: int) -> str:
+    """ebn_expression_source: the CUDA functor generated for an expression program."""
+    consts = np.ascontiguousarray(consts, dtype=np.float64).ravel()
+    L = load()
+    n = L.ebn_expression_source(_dp(consts) if consts.size else None, consts.size, d, None, 0)
+    if n < 0:
+        raise EbnError(int(n), L.ebn_last_error().decode())
+    buf = C.create_string_buffer(int(n) + 1)
+    L.ebn_expression_source(_dp(consts), consts.size, d, buf, int(n) + 1)
+    return buf.value.decode()
+
+
+def jit_compile(job: Job, role: int = 0) -> int:
+    """ebn_jit_compile → bytes of machine code (0: the job runs a compiled-in kernel). Needs no GPU."""
+    out = C.c_int64(0)
+    cj = job.c_struct()
+    _check(load().ebn_jit_compile(C.byref(cj), role, C.byref(out)))
+    return out.value
 
 
 def limit_state_id(name: str) -> int:

@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include "ebn_expr.h"
+#include "ebn_jit.h"
 #include "ebn_kernels.h"
 
 static_assert(sizeof(ebn_input_t) == 56, "ebn_input_t must be 56 bytes");
@@ -279,6 +281,7 @@ const LsInfo kLs[] = {
     {EBN_LS_MIN_AFFINE, "min_affine", -1, -1},
     {EBN_LS_STRAUB_FRAME_R45, "straub_frame_r45", 8, 3},
     {EBN_LS_STRAUB_CAPACITY, "straub_capacity", 2, 3},
+    {EBN_LS_EXPRESSION, "expression", -1, -1},
 };
 const LsInfo* ls_info(int id) {
   for (const auto& l : kLs)
@@ -325,6 +328,9 @@ int check_limit_state(int id, const double* consts, int n_consts, int d) {
     }
     if (pos != n_consts)
       return fail(EBN_ELIMITSTATE, "polynomial program has %d trailing consts", n_consts - pos);
+  } else if (id == EBN_LS_EXPRESSION) {
+    const std::string bad = expr_check(consts, n_consts, d, nullptr);
+    if (!bad.empty()) return fail(EBN_ELIMITSTATE, "%s", bad.c_str());
   } else if (id == EBN_LS_MIN_AFFINE) {
     if (n_consts < 1) return fail(EBN_ELIMITSTATE, "min_affine needs consts");
     const int K = (int)consts[0];
@@ -346,7 +352,74 @@ struct Prepared {
   int plan_class = PLAN_DYNAMIC;
   int64_t first = 0, last = 0, pair_base = 0, pairs_per_item = 0, items_per_scenario = 0;
   int world = 1;  // job world * devices
+  // run-time compiled kernels (expression limit states, sampling plans without a compiled-in plan)
+  bool jit = false;
+  JitSpec jit_spec;
+  JitKernel* jit_kernel[4] = {nullptr, nullptr, nullptr, nullptr};  // by JitRole
+  int jit_compiles = 0;
 };
+
+// Jobs below this many samples keep the runtime-dispatched plan: compiling (~1 s the first time a
+// plan is seen; kept in memory, and on disk when EBN_JIT_CACHE names a directory) would cost more than
+// it saves.
+constexpr double kJitPlanMinSamples = 2e10;
+
+int jit_kernel_of(Prepared& P, JitRole role, JitKernel** out) {
+  if (!P.jit_kernel[role]) {
+    bool compiled = false;
+    std::string err;
+    if (!jit_get(P.jit_spec, role, &P.jit_kernel[role], &compiled, &err))
+      return fail(EBN_EJIT, "%s", err.c_str());
+    if (compiled) ++P.jit_compiles;
+  }
+  *out = P.jit_kernel[role];
+  return EBN_OK;
+}
+
+// The four kernel entry points of a job, compiled-in or run-time compiled.
+int k_occupancy(Dev& dv, const ebn_job_t* job, Prepared& P, int mode, size_t dyn, int* per_sm) {
+  if (!P.jit) {
+    CU(ls_vtable(job->limit_state)->occupancy(job->strict ? 1 : 0, P.plan_class, mode, dyn, per_sm));
+    return EBN_OK;
+  }
+  JitKernel* k;
+  int rc = jit_kernel_of(P, mode == 0 ? JIT_COUNT : JIT_HIST, &k);
+  if (rc) return rc;
+  std::string err;
+  if (!jit_occupancy(k, dv.id, threads_per_block(), dyn, per_sm, &err)) return fail(EBN_ECUDA, "%s", err.c_str());
+  return EBN_OK;
+}
+
+int k_launch(Dev& dv, const ebn_job_t* job, Prepared& P, int mode, const McParams& mp, int blocks, size_t dyn) {
+  if (!P.jit) {
+    CU(ls_vtable(job->limit_state)->launch(job->strict ? 1 : 0, P.plan_class, mode, mp, blocks, dyn, dv.st));
+    return EBN_OK;
+  }
+  JitKernel* k;
+  int rc = jit_kernel_of(P, mode == 0 ? JIT_COUNT : JIT_HIST, &k);
+  if (rc) return rc;
+  McParams arg = mp;
+  void* args[] = {&arg};
+  std::string err;
+  if (!jit_launch(k, dv.id, blocks, threads_per_block(), dyn, dv.st, args, &err)) return fail(EBN_ECUDA, "%s", err.c_str());
+  return EBN_OK;
+}
+
+int k_replay(Dev& dv, const ebn_job_t* job, Prepared& P, const McParams& mp, int scenario, int64_t n, double* X,
+             double* g_out, int blocks) {
+  if (!P.jit) {
+    CU(ls_vtable(job->limit_state)->replay(job->strict ? 1 : 0, P.plan_class, mp, scenario, n, X, g_out, blocks, dv.st));
+    return EBN_OK;
+  }
+  JitKernel* k;
+  int rc = jit_kernel_of(P, JIT_REPLAY, &k);
+  if (rc) return rc;
+  McParams arg = mp;
+  void* args[] = {&arg, &scenario, &n, &X, &g_out};
+  std::string err;
+  if (!jit_launch(k, dv.id, blocks, threads_per_block(), 0, dv.st, args, &err)) return fail(EBN_ECUDA, "%s", err.c_str());
+  return EBN_OK;
+}
 
 int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) {
   if (!job) return fail(EBN_EINVAL, "job is NULL");
@@ -354,7 +427,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
   if (!job->inputs) return fail(EBN_EINVAL, "inputs is NULL");
   if (job->n_per_scenario < 1) return fail(EBN_EINVAL, "n_per_scenario must be >= 1");
   if (job->sample_offset < 0) return fail(EBN_EINVAL, "sample_offset must be >= 0");
-  if (job->flags & ~(EBN_JOB_COPULA_SHARED | EBN_JOB_PARTIAL)) return fail(EBN_EINVAL, "unknown job flags 0x%x", job->flags);
+  if (job->flags & ~(EBN_JOB_COPULA_SHARED | EBN_JOB_PARTIAL | EBN_JOB_JIT_PLAN | EBN_JOB_NO_JIT_PLAN)) return fail(EBN_EINVAL, "unknown job flags 0x%x", job->flags);
   int rc = check_limit_state(job->limit_state, job->consts, job->n_consts, job->n_inputs);
   if (rc) return rc;
   const int jw = job->shard_world <= 1 ? 1 : job->shard_world;
@@ -398,6 +471,42 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
     P.plan_class = PLAN_COPULA;
   } else if (const int which = static_plan_matches(job->limit_state, P.plan.data(), S, d)) {
     P.plan_class = which == 1 ? PLAN_STATIC : PLAN_STATIC2;
+  }
+  // Run-time compilation: always for an expression limit state; for the others when no compiled-in
+  // plan fits, every scenario has the same marginal kinds, and the job is large (or asks for it).
+  {
+    const bool expr = job->limit_state == EBN_LS_EXPRESSION;
+    bool uniform = !copula;
+    for (int s = 1; s < S && uniform; ++s)
+      for (int j = 0; j < d; ++j)
+        if (P.plan[(size_t)s * d + j].kind != P.plan[j].kind) { uniform = false; break; }
+    const bool never = (job->flags & EBN_JOB_NO_JIT_PLAN) != 0;
+    const bool forced = (job->flags & EBN_JOB_JIT_PLAN) != 0;
+    if (never && forced) return fail(EBN_EINVAL, "EBN_JOB_JIT_PLAN and EBN_JOB_NO_JIT_PLAN are exclusive");
+    bool plan_jit = false;
+    if (!expr && P.plan_class == PLAN_DYNAMIC && uniform && !never) {
+      const char* env = getenv("EBN_JIT_PLAN");  // "0": never, "1": always (experiments)
+      const bool big = (double)job->n_per_scenario * S >= kJitPlanMinSamples;
+      if (forced || (env && env[0] == '1')) {
+        std::string why;
+        if (!jit_available(&why)) return fail(EBN_EJIT, "EBN_JOB_JIT_PLAN: %s", why.c_str());
+        plan_jit = true;
+      } else if (big && !(env && env[0] == '0')) {
+        plan_jit = jit_available(nullptr);  // optional speed-up: without NVRTC the dynamic plan runs
+      }
+    }
+    if (expr || plan_jit) {
+      P.jit = true;
+      P.jit_spec.limit_state = job->limit_state;
+      P.jit_spec.d = d;
+      P.jit_spec.strict = job->strict != 0;
+      P.jit_spec.copula = copula;
+      P.jit_spec.consts = job->consts;
+      P.jit_spec.n_consts = job->n_consts;
+      if (uniform && !(expr && never))
+        for (int j = 0; j < d; ++j) P.jit_spec.kinds.push_back(P.plan[j].kind);
+      if (!P.jit_spec.kinds.empty()) P.plan_class = PLAN_STATIC;
+    }
   }
   P.world = jw * (ndev_override > 0 ? ndev_override : (int)g.devs.size());
   P.first = job->sample_offset;
@@ -479,10 +588,11 @@ int stage(Dev& dv, const ebn_job_t* job, const Prepared& P, int rank, McParams& 
   return EBN_OK;
 }
 
-int grid_for(Dev& dv, const ebn_job_t* job, const Prepared& P, int mode, size_t dyn,
+int grid_for(Dev& dv, const ebn_job_t* job, Prepared& P, int mode, size_t dyn,
              int64_t local_items, int* blocks) {
   int per_sm = 0;
-  CU(ls_vtable(job->limit_state)->occupancy(job->strict ? 1 : 0, P.plan_class, mode, dyn, &per_sm));
+  int rc = k_occupancy(dv, job, P, mode, dyn, &per_sm);
+  if (rc) return rc;
   if (per_sm < 1) return fail(EBN_ECUDA, "kernel does not fit on an SM (dyn smem %zu)", dyn);
   if (const char* cap = getenv("EBN_BLOCKS_PER_SM")) {  // tuning experiments only
     const int c = atoi(cap);
@@ -578,8 +688,7 @@ int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, i
     }
     if ((rc = grid_for(dv, job, P, mode, dyn, mp.local_items, &blocks[k]))) return rc;
     CU(cudaEventRecord(dv.ev0, dv.st));
-    if (mp.local_items > 0)
-      CU(ls_vtable(job->limit_state)->launch(job->strict ? 1 : 0, P.plan_class, mode, mp, blocks[k], dyn, dv.st));
+    if (mp.local_items > 0 && (rc = k_launch(dv, job, P, mode, mp, blocks[k], dyn))) return rc;
     if (mode == 1)
       CU(moments_launch(mp.partial, mp.local_items, mp.items_per_scenario, mp.shard_rank,
                         mp.shard_world, S, (double*)dv.sums.p, (double*)dv.sums.p + S, dv.st));
@@ -631,6 +740,7 @@ int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, i
   g.stats.launches = (int)nd * (mode == 1 ? 2 : 1);
   g.stats.devices = (int)nd;
   g.stats.specialised = P.plan_class == PLAN_STATIC || P.plan_class == PLAN_STATIC2;
+  g.stats.jit_compiles = P.jit_compiles;
   return EBN_OK;
 }
 
@@ -669,6 +779,7 @@ int ebn_shutdown(void) {
     if (dv.ev1) cudaEventDestroy(dv.ev1);
     if (dv.own) cudaStreamDestroy(dv.own);
   }
+  jit_unload_all();
   g.devs.clear();
   g.ready = false;
   return EBN_OK;
@@ -804,9 +915,29 @@ int ebn_eval_matrix(int limit_state, const double* consts, int n_consts, const d
   const int64_t cap = (int64_t)dv.sms * 8;
   if (blocks > cap) blocks = cap;
   CU(cudaEventRecord(dv.ev0, dv.st));
-  CU(ls_vtable(limit_state)->matrix(strict ? 1 : 0, (const double*)dv.consts.p, n_consts,
-                   (const double*)dv.mat.p, n, d, ld, (unsigned long long*)dv.counts.p,
-                   g_out ? (double*)dv.gout.p : nullptr, (int)blocks, dv.st));
+  if (limit_state == EBN_LS_EXPRESSION) {
+    JitSpec spec;
+    spec.limit_state = limit_state;
+    spec.d = d;
+    spec.strict = strict != 0;
+    spec.consts = consts;
+    spec.n_consts = n_consts;
+    JitKernel* k = nullptr;
+    bool compiled = false;
+    std::string err;
+    if (!jit_get(spec, JIT_MATRIX, &k, &compiled, &err)) return fail(EBN_EJIT, "%s", err.c_str());
+    const double* a_consts = (const double*)dv.consts.p;
+    const double* a_X = (const double*)dv.mat.p;
+    unsigned long long* a_count = (unsigned long long*)dv.counts.p;
+    double* a_g = g_out ? (double*)dv.gout.p : nullptr;
+    void* args[] = {&a_consts, &n_consts, &a_X, &n, &d, &ld, &a_count, &a_g};
+    if (!jit_launch(k, dv.id, (int)blocks, threads_per_block(), 0, dv.st, args, &err))
+      return fail(EBN_ECUDA, "%s", err.c_str());
+  } else {
+    CU(ls_vtable(limit_state)->matrix(strict ? 1 : 0, (const double*)dv.consts.p, n_consts,
+                     (const double*)dv.mat.p, n, d, ld, (unsigned long long*)dv.counts.p,
+                     g_out ? (double*)dv.gout.p : nullptr, (int)blocks, dv.st));
+  }
   CU(cudaEventRecord(dv.ev1, dv.st));
   CU(cudaMemcpyAsync(fail_count, dv.counts.p, sizeof(int64_t), cudaMemcpyDeviceToHost, dv.st));
   if (g_out) CU(cudaMemcpyAsync(g_out, dv.gout.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, dv.st));
@@ -842,7 +973,12 @@ int ebn_sample_matrix_ex(const ebn_job_t* job, int scenario, int64_t first, int6
   const int d = job->n_inputs;
   if (ncols < d || ncols > EBN_MAX_INPUTS) return fail(EBN_EINVAL, "ncols %d outside [%d,%d]", ncols, d, EBN_MAX_INPUTS);
   if (ncols > d) {
-    const int stages = job->limit_state == EBN_LS_POLYNOMIAL ? (int)job->consts[0] : 0;
+    int stages = job->limit_state == EBN_LS_POLYNOMIAL ? (int)job->consts[0] : 0;
+    if (job->limit_state == EBN_LS_EXPRESSION) {
+      ExprInfo info;
+      expr_check(job->consts, job->n_consts, d, &info);
+      stages = info.n_store;
+    }
     if (ncols > d + stages)
       return fail(EBN_EINVAL, "ncols %d: the limit state defines only %d model columns after the %d inputs", ncols, stages, d);
   }
@@ -851,8 +987,9 @@ int ebn_sample_matrix_ex(const ebn_job_t* job, int scenario, int64_t first, int6
   if (g_out && (rc = dv.gout.ensure((size_t)n * sizeof(double)))) return rc;
   int64_t blocks = ((n + 1) / 2 + threads_per_block()) / threads_per_block();
   if (blocks > (int64_t)dv.sms * 8) blocks = (int64_t)dv.sms * 8;
-  CU(ls_vtable(job->limit_state)->replay(job->strict ? 1 : 0, P.plan_class, mp, scenario, n,
-                   (double*)dv.mat.p, g_out ? (double*)dv.gout.p : nullptr, (int)blocks, dv.st));
+  if ((rc = k_replay(dv, job, P, mp, scenario, n, (double*)dv.mat.p, g_out ? (double*)dv.gout.p : nullptr,
+                     (int)blocks)))
+    return rc;
   CU(cudaMemcpyAsync(X, dv.mat.p, (size_t)n * ncols * sizeof(double), cudaMemcpyDeviceToHost, dv.st));
   if (g_out) CU(cudaMemcpyAsync(g_out, dv.gout.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, dv.st));
   CU(cudaStreamSynchronize(dv.st));
@@ -907,6 +1044,49 @@ int ebn_partition(const ebn_job_t* job, int histogram, int64_t out[4]) {
   out[1] = P.items_per_scenario;
   out[2] = local_items_of(P, job->n_scenarios, jr);
   out[3] = P.pair_base;
+  return EBN_OK;
+}
+
+int ebn_jit_available(void) {
+  std::string why;
+  if (jit_available(&why)) return 1;
+  fail(EBN_EJIT, "%s", why.c_str());
+  return 0;
+}
+
+int ebn_expression_check(const double* consts, int n_consts, int d, int* n_columns) {
+  if (d < 1 || d > EBN_MAX_INPUTS) return fail(EBN_EINVAL, "n_inputs %d outside [1,%d]", d, EBN_MAX_INPUTS);
+  ExprInfo info;
+  const std::string bad = expr_check(consts, n_consts, d, &info);
+  if (!bad.empty()) return fail(EBN_ELIMITSTATE, "%s", bad.c_str());
+  if (n_columns) *n_columns = d + info.n_store;
+  return EBN_OK;
+}
+
+int64_t ebn_expression_source(const double* consts, int n_consts, int d, char* buf, int64_t cap) {
+  int rc = ebn_expression_check(consts, n_consts, d, nullptr);
+  if (rc) return rc;
+  const std::string src = expr_codegen(consts, n_consts, d);
+  if (buf && cap > 0) {
+    const size_t m = src.size() < (size_t)cap - 1 ? src.size() : (size_t)cap - 1;
+    memcpy(buf, src.data(), m);
+    buf[m] = '\0';
+  }
+  return (int64_t)src.size();
+}
+
+int ebn_jit_compile(const ebn_job_t* job, int role, int64_t* cubin_bytes) {
+  if (role < 0 || role > 2) return fail(EBN_EINVAL, "role must be 0 (count), 1 (histogram) or 2 (replay)");
+  Prepared P;
+  int rc = prepare(job, role == 1 ? 1 : 0, P, 1);  // host logic only
+  if (rc) return rc;
+  if (cubin_bytes) *cubin_bytes = 0;
+  if (!P.jit) return EBN_OK;  // this job runs a compiled-in kernel
+  JitKernel* k = nullptr;
+  if ((rc = jit_kernel_of(P, (JitRole)role, &k))) return rc;
+  if (cubin_bytes) *cubin_bytes = (int64_t)jit_cubin_bytes(k);
+  g.stats = ebn_stats_t{};
+  g.stats.jit_compiles = P.jit_compiles;
   return EBN_OK;
 }
 

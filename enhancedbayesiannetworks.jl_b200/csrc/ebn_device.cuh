@@ -1,6 +1,6 @@
 // Device-side plan structures shared by the kernels and the host API.
 #pragma once
-#include <cstdint>
+#include "ebn_rtc_compat.h"
 
 namespace ebn {
 

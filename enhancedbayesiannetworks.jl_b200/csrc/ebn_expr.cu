@@ -1,0 +1,177 @@
+// Expression limit states: program validation and CUDA code generation (host only).
+// Program format: include/ebncuda.h "expression program".
+#include "ebn_expr.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/ebncuda.h"
+
+namespace ebn {
+namespace {
+
+struct OpShape { int pops, pushes; const char* name; };
+// stack effect of each opcode
+const OpShape kShape[EBN_OP_NOPS] = {
+    {0, 1, "input"}, {0, 1, "param"}, {0, 1, "const"}, {2, 1, "add"}, {2, 1, "sub"}, {2, 1, "mul"},
+    {2, 1, "div"},   {1, 1, "neg"},   {1, 1, "abs"},   {1, 1, "sqrt"}, {1, 1, "exp"}, {1, 1, "log"},
+    {1, 1, "sin"},   {1, 1, "cos"},   {2, 1, "min"},   {2, 1, "max"}, {2, 1, "pow"}, {1, 1, "powi"},
+    {2, 1, "lt"},    {3, 1, "select"}, {1, 0, "store"}};
+
+bool is_int(double v) { return std::isfinite(v) && v == std::floor(v) && std::fabs(v) < 1e9; }
+
+std::string fmt(const char* f, ...) {
+  char buf[256];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof buf, f, ap);
+  va_end(ap);
+  return buf;
+}
+
+// exact literal: the bit pattern, so the generated code never depends on decimal printing
+std::string lit(double v) {
+  uint64_t b;
+  memcpy(&b, &v, 8);
+  return fmt("__longlong_as_double(0x%016llxLL)", (unsigned long long)b);
+}
+
+}  // namespace
+
+std::string expr_check(const double* consts, int n_consts, int d, ExprInfo* info) {
+  ExprInfo I;
+  if (!consts || n_consts < 2) return "expression program is empty";
+  if (!is_int(consts[0]) || !is_int(consts[1])) return "expression header (P, L) must be integers";
+  I.n_params = (int)consts[0];
+  I.n_ops = (int)consts[1];
+  if (I.n_params < 0 || I.n_params > EBN_EXPR_MAX_PARAMS)
+    return fmt("expression has %d runtime constants (at most %d)", I.n_params, EBN_EXPR_MAX_PARAMS);
+  if (I.n_ops < 1 || I.n_ops > EBN_EXPR_MAX_OPS)
+    return fmt("expression has %d instructions (1..%d)", I.n_ops, EBN_EXPR_MAX_OPS);
+  if ((int64_t)n_consts != 2 + (int64_t)I.n_params + 2 * (int64_t)I.n_ops)
+    return fmt("expression program: expected %lld consts for P=%d, L=%d, got %d",
+               2 + (long long)I.n_params + 2 * (long long)I.n_ops, I.n_params, I.n_ops, n_consts);
+  const double* code = consts + 2 + I.n_params;
+  int depth = 0;
+  for (int i = 0; i < I.n_ops; ++i) {
+    const double opd = code[2 * i], arg = code[2 * i + 1];
+    if (!is_int(opd) || opd < 0 || opd >= EBN_OP_NOPS) return fmt("instruction %d: unknown opcode %g", i, opd);
+    const int op = (int)opd;
+    if (depth < kShape[op].pops)
+      return fmt("instruction %d (%s): needs %d operands, the stack holds %d", i, kShape[op].name,
+                 kShape[op].pops, depth);
+    depth += kShape[op].pushes - kShape[op].pops;
+    if (depth > I.max_depth) I.max_depth = depth;
+    if (depth > EBN_EXPR_MAX_DEPTH) return fmt("instruction %d: stack deeper than %d", i, EBN_EXPR_MAX_DEPTH);
+    switch (op) {
+      case EBN_OP_INPUT:
+        if (!is_int(arg) || arg < 0 || arg >= d + I.n_store)
+          return fmt("instruction %d reads column %g (only %d exist)", i, arg, d + I.n_store);
+        break;
+      case EBN_OP_PARAM:
+        if (!is_int(arg) || arg < 0 || arg >= I.n_params)
+          return fmt("instruction %d reads runtime constant %g (only %d exist)", i, arg, I.n_params);
+        break;
+      case EBN_OP_POWI:
+        if (!is_int(arg)) return fmt("instruction %d: powi exponent %g is not an integer", i, arg);
+        break;
+      case EBN_OP_STORE:
+        ++I.n_store;
+        if (d + I.n_store > EBN_MAX_INPUTS)
+          return fmt("instruction %d: %d inputs + %d stored columns exceed %d columns", i, d, I.n_store,
+                     EBN_MAX_INPUTS);
+        break;
+      default:
+        break;
+    }
+  }
+  if (depth != 1) return fmt("expression leaves %d values on the stack (expected exactly 1: g)", depth);
+  if (info) *info = I;
+  return "";
+}
+
+std::string expr_code_key(const double* consts, int n_consts, int d) {
+  const int P = (int)consts[0];
+  std::string key = fmt("expr:d=%d:P=%d:", d, P);
+  key.append((const char*)(consts + 2 + P), (size_t)(n_consts - 2 - P) * sizeof(double));
+  return key;
+}
+
+std::string expr_codegen(const double* consts, int n_consts, int d) {
+  ExprInfo I;
+  if (!expr_check(consts, n_consts, d, &I).empty()) return "";
+  const double* code = consts + 2 + I.n_params;
+  std::string s;
+  s += "namespace ebn {\ntemplate <class Ops>\nstruct JitExpr {\n";
+  s += "  static constexpr int ID = EBN_LS_EXPRESSION;\n";
+  s += "  static constexpr bool HAS_FAILS = false;\n";
+  s += "  static constexpr int MIN_BLOCKS = 2;\n";
+  s += fmt("  static constexpr int D = %d;\n", d);
+  s += fmt("  static constexpr int XCAP = %d;\n", d + I.n_store);
+  s += "  static constexpr int NC = -1;\n";
+  s += fmt("  struct Ctx { double k[%d]; };\n", I.n_params > 0 ? I.n_params : 1);
+  s += "  __device__ static void setup(Ctx& c, const double* k, int, int, const FastMathSmem*) {\n";
+  s += fmt("#pragma unroll\n    for (int i = 0; i < %d; ++i) c.k[i] = k[2 + i];\n  }\n", I.n_params);
+  s += "  __device__ __forceinline__ static double eval(const Ctx& c, double* x) {\n";
+  std::vector<std::string> st;
+  int nv = 0, col = d;
+  auto def = [&](const std::string& rhs) {
+    const std::string v = fmt("v%d", nv++);
+    s += "    const double " + v + " = " + rhs + ";\n";
+    st.push_back(v);
+  };
+  auto pop = [&]() {
+    std::string v = st.back();
+    st.pop_back();
+    return v;
+  };
+  for (int i = 0; i < I.n_ops; ++i) {
+    const int op = (int)code[2 * i];
+    const double arg = code[2 * i + 1];
+    std::string a, b, c3;
+    if (kShape[op].pops == 3) { b = pop(); a = pop(); c3 = pop(); }
+    else if (kShape[op].pops == 2) { b = pop(); a = pop(); }
+    else if (kShape[op].pops == 1) { a = pop(); }
+    switch (op) {
+      case EBN_OP_INPUT: st.push_back(fmt("x[%d]", (int)arg)); break;
+      case EBN_OP_PARAM: st.push_back(fmt("c.k[%d]", (int)arg)); break;
+      case EBN_OP_CONST: st.push_back(lit(arg)); break;
+      case EBN_OP_ADD: def("Ops::add(" + a + ", " + b + ")"); break;
+      case EBN_OP_SUB: def("Ops::sub(" + a + ", " + b + ")"); break;
+      case EBN_OP_MUL: def("Ops::mul(" + a + ", " + b + ")"); break;
+      case EBN_OP_DIV: def("Ops::div(" + a + ", " + b + ")"); break;
+      case EBN_OP_NEG: def("-(" + a + ")"); break;
+      case EBN_OP_ABS: def("fabs(" + a + ")"); break;
+      case EBN_OP_SQRT: def("Ops::sqrt(" + a + ")"); break;
+      case EBN_OP_EXP: def("exp(" + a + ")"); break;
+      case EBN_OP_LOG: def("log(" + a + ")"); break;
+      case EBN_OP_SIN: def("sin(" + a + ")"); break;
+      case EBN_OP_COS: def("cos(" + a + ")"); break;
+      case EBN_OP_MIN: def("Ops::min(" + a + ", " + b + ")"); break;
+      case EBN_OP_MAX: def("Ops::max(" + a + ", " + b + ")"); break;
+      case EBN_OP_POW: def("pow(" + a + ", " + b + ")"); break;
+      case EBN_OP_POWI: {
+        const int n = (int)arg;
+        if (n == 0) def("1.0");
+        else if (n == 1) def(a);
+        else if (n == 2) def("Ops::mul(" + a + ", " + a + ")");
+        else if (n == 3) def("Ops::mul(Ops::mul(" + a + ", " + a + "), " + a + ")");
+        else def("pow(" + a + ", " + fmt("%d.0", n) + ")");
+        break;
+      }
+      case EBN_OP_LT: def("((" + a + ") < (" + b + ") ? 1.0 : 0.0)"); break;
+      case EBN_OP_SELECT: def("((" + c3 + ") != 0.0 ? (" + a + ") : (" + b + "))"); break;
+      case EBN_OP_STORE:
+        // a value that is still an `x[..]` / constant reference is copied like any other
+        s += fmt("    x[%d] = ", col++) + a + ";\n";
+        break;
+    }
+  }
+  s += "    return " + st.back() + ";\n  }\n};\n}  // namespace ebn\n";
+  return s;
+}
+
+}  // namespace ebn

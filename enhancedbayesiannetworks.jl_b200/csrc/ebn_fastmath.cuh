@@ -12,8 +12,7 @@
 // coefficients in __constant__ memory (consumed as c[bank][off] operands).
 // Accuracy: a few ulp (measured against NumPy/mpmath in tests/test_gpu_parity.py).
 #pragma once
-#include <cstdint>
-#include <cuda_runtime.h>
+#include "ebn_rtc_compat.h"
 
 namespace ebn {
 

@@ -1,9 +1,6 @@
 // Host-callable launchers of ebn_kernels.cu.
 #pragma once
-#include <cstddef>
-#include <cstdint>
-#include <type_traits>
-#include <cuda_runtime.h>
+#include "ebn_rtc_compat.h"
 #include "../../include/ebncuda.h"
 #include "ebn_device.cuh"
 
@@ -11,6 +8,7 @@ namespace ebn {
 
 enum PlanClass { PLAN_DYNAMIC = 0, PLAN_STATIC = 1, PLAN_COPULA = 2, PLAN_STATIC2 = 3 };
 
+#ifndef __CUDACC_RTC__
 int threads_per_block();
 // 0: no compile-time plan matches every scenario; 1 / 2: the limit state's first / second plan does.
 int static_plan_matches(int limit_state, const DevInput* plan, int S, int d);
@@ -36,5 +34,6 @@ cudaError_t moments_launch(const double* partial, int64_t local_items, int64_t i
                            int shard_rank, int shard_world, int S, double* sum, double* sumsq,
                            cudaStream_t st);
 cudaError_t dfma_launch(double* out, int iters, int blocks, cudaStream_t st);
+#endif  // !__CUDACC_RTC__
 
 }  // namespace ebn

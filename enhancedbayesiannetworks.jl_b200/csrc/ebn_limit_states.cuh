@@ -10,7 +10,7 @@
 //               from strict by a few ulp; count differences can only come from
 //               samples with |g| ~ 1e-13 (reported as ties by the tests).
 #pragma once
-#include <cuda_runtime.h>
+#include "ebn_rtc_compat.h"
 #include "../../include/ebncuda.h"
 #include "ebn_fastmath.cuh"
 
@@ -27,6 +27,9 @@ struct StrictOps {
   __device__ __forceinline__ static double min(double a, double b) {
     return (b < a || b != b) ? b : a;
   }
+  __device__ __forceinline__ static double max(double a, double b) {
+    return (b > a || b != b) ? b : a;
+  }
 };
 
 struct FastOps {
@@ -38,6 +41,9 @@ struct FastOps {
   __device__ __forceinline__ static double sqrt(double a) { return ::sqrt(a); }
   __device__ __forceinline__ static double min(double a, double b) {
     return (b < a || b != b) ? b : a;
+  }
+  __device__ __forceinline__ static double max(double a, double b) {
+    return (b > a || b != b) ? b : a;
   }
 };
 

@@ -10,7 +10,9 @@
 // item. No global memory is touched per sample: the only traffic is the plan
 // (48 B per input per item, L2 resident) in and one 64-bit atomic per item out.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdio>
+#endif
 #include "ebn_kernels.h"
 #include "ebn_limit_states.cuh"
 #include "ebn_sampling.cuh"
@@ -434,6 +436,7 @@ __global__ void __launch_bounds__(kThreads) matrix_kernel(const double* consts, 
   }
 }
 
+#ifndef __CUDACC_RTC__
 // ---------------------------------------------------------------------------
 // per-limit-state table of launchers (one translation unit per limit state so
 // the build parallelises)
@@ -541,5 +544,7 @@ struct LsLaunch {
     return v;
   }
 };
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace ebn

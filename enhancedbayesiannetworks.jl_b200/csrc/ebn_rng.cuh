@@ -6,8 +6,7 @@
 // The replacement for `rand(dist, n)` inside UQ.jl's `sample(inputs, n)`
 // (called from reference src/networks/ebn/evaluation/evaluate_node.jl:24,83).
 #pragma once
-#include <cstdint>
-#include <cuda_runtime.h>
+#include "ebn_rtc_compat.h"
 
 namespace ebn {
 

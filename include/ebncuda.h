@@ -22,14 +22,16 @@
 #ifndef EBNCUDA_H
 #define EBNCUDA_H
 
+#ifndef __CUDACC_RTC__ /* the device code is also compiled at run time, without host headers */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define EBN_ABI_VERSION 1
+#define EBN_ABI_VERSION 2
 #define EBN_MAX_INPUTS 16 /* columns a limit state can read (random + Parameter) */
 #define EBN_MAX_EDGES 1025 /* histogram edges per ebn_hist_batch call */
 
@@ -43,7 +45,9 @@ enum {
   EBN_ENCCL = -5,        /* NCCL missing or NCCL error                         */
   EBN_ENODEV = -6,       /* no CUDA device / library not initialised           */
   EBN_ENOMEM = -7,       /* host or device allocation failed                   */
-  EBN_ESTATE = -8        /* call not valid in the current state                */
+  EBN_ESTATE = -8,       /* call not valid in the current state                */
+  EBN_EJIT = -9          /* run-time compilation unavailable (no libnvrtc) or failed;
+                            the compiler log is in ebn_last_error                */
 };
 
 /* ---- limit states compiled into the kernels as device functors ---------- */
@@ -75,7 +79,12 @@ enum {
    * (demo/straub_example.jl:16-26) — the model of a ContinuousFunctionalNode R_i that is
    * evaluated on its own (histogram path). inputs (Ur, e); consts (lambda, zeta, rho).
    * As a limit state its value is r itself.                                              */
-  EBN_LS_STRAUB_CAPACITY = 7
+  EBN_LS_STRAUB_CAPACITY = 7,
+  /* Any chain of algebraic models and a performance function, given as a stack program in
+   * consts (see "expression program" below) and compiled for the GPU at run time (NVRTC).
+   * This is the route for user-written `Model(df -> ..., :name)` closures
+   * (src/nodes/functionalnodes.jl:27-52). d = n_inputs of the job.                          */
+  EBN_LS_EXPRESSION = 8
 };
 
 /*
@@ -88,6 +97,50 @@ enum {
  * The last stage is the performance function; its value is g. A term with
  * zero factors is the constant `coef`. At most EBN_MAX_INPUTS columns total.
  */
+
+/*
+ * Expression program (EBN_LS_EXPRESSION), all numbers stored as doubles:
+ *   consts[0] = P, the number of runtime constants; consts[1] = L, the number of instructions;
+ *   consts[2 .. 2+P) = the runtime constants k[0..P);
+ *   then L instructions of two doubles each: (opcode, operand).
+ * The program runs on an evaluation stack, once per sample. Columns 0..d-1 are the job's inputs;
+ * every EBN_OP_STORE appends the next column (a model output, readable by later instructions and
+ * returned by ebn_sample_matrix_ex). After the last instruction the stack holds exactly one value,
+ * g; the sample fails iff g < 0. Kernels are cached by (instructions, literals, d, sampling plan,
+ * strict): changing only the runtime constants reuses the compiled kernel.
+ * Strict mode executes one IEEE operation per instruction in program order, which is Julia's
+ * evaluation order when the wrapper emits the expression tree in post-order; sqrt/log of a
+ * negative number gives NaN (a safe sample) where Julia would throw a DomainError.
+ * exp, log, sin, cos and pow are within 1-2 ulp of Julia's, not bit-identical.
+ */
+enum {
+  EBN_OP_INPUT = 0,   /* push column `operand` (an input or an already stored column)        */
+  EBN_OP_PARAM = 1,   /* push runtime constant k[operand]                                    */
+  EBN_OP_CONST = 2,   /* push the literal `operand`                                          */
+  EBN_OP_ADD = 3,     /* a b -> a + b                                                        */
+  EBN_OP_SUB = 4,     /* a b -> a - b                                                        */
+  EBN_OP_MUL = 5,     /* a b -> a * b                                                        */
+  EBN_OP_DIV = 6,     /* a b -> a / b                                                        */
+  EBN_OP_NEG = 7,     /* a -> -a                                                             */
+  EBN_OP_ABS = 8,     /* a -> |a|                                                            */
+  EBN_OP_SQRT = 9,    /* a -> sqrt(a)                                                        */
+  EBN_OP_EXP = 10,    /* a -> exp(a)                                                         */
+  EBN_OP_LOG = 11,    /* a -> log(a)                                                         */
+  EBN_OP_SIN = 12,    /* a -> sin(a)                                                         */
+  EBN_OP_COS = 13,    /* a -> cos(a)                                                         */
+  EBN_OP_MIN = 14,    /* a b -> min(a, b), NaN-propagating like Julia's min                  */
+  EBN_OP_MAX = 15,    /* a b -> max(a, b), NaN-propagating                                   */
+  EBN_OP_POW = 16,    /* a b -> a ^ b                                                        */
+  EBN_OP_POWI = 17,   /* a -> a ^ operand for a literal integer: 2 -> a*a, 3 -> (a*a)*a as
+                         Julia's literal_pow does; other exponents go through pow()          */
+  EBN_OP_LT = 18,     /* a b -> 1.0 if a < b else 0.0                                        */
+  EBN_OP_SELECT = 19, /* c a b -> a if c != 0 else b                                         */
+  EBN_OP_STORE = 20,  /* a -> (nothing); appends `a` as the next column                      */
+  EBN_OP_NOPS = 21
+};
+#define EBN_EXPR_MAX_OPS 4096
+#define EBN_EXPR_MAX_PARAMS 64
+#define EBN_EXPR_MAX_DEPTH 64
 
 /* ---- marginals ---------------------------------------------------------- */
 enum {
@@ -116,6 +169,10 @@ typedef struct ebn_input {
 
 /* job->flags */
 #define EBN_JOB_COPULA_SHARED 1u /* corr_chol is one [d*d] block for all scenarios */
+#define EBN_JOB_JIT_PLAN 4u      /* compile the job's sampling plan into the kernel at run time
+                                    even for a small job (default: only when the job is large
+                                    enough to repay ~1 s of compilation)                    */
+#define EBN_JOB_NO_JIT_PLAN 8u   /* never do that: use the runtime-dispatched sampling plan    */
 #define EBN_JOB_PARTIAL 2u       /* sharded job: return THIS shard's counts, no all-reduce
                                     (the caller combines shards; also used to emulate
                                     several ranks on one GPU in tests)                  */
@@ -159,9 +216,11 @@ typedef struct ebn_stats {
   int32_t launches;        /* kernels launched by the last call                  */
   int32_t devices;         /* devices that took part                             */
   int32_t specialised;     /* 1 if a compile-time sampling plan was used         */
-  int32_t reserved;
+  int32_t jit_compiles;    /* kernels compiled at run time by the last call (0 when
+                              they came from the cache)                          */
 } ebn_stats_t;
 
+#ifndef __CUDACC_RTC__ /* host entry points */
 /* ---- lifecycle ---------------------------------------------------------- */
 int ebn_abi_version(void);
 int ebn_device_count(void);
@@ -245,6 +304,22 @@ int ebn_limit_state_id(const char* name);       /* <0 if unknown */
 const char* ebn_limit_state_name(int id);       /* NULL if unknown */
 /* n_inputs / n_consts = -1 when the limit state is variadic. */
 int ebn_limit_state_arity(int id, int* n_inputs, int* n_consts);
+
+/* ---- run-time compilation (expression limit states, sampling plans) ------ */
+/* 1 if libnvrtc could be loaded, else 0 (reason in ebn_last_error). No GPU needed. */
+int ebn_jit_available(void);
+/* Validates an expression program for d inputs without running anything (no GPU needed).
+ * On success *n_columns (nullable) = d + the number of stored columns.                    */
+int ebn_expression_check(const double* consts, int n_consts, int d, int* n_columns);
+/* Writes the CUDA source generated for the program into buf (NUL-terminated, truncated to cap);
+ * returns the full length. For inspection and tests; no GPU needed.                        */
+int64_t ebn_expression_source(const double* consts, int n_consts, int d, char* buf, int64_t cap);
+/* Compiles (or finds in the cache) the kernel `job` would run, without running it; no GPU needed.
+ * role 0 = count (ebn_pf_batch), 1 = histogram (ebn_hist_batch), 2 = replay (ebn_sample_matrix).
+ * *cubin_bytes (nullable) = size of the machine code, 0 when the job uses a compiled-in kernel.
+ * Lets a caller pay the compilation ahead of time and check a program compiles.            */
+int ebn_jit_compile(const ebn_job_t* job, int role, int64_t* cubin_bytes);
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

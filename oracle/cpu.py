@@ -17,6 +17,7 @@ INPUT_DTYPE = np.dtype(
 assert INPUT_DTYPE.itemsize == 56
 
 LS_VEHICLE, LS_STRAUB, LS_HYDROGEN, LS_POLYNOMIAL, LS_MIN_AFFINE, LS_STRAUB_R45, LS_STRAUB_CAPACITY = 1, 2, 3, 4, 5, 6, 7
+LS_EXPRESSION = 8
 IN_PARAM, IN_NORMAL, IN_LOGNORMAL, IN_UNIFORM, IN_GUMBEL, IN_GAMMA, IN_EXP_AFFINE, IN_TABULATED = range(8)
 
 

@@ -152,8 +152,59 @@ static double g_min_affine(const double *x, int d, const double *k) {
   return g;
 }
 
+static double jl_max(double a, double b) {
+  if (isnan(a)) return a;
+  if (isnan(b)) return b;
+  return b > a ? b : a;
+}
+
+/* Expression program (include/ebncuda.h "expression program"): a stack machine, one IEEE
+ * operation per instruction in program order — the evaluation order of the Julia expression the
+ * wrapper compiled (Model closures + performance, src/nodes/functionalnodes.jl:27-52).
+ * x^2 = x*x and x^3 = (x*x)*x as Julia's literal_pow; other powers through pow(). */
+static double g_expression(double *cols, int d, const double *p) {
+  const int P = (int)p[0], L = (int)p[1];
+  const double *k = p + 2, *code = p + 2 + P;
+  double st[EBN_EXPR_MAX_DEPTH];
+  int sp = 0, col = d;
+  for (int i = 0; i < L; ++i) {
+    const int op = (int)code[2 * i];
+    const double arg = code[2 * i + 1];
+    switch (op) {
+      case EBN_OP_INPUT: st[sp++] = cols[(int)arg]; break;
+      case EBN_OP_PARAM: st[sp++] = k[(int)arg]; break;
+      case EBN_OP_CONST: st[sp++] = arg; break;
+      case EBN_OP_ADD: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
+      case EBN_OP_SUB: sp--; st[sp - 1] = st[sp - 1] - st[sp]; break;
+      case EBN_OP_MUL: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
+      case EBN_OP_DIV: sp--; st[sp - 1] = st[sp - 1] / st[sp]; break;
+      case EBN_OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+      case EBN_OP_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+      case EBN_OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
+      case EBN_OP_EXP: st[sp - 1] = exp(st[sp - 1]); break;
+      case EBN_OP_LOG: st[sp - 1] = log(st[sp - 1]); break;
+      case EBN_OP_SIN: st[sp - 1] = sin(st[sp - 1]); break;
+      case EBN_OP_COS: st[sp - 1] = cos(st[sp - 1]); break;
+      case EBN_OP_MIN: sp--; st[sp - 1] = jl_min(st[sp - 1], st[sp]); break;
+      case EBN_OP_MAX: sp--; st[sp - 1] = jl_max(st[sp - 1], st[sp]); break;
+      case EBN_OP_POW: sp--; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+      case EBN_OP_POWI: {
+        const int n = (int)arg;
+        const double a = st[sp - 1];
+        st[sp - 1] = n == 0 ? 1.0 : n == 1 ? a : n == 2 ? a * a : n == 3 ? (a * a) * a : pow(a, (double)n);
+        break;
+      }
+      case EBN_OP_LT: sp--; st[sp - 1] = st[sp - 1] < st[sp] ? 1.0 : 0.0; break;
+      case EBN_OP_SELECT: sp -= 2; st[sp - 1] = st[sp - 1] != 0.0 ? st[sp] : st[sp + 1]; break;
+      case EBN_OP_STORE: cols[col++] = st[--sp]; break;
+    }
+  }
+  return st[0];
+}
+
 static double limit_state(int ls, const double *consts, double *x, int d) {
   switch (ls) {
+    case EBN_LS_EXPRESSION: return g_expression(x, d, consts);
     case EBN_LS_VEHICLE_SUSPENSION: return g_vehicle(x, consts);
     case EBN_LS_STRAUB_FRAME: return g_straub(x, consts);
     case EBN_LS_HYDROGEN_RADIUS: return g_hydrogen(x);

@@ -332,7 +332,51 @@ def g_min_affine(X, k):
     return g
 
 
-LIMIT_STATES = {LS_VEHICLE: g_vehicle, LS_STRAUB: g_straub, LS_HYDROGEN: g_hydrogen,
+def _jl_max(a, b):
+    return np.where(np.isnan(a), a, np.where(np.isnan(b), b, np.maximum(a, b)))
+
+
+def g_expression(X, prog, want_columns: bool = False):
+    """Expression program (include/ebncuda.h), vectorised over the rows of X: second restatement of
+    oracle/ebn_oracle.c g_expression. Opcode numbers are the EBN_OP_* values."""
+    prog = np.asarray(prog, dtype=np.float64)
+    n = X.shape[0]
+    P, L = int(prog[0]), int(prog[1])
+    k, code = prog[2:2 + P], prog[2 + P:]
+    cols = [X[:, j] for j in range(X.shape[1])]
+    st = []
+    full = lambda v: np.full(n, v)  # noqa: E731
+    with np.errstate(all="ignore"):
+        for i in range(L):
+            op, arg = int(code[2 * i]), code[2 * i + 1]
+            if op == 0: st.append(cols[int(arg)])
+            elif op == 1: st.append(full(k[int(arg)]))
+            elif op == 2: st.append(full(arg))
+            elif op in (3, 4, 5, 6, 14, 15, 16, 18):
+                b = st.pop(); a = st.pop()
+                st.append({3: lambda: a + b, 4: lambda: a - b, 5: lambda: a * b, 6: lambda: a / b,
+                           14: lambda: _jl_min(a, b), 15: lambda: _jl_max(a, b), 16: lambda: np.power(a, b),
+                           18: lambda: (a < b).astype(np.float64)}[op]())
+            elif op in (7, 8, 9, 10, 11, 12, 13):
+                a = st.pop()
+                st.append({7: np.negative, 8: np.abs, 9: np.sqrt, 10: np.exp, 11: np.log, 12: np.sin, 13: np.cos}[op](a))
+            elif op == 17:
+                a = st.pop(); e = int(arg)
+                st.append(np.ones(n) if e == 0 else a if e == 1 else a * a if e == 2 else (a * a) * a if e == 3
+                          else np.power(a, float(e)))
+            elif op == 19:
+                b = st.pop(); a = st.pop(); c = st.pop()
+                st.append(np.where(c != 0.0, a, b))
+            elif op == 20:
+                cols.append(st.pop())
+            else:
+                raise ValueError(f"opcode {op}")
+    assert len(st) == 1
+    return (st[0], np.column_stack(cols)) if want_columns else st[0]
+
+
+LS_EXPRESSION = 8
+LIMIT_STATES = {LS_EXPRESSION: g_expression, LS_VEHICLE: g_vehicle, LS_STRAUB: g_straub, LS_HYDROGEN: g_hydrogen,
                 LS_POLYNOMIAL: g_polynomial, LS_MIN_AFFINE: g_min_affine}
 
 

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ebncuda.h but not exported"
     assert sorted(L.EXPORTS) == names
-    assert lib.ebn_abi_version() == 1
+    assert lib.ebn_abi_version() == 2
 
 
 def test_struct_layouts():

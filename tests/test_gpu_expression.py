@@ -1,0 +1,165 @@
+"""GPU parity of the run-time compiled kernels (NVRTC): expression limit states and sampling plans
+compiled on demand. Through the C ABI, against the C oracle's stack machine and the compiled-in kernels.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import cpu as ocpu
+from oracle import replay
+
+pytestmark = pytest.mark.gpu
+
+INF = math.inf
+
+VEHICLE_MODELS = [
+    # demo/vehicle_suspension.jl:17-23, the closures' text; the two non-integer powers are runtime constants
+    ("g1", "1 .- (pi .* m .* df.V .* df.A) ./ (df.b0 .* df.K .* g .^ 2) .* ((df.Ck ./ (m .+ M) .- (df.C ./ M)) .^ 2"
+           " .+ df.C .^ 2 ./ (m .* M) .+ df.Ck .* df.K .^ 2 ./ (m .* M .^ 2))"),
+    ("g2", "4000 .* df.C .* Mg15 .- 8.6394"),
+    ("g3", "2 .* sqrt(M .* g .* (df.K .^ 2 .* df.Ck ./ (df.C .* (m .+ M)) .+ df.C)) .- 1"),
+    ("g4", "df.Ck .- gMm"),
+    ("y", "minimum([g1[1], g2, g3, g4[1]])"),
+]
+
+
+def vehicle_program():
+    from ebn_b200 import expr, workloads as W
+    k = W.vehicle_consts()
+    return expr.compile_program(["A", "b0", "V", "C", "Ck", "K"], VEHICLE_MODELS, "y",
+                                params={"M": k[0], "m": k[1], "g": k[2], "Mg15": k[3], "gMm": k[4]})
+
+
+def test_expression_vehicle_equals_compiled_in_functor(ebn):
+    """The vehicle limit state written as text gives, in strict mode, the same g bit for bit and the
+    same fused counts as the hand-written functor; the sampler streams are identical."""
+    from ebn_b200 import workloads as W
+    prog = vehicle_program()
+    n = 200_001
+    ref = W.w1_vehicle(n=n, strict=True)
+    job = ebn.Job(ebn._lib.LS_EXPRESSION, prog.consts, ref.inputs, n=n, seed=ref.seed, strict=True)
+    cnt_ref, _, _ = ebn.pf_batch(ref)
+    cnt, pf, var = ebn.pf_batch(job)
+    st = ebn.last_stats()
+    assert st["specialised"] == 1          # the job's kinds became a StaticPlan of the generated kernel
+    assert np.array_equal(cnt, cnt_ref)
+    assert np.array_equal(pf, cnt / n)
+    # replayed matrix with the model columns g1..g4, y appended (evaluate!(models, df))
+    X, g = ebn.sample_matrix(job, 3, 0, n, want_g=True, ncols=prog.ncols)
+    Xr = ebn.sample_matrix(ref, 3, 0, n)
+    assert np.array_equal(X[:, :6], Xr)
+    want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_VEHICLE, ref.consts, Xr, want_g=True)
+    assert np.array_equal(g, want_g) and int(cnt[3]) == want_cnt
+    g_np, cols = replay.g_expression(Xr, prog.consts, want_columns=True)
+    assert np.array_equal(cols, X) and np.array_equal(g_np, g)
+    # eval_matrix on a given matrix
+    c2, g2 = ebn.eval_matrix(ebn._lib.LS_EXPRESSION, prog.consts, Xr, strict=True, want_g=True)
+    assert c2 == want_cnt and np.array_equal(g2, want_g)
+    # second call: kernels come from the cache
+    ebn.pf_batch(job)
+    assert ebn.last_stats()["jit_compiles"] == 0
+    # new runtime constants reuse the code (a heavier car: more failures in g4? just check it runs and differs)
+    job2 = ebn.Job(ebn._lib.LS_EXPRESSION, prog.with_params({"gMm": 1460.0}), ref.inputs, n=n, seed=ref.seed, strict=True)
+    cnt2, _, _ = ebn.pf_batch(job2)
+    assert ebn.last_stats()["jit_compiles"] == 0 and np.all(cnt2 >= cnt) and np.any(cnt2 > cnt)
+    # fast mode: ties only
+    jobf = ebn.Job(ebn._lib.LS_EXPRESSION, prog.consts, ref.inputs, n=n, seed=ref.seed, strict=False)
+    cntf, _, _ = ebn.pf_batch(jobf)
+    assert np.max(np.abs(cntf - cnt)) <= 1
+
+
+def test_expression_all_opcodes_against_oracle(ebn):
+    """Every opcode, on random inputs, against the C and NumPy stack machines: exact for the IEEE
+    operations, a few ulp for exp/log/sin/cos/pow."""
+    from ebn_b200 import expr
+    models = [
+        ("s", "a + b * c - a / (abs(b) + 1.5)"),
+        ("t", "sqrt(abs(s)) + min(a, b, c) - max(a, -b) + (-c)^2 + b^3"),
+        ("u", "ifelse(a < b, s, t) + (c if b > a else 2.0) + k0 * a"),
+    ]
+    exact = expr.compile_program(["a", "b", "c"], models, "u - k1", params={"k0": 0.25, "k1": 0.5})
+    rng = np.random.default_rng(7)
+    X = rng.normal(0, 2, (50_000, 3))
+    X[:5] = [[np.nan, 1, 2], [1, np.nan, 2], [0.0, -0.0, 1], [np.inf, 1, 1], [1e-310, 1e300, -1e300]]
+    want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_EXPRESSION, exact.consts, X, want_g=True)
+    got_cnt, got_g = ebn.eval_matrix(ebn._lib.LS_EXPRESSION, exact.consts, X, strict=True, want_g=True)
+    assert got_cnt == want_cnt
+    assert np.array_equal(got_g, want_g, equal_nan=True)
+    assert np.array_equal(replay.g_expression(X, exact.consts), want_g, equal_nan=True)
+
+    transc = expr.compile_program(["a", "b", "c"], [("w", "exp(a / 4) + log(abs(b) + 1) + sin(c) * cos(a)")],
+                                  "w - abs(a)^1.5 - b^5 / 100 + c^-2", params={})
+    X2 = rng.normal(0, 2, (50_000, 3))
+    _, want = ocpu.eval_matrix(ocpu.LS_EXPRESSION, transc.consts, X2, want_g=True)
+    _, got = ebn.eval_matrix(ebn._lib.LS_EXPRESSION, transc.consts, X2, strict=True, want_g=True)
+    err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
+    assert np.max(err) < 1e-12, np.max(err)
+
+
+def test_expression_reference_toy_models(ebn):
+    """The models of test/networks/ebn/evaluate/evaluate_node.jl:96-110 (C = A + B, performance 2 - C)
+    as expressions: analytic anchors Phi(-1) and 0.5, and equality with the polynomial functor."""
+    from ebn_b200 import expr
+    from test_gpu_parity import PROG_2_MINUS_A_PLUS_B
+    prog = expr.compile_program(["A", "B"], [("C", "df.A .+ df.B")], "2 .- df.C")
+    rows = [[(0, a, 0, 0, 0, -INF, INF), (1, 0.0, 1.0, 0, 0, -INF, INF)] for a in (1.0, 2.0)]
+    inputs = ebn.make_inputs(rows)
+    n = 2_000_000
+    je = ebn.Job(ebn._lib.LS_EXPRESSION, prog.consts, inputs, n=n, seed=11, strict=True)
+    jp = ebn.Job(ebn._lib.LS_POLYNOMIAL, PROG_2_MINUS_A_PLUS_B, inputs, n=n, seed=11, strict=True)
+    ce, pfe, vare = ebn.pf_batch(je)
+    cp, _, _ = ebn.pf_batch(jp)
+    assert np.array_equal(ce, cp)
+    for pf, var, want in zip(pfe, vare, (0.158655, 0.5)):
+        assert abs(pf - want) < 4 * math.sqrt(var) + 1e-9
+    # histogram path (ContinuousFunctionalNode): same counts as the polynomial functor
+    edges = np.linspace(-4, 4, 33)
+    he, se, qe = ebn.hist_batch(je, edges)
+    hp, sp, qp = ebn.hist_batch(jp, edges)
+    assert np.array_equal(he, hp) and np.allclose(se, sp, rtol=1e-12) and np.allclose(qe, qp, rtol=1e-12)
+
+
+def test_jit_sampling_plan_matches_dynamic_plan(ebn):
+    """A job no compiled-in plan covers (truncated normals): the run-time compiled StaticPlan gives
+    exactly the counts and streams of the runtime-dispatched plan."""
+    from ebn_b200 import workloads as W
+    n = 300_001
+    base = W.w1_vehicle(n=n, strict=True)
+    base.inputs[:, 3]["lo"] = 400.0       # C truncated at 400 → inverse-CDF kind
+    base.inputs[:, 5]["hi"] = 80.0
+    dyn = ebn.Job(base.limit_state, base.consts, base.inputs, n=n, seed=base.seed, strict=True, jit_plan=False)
+    jit = ebn.Job(base.limit_state, base.consts, base.inputs, n=n, seed=base.seed, strict=True, jit_plan=True)
+    c_dyn, _, _ = ebn.pf_batch(dyn)
+    assert ebn.last_stats()["specialised"] == 0
+    c_jit, _, _ = ebn.pf_batch(jit)
+    st = ebn.last_stats()
+    assert st["specialised"] == 1
+    assert np.array_equal(c_dyn, c_jit)
+    assert np.array_equal(ebn.sample_matrix(dyn, 7, 5, 4097), ebn.sample_matrix(jit, 7, 5, 4097))
+    # every marginal kind through a run-time plan
+    from test_gpu_parity import ALL_KINDS_ROW, TABLE
+    inputs = ebn.make_inputs([ALL_KINDS_ROW, ALL_KINDS_ROW])
+    d = inputs.shape[1]
+    k = np.array([1.0, -150.0] + [1.0] * d)
+    a = ebn.Job(ebn._lib.LS_MIN_AFFINE, k, inputs, n=100_000, seed=5, strict=True, tables=TABLE, jit_plan=False)
+    b = ebn.Job(ebn._lib.LS_MIN_AFFINE, k, inputs, n=100_000, seed=5, strict=True, tables=TABLE, jit_plan=True)
+    ca, _, _ = ebn.pf_batch(a)
+    cb, _, _ = ebn.pf_batch(b)
+    assert ebn.last_stats()["specialised"] == 1
+    assert np.array_equal(ca, cb)
+    assert np.array_equal(ebn.sample_matrix(a, 1, 0, 5000), ebn.sample_matrix(b, 1, 0, 5000))
+
+
+def test_expression_errors(ebn):
+    from ebn_b200 import expr
+    L = ebn._lib
+    rows = [[(1, 0.0, 1.0, 0, 0, -INF, INF)] * 2]
+    bad = np.array([0, 1, L.OP_ADD, 0], dtype=float)
+    with pytest.raises(ebn.EbnError) as e:
+        ebn.pf_batch(ebn.Job(L.LS_EXPRESSION, bad, ebn.make_inputs(rows), n=10))
+    assert e.value.code == -2 and "operands" in e.value.message
+    prog = expr.compile_program(["a", "b"], [], "a - b")
+    with pytest.raises(ebn.EbnError) as e:   # program compiled for 2 inputs, job has 1
+        ebn.pf_batch(ebn.Job(L.LS_EXPRESSION, prog.consts, ebn.make_inputs([[rows[0][0]]]), n=10))
+    assert e.value.code == -2
