@@ -6,6 +6,7 @@ at the repository root (``import ebn_b200``).
 Layout
     csrc/         hand-written sm_100a kernels + the C ABI (libebncuda.so)
     _lib.py       ctypes binding of include/ebncuda.h
+    expr.py       model formulas as text (Julia or Python syntax) -> expression program of the C ABI
     workloads.py  the BASELINE.json configurations as C-ABI jobs
     julia/        the `ccall` wrapper a maintainer drops into the reference
     distributions.py, nodes.py, network.py, uq.py, evaluation.py
@@ -21,7 +22,7 @@ from .distributions import (Normal, LogNormal, Uniform, Gumbel, Gamma, Exponenti
                             RandomVariable, Interval, ProbabilityBox, GaussianCopula, JointDistribution)
 from .nodes import (DiscreteConditionalProbabilityTable, ContinuousConditionalProbabilityTable,  # noqa: F401
                     ExactDiscretization, ApproximatedDiscretization, UnamedProbabilityBox, DiscreteNode,
-                    ContinuousNode, DiscreteFunctionalNode, ContinuousFunctionalNode, Model, Poly, Catalogue,
+                    ContinuousNode, DiscreteFunctionalNode, ContinuousFunctionalNode, Model, Poly, Catalogue, Expression,
                     CudaMonteCarlo, MonteCarlo, CudaDoubleLoop, DoubleLoop, CudaRandomSlicing, RandomSlicing)
 from .network import (EnhancedBayesianNetwork, BayesianNetwork, CredalNetwork, add_child, order, parents,  # noqa: F401
                       children, discrete_ancestors, markov_blanket, markov_envelope)

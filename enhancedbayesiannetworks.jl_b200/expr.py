@@ -13,14 +13,18 @@ GPU at run time (NVRTC); there is no interpreter and no CPU fallback.
 
 Julia semantics kept: ``a*b*c`` and ``a+b+c`` fold left to right; ``x^2`` is ``x*x`` and ``x^3`` is
 ``(x*x)*x`` (literal_pow); ``min``/``max``/``minimum([...])``/``maximum([...])`` propagate NaN;
-integer literals take part as Float64 (exact). Not supported: anything that is not a scalar formula of
-the row (loops, ``rand`` inside a model, array indexing other than ``x[1]`` on a scalar).
+integer literals take part as Float64 (exact). ``randn()`` and ``rand(Normal(mu, sigma))`` inside a
+model (demo/straub_example.jl:26) become hidden standard-normal input columns, one per textual
+occurrence, drawn by the device sampler: ``rand(Normal(mu, sigma))`` is ``mu + sigma * z`` as in
+Distributions.jl. Not supported: anything that is not a scalar formula of the row (loops, array
+indexing other than ``x[1]`` on a scalar, other in-model distributions).
 """
 from __future__ import annotations
 
 import ast
 import math
 import re
+import unicodedata
 from dataclasses import dataclass, field
 from typing import Dict, List, Sequence, Tuple
 
@@ -34,17 +38,19 @@ class ExpressionError(ValueError):
 
 
 _UNARY = {"sqrt": L.OP_SQRT, "exp": L.OP_EXP, "log": L.OP_LOG, "abs": L.OP_ABS, "sin": L.OP_SIN, "cos": L.OP_COS}
-_NAMED_CONSTS = {"pi": math.pi, "π": math.pi, "ℯ": math.e, "Inf": math.inf}
+_NAMED_CONSTS = {"pi": math.pi, "π": math.pi, "_euler": math.e, "Inf": math.inf}
 
 
 def _to_python(src: str) -> str:
     """Julia surface syntax → something Python's parser accepts (same tree shape)."""
-    s = src.strip()
+    # Julia identifiers may carry subscripts Python's parser rejects (b₀) or silently normalises
+    # (Uᵣ): NFKC the whole text (b₀ → b0, Cₖ → Ck); column and constant names get the same treatment
+    s = unicodedata.normalize("NFKC", src.strip().replace("ℯ", "_euler"))
     s = re.sub(r"\.(\^|\*|/|\+|-|<=|>=|<|>)", r"\1", s)      # broadcasting operators: .* ./ .^ .+ .-
-    s = re.sub(r"([A-Za-z_)\]])\.\(", r"\1(", s)               # broadcast calls: sqrt.(x)
+    s = re.sub(r"([^\W\d]|[)\]])\.\(", r"\1(", s)               # broadcast calls: sqrt.(x)
     s = s.replace("^", "**")
-    s = re.sub(r"\bdf\.([A-Za-z_]\w*)", r"\1", s)              # df.x → x
-    s = re.sub(r"\bdf\[\s*[:!]\s*,\s*:([A-Za-z_]\w*)\s*\]", r"\1", s)  # df[:, :x] / df[!, :x]
+    s = re.sub(r"\bdf\.([^\W\d]\w*)", r"\1", s)              # df.x → x
+    s = re.sub(r"\bdf\[\s*[:!]\s*,\s*:([^\W\d]\w*)\s*\]", r"\1", s)  # df[:, :x] / df[!, :x]
     s = s.replace("π", "pi")
     s = re.sub(r"\bifelse\(", "_ifelse(", s)
     return s
@@ -54,7 +60,13 @@ def _to_python(src: str) -> str:
 class _Emitter:
     columns: Dict[str, int]            # name → column index (inputs, then stored models)
     params: Dict[str, int]             # name → runtime-constant index
+    hidden_base: int = 0               # first hidden standard-normal column
+    n_hidden: int = 0                  # hidden columns handed out so far
     code: List[Tuple[int, float]] = field(default_factory=list)
+
+    def _hidden(self):
+        self.emit(L.OP_INPUT, self.hidden_base + self.n_hidden)
+        self.n_hidden += 1
 
     def emit(self, op: int, arg: float = 0.0):
         self.code.append((op, float(arg)))
@@ -125,6 +137,17 @@ class _Emitter:
                 self.emit(L.OP_SELECT)
             elif f == "float" and len(args) == 1:
                 self.expr(args[0])
+            elif f == "randn" and not args:
+                self._hidden()
+            elif f == "rand" and len(args) == 1 and _is_normal_call(args[0]):
+                pa = args[0].args
+                if len(pa) == 0:
+                    self._hidden()
+                elif len(pa) == 2:                                  # mu + sigma * randn()
+                    self.expr(pa[0]); self.expr(pa[1]); self._hidden()
+                    self.emit(L.OP_MUL); self.emit(L.OP_ADD)
+                else:
+                    raise ExpressionError("rand(Normal(...)) takes Normal() or Normal(mu, sigma)")
             else:
                 raise ExpressionError(f"function '{f}' with {len(args)} argument(s) is not supported")
         else:
@@ -135,6 +158,24 @@ class _Emitter:
         for it in items[1:]:
             self.expr(it)
             self.emit(op)
+
+
+def _norm(name: str) -> str:
+    return unicodedata.normalize("NFKC", name)
+
+
+def _is_normal_call(n: ast.AST) -> bool:
+    return isinstance(n, ast.Call) and isinstance(n.func, ast.Name) and n.func.id == "Normal"
+
+
+def _count_hidden(n: ast.AST) -> int:
+    c = 0
+    for sub in ast.walk(n):
+        if isinstance(sub, ast.Call) and isinstance(sub.func, ast.Name):
+            if (sub.func.id == "randn" and not sub.args) or \
+                    (sub.func.id == "rand" and len(sub.args) == 1 and _is_normal_call(sub.args[0])):
+                c += 1
+    return c
 
 
 def _literal_int(n: ast.AST):
@@ -157,17 +198,23 @@ def _parse(src: str) -> ast.AST:
 class Program:
     """A compiled chain of models + performance: what ebn_job_t.consts carries."""
     consts: np.ndarray           # the expression program
-    inputs: List[str]            # column names 0..d-1
-    stored: List[str]            # model output names, columns d..d+T-1
+    inputs: List[str]            # the caller's column names
+    stored: List[str]            # model output names, the last columns
     params: List[str]            # runtime constants, in k[] order
+    n_hidden: int = 0            # hidden N(0,1) columns between the inputs and the stored columns
 
     @property
     def d(self) -> int:
-        return len(self.inputs)
+        """n_inputs of the job: the caller's inputs plus the hidden standard normals."""
+        return len(self.inputs) + self.n_hidden
 
     @property
     def ncols(self) -> int:
-        return len(self.inputs) + len(self.stored)
+        return self.d + len(self.stored)
+
+    @property
+    def columns(self) -> List[str]:
+        return self.inputs + [f"__randn{i + 1}" for i in range(self.n_hidden)] + self.stored
 
     def with_params(self, values: Dict[str, float]) -> np.ndarray:
         """Same code, new runtime constants (no recompilation on the device)."""
@@ -187,15 +234,23 @@ def compile_program(inputs: Sequence[str], models: Sequence[Tuple[str, str]], pe
     inputs = list(inputs)
     if len(set(inputs)) != len(inputs):
         raise ExpressionError("duplicate input names")
-    em = _Emitter({n: i for i, n in enumerate(inputs)}, {n: i for i, n in enumerate(params)})
+    trees = [(name, _parse(src)) for name, src in models]
+    perf = _parse(performance)
+    n_hidden = sum(_count_hidden(t) for _, t in trees) + _count_hidden(perf)
+    # Python's parser NFKC-normalises identifiers (Uᵣ → Ur, Cₖ → Ck): look names up the same way
+    em = _Emitter({_norm(n): i for i, n in enumerate(inputs)}, {_norm(n): i for i, n in enumerate(params)},
+                  hidden_base=len(inputs))
+    if len(em.columns) != len(inputs) or len(em.params) != len(params) or set(em.columns) & set(em.params):
+        raise ExpressionError("input / constant names collide after Unicode normalisation")
     stored = []
-    for name, src in models:
-        em.expr(_parse(src))
+    for name, tree in trees:
+        em.expr(tree)
         em.emit(L.OP_STORE)
-        em.columns[name] = len(inputs) + len(stored)     # a later model may shadow an earlier name
+        em.columns[_norm(name)] = len(inputs) + n_hidden + len(stored)     # a later model may shadow an earlier name
         stored.append(name)
-    em.expr(_parse(performance))
+    em.expr(perf)
+    assert em.n_hidden == n_hidden
     flat = [float(len(params)), float(len(em.code))] + [float(v) for v in params.values()]
     for op, arg in em.code:
         flat += [float(op), arg]
-    return Program(np.asarray(flat, dtype=np.float64), inputs, stored, list(params))
+    return Program(np.asarray(flat, dtype=np.float64), inputs, stored, list(params), n_hidden)

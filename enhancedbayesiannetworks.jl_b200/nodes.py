@@ -409,9 +409,25 @@ class Catalogue:
 
 
 @dataclass(frozen=True)
+class Expression:
+    """The body of a model closure (or of `performance`) as text, Julia or Python syntax:
+    `Model(Expression("df.A .+ df.B"), "C")` stands for `Model(df -> df.A .+ df.B, :C)`.
+    Keyword arguments are named constants of the formula; they travel as run-time constants, so the
+    same formula with other values reuses the compiled kernel. Compiled for the GPU at run time
+    (expr.py → EBN_LS_EXPRESSION → NVRTC)."""
+    text: str
+    constants: Tuple[Tuple[str, float], ...]
+
+    def __init__(self, text: str, **constants):
+        object.__setattr__(self, "text", text)
+        object.__setattr__(self, "constants", tuple((k, float(v)) for k, v in constants.items()))
+
+
+@dataclass(frozen=True)
 class Model:
-    """UQ.jl `Model(func, name)`. Arbitrary closures cannot run on the GPU: `func` is a `Poly` or a
-    `Catalogue` entry, anything else raises when the node is evaluated (no CPU fallback)."""
+    """UQ.jl `Model(func, name)`. A Python closure cannot run on the GPU: `func` is an `Expression`
+    (the closure's formula as text), a `Poly`, or a `Catalogue` entry; anything else raises when the
+    node is evaluated (no CPU fallback)."""
     func: Any
     name: str
 

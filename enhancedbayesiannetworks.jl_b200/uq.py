@@ -5,7 +5,7 @@ Replaces the three UQ.jl call sites of the reference hot path:
   src/networks/ebn/evaluation/evaluate_node.jl:83      probability_of_failure(models, performance, inputs, sim)
   src/networks/ebn/evaluation/evaluate_node.jl:24-26   sample / evaluate! / EmpiricalDistribution
 and the DoubleLoop / RandomSlicing branches at :104-117.
-There is no CPU fallback: a model that is not a `Poly` or a `Catalogue` entry raises.
+There is no CPU fallback: a model that is not an `Expression`, a `Poly` or a `Catalogue` entry raises.
 """
 from __future__ import annotations
 
@@ -19,7 +19,8 @@ import numpy as np
 from . import _lib as L
 from .distributions import (INF, Gamma, Interval, JointDistribution, NeedsTable, Normal, Parameter,
                             ProbabilityBox, RandomVariable, Truncated, table_for)
-from .nodes import Catalogue, CudaDoubleLoop, CudaMonteCarlo, CudaRandomSlicing, Model, Poly
+from . import expr as _expr
+from .nodes import Catalogue, CudaDoubleLoop, CudaMonteCarlo, CudaRandomSlicing, Expression, Model, Poly
 
 VEHICLE_ARGS = ("A", "b₀", "V", "C", "Cₖ", "K")
 HIST_BINS = 2048  # fine grid a ContinuousFunctionalNode's output is histogrammed on
@@ -54,6 +55,50 @@ def _poly_program(stages: List[Poly], columns: List[str], stage_names: List[str]
     return np.array(out)
 
 
+def _poly_text(p: Poly) -> str:
+    """A Poly as expression text with the same evaluation order: ((coef*a)*b) + ((coef2*c)) + ..."""
+    terms = []
+    for coef, names in p.terms:
+        terms.append("(" + "*".join([repr(float(coef))] + [f"df.{n}" for n in names]) + ")")
+    return " + ".join(terms)
+
+
+def _lower_expression(models: List[Model], performance, input_names: List[str]) -> Lowered:
+    consts: Dict[str, float] = {}
+    chain = []
+    for m in models:
+        f = m.func
+        if isinstance(f, Expression):
+            for k, v in f.constants:
+                if consts.setdefault(k, v) != v:
+                    raise UnsupportedModel(f"constant '{k}' has two different values in one model chain")
+            chain.append((m.name, f.text))
+        elif isinstance(f, Poly):
+            chain.append((m.name, _poly_text(f)))
+        else:
+            raise UnsupportedModel(f"model '{m.name}': an Expression chain takes Expression and Poly models only")
+    if isinstance(performance, Expression):
+        for k, v in performance.constants:
+            if consts.setdefault(k, v) != v:
+                raise UnsupportedModel(f"constant '{k}' has two different values in one model chain")
+        perf = performance.text
+    elif isinstance(performance, Poly):
+        perf = _poly_text(performance)
+    elif isinstance(performance, str):
+        perf = f"df.{performance}"
+    elif performance is None and chain:
+        perf = f"df.{chain[-1][0]}"
+    else:
+        raise UnsupportedModel("performance must be an Expression, a Poly or a column name")
+    try:
+        prog = _expr.compile_program(input_names, chain, perf, consts)
+        L.expression_check(prog.consts, prog.d)
+    except (_expr.ExpressionError, L.EbnError) as e:
+        raise UnsupportedModel(str(e)) from None
+    hidden = [Normal(0.0, 1.0).abi()] * prog.n_hidden
+    return Lowered(L.LS_EXPRESSION, prog.consts, list(input_names), hidden, prog.columns)
+
+
 def lower(models: Sequence[Model], performance, input_names: Sequence[str]) -> Lowered:
     """Maps a model chain (+ performance) onto a device limit state."""
     models = list(models)
@@ -64,6 +109,8 @@ def lower(models: Sequence[Model], performance, input_names: Sequence[str]) -> L
             seen.add(m.name)
     models = uniq
     input_names = list(input_names)
+    if any(isinstance(m.func, Expression) for m in models) or isinstance(performance, Expression):
+        return _lower_expression(models, performance, input_names)
     if all(isinstance(m.func, Poly) for m in models) and (performance is None or isinstance(performance, (Poly, str))):
         stages = [m.func for m in models]
         names = [m.name for m in models]
@@ -82,8 +129,9 @@ def lower(models: Sequence[Model], performance, input_names: Sequence[str]) -> L
     cats = [m for m in models if isinstance(m.func, Catalogue)]
     if len(cats) != len(models):
         bad = [m.name for m in models if not isinstance(m.func, (Poly, Catalogue))]
-        raise UnsupportedModel(f"models {bad or [m.name for m in models]} have no device functor: use Poly or Catalogue "
-                               "(arbitrary closures cannot run on the GPU and there is no CPU fallback)")
+        raise UnsupportedModel(f"models {bad or [m.name for m in models]} have no device functor: pass the closure's "
+                               "formula as Expression(text), or use Poly / Catalogue (a Python closure cannot run "
+                               "on the GPU and there is no CPU fallback)")
     last = cats[-1]
     if isinstance(performance, str) and performance != last.name:
         raise UnsupportedModel("a Catalogue chain needs `performance = df -> df.<last model>`")
@@ -219,7 +267,8 @@ class Samples:
 
     def fetch(self, first: int = 0, n: int = 1000) -> Dict[str, np.ndarray]:
         n = min(n, self.job.n - first)
-        ncols = min(len(self.columns), L.EBN_MAX_INPUTS) if self.job.limit_state == L.LS_POLYNOMIAL else self.job.d
+        ncols = (min(len(self.columns), L.EBN_MAX_INPUTS)
+                 if self.job.limit_state in (L.LS_POLYNOMIAL, L.LS_EXPRESSION) else self.job.d)
         X, g = L.sample_matrix(self.job, self.scenario, self.job.sample_offset + first, n, want_g=True, ncols=ncols)
         out = {c: X[:, j] for j, c in enumerate(self.columns[:X.shape[1]])}
         out["g"] = g

@@ -248,17 +248,25 @@ def test_evaluate_net_chain_and_error_messages(E):
         E.evaluate(net)
 
 
-def straub_net(E, n):
-    """demo/straub_example.jl in the current API (test/inference/variableselimination.jl:133-206)."""
+def straub_net(E, n, as_text=False, strict=False):
+    """demo/straub_example.jl in the current API (test/inference/variableselimination.jl:133-206).
+    as_text: the model closures typed in as their own text (Expression) instead of catalogue entries."""
     lam, zeta = E.distribution_parameters(150, 30, "LogNormal")
     ur = _cont_root(E, "Uᵣ", E.Normal())
     v = _cont_root(E, "V", E.Gamma(*E.distribution_parameters(60, 12, "Gamma")))
     h = _cont_root(E, "H", E.Gumbel(*E.distribution_parameters(50, 20, "Gumbel")))
-    sim = E.MonteCarlo(n)
-    rs = [E.ContinuousFunctionalNode(f"R{i}", [E.Model(E.Catalogue("straub_capacity", (lam, zeta, 0.5477), ("Uᵣ",)), f"r{i}")], sim)
-          for i in range(1, 6)]
-    frame = E.DiscreteFunctionalNode(
-        "E", [E.Model(E.Catalogue("straub_frame", (), ("r1", "r2", "r3", "r4", "r5", "V", "H")), "G")], "G", sim)
+    sim = E.MonteCarlo(n, strict=strict)
+    if as_text:
+        cap = E.Expression("exp(rand(Normal(λ + ρ * ζ * df.Uᵣ, sqrt((1 - ρ^2) * ζ^2))))", λ=lam, ζ=zeta, ρ=0.5477)
+        frm = E.Expression("minimum([df.r1 + df.r2 + df.r4 + df.r5 - 5 * df.H, df.r2 + 2 * df.r3 + df.r4 - 5 * df.V, "
+                           "df.r1 + 2 * df.r3 + 2 * df.r4 + df.r5 - 5 * df.H - 5 * df.V])")
+        perf = E.Expression("df.G")
+    else:
+        cap = E.Catalogue("straub_capacity", (lam, zeta, 0.5477), ("Uᵣ",))
+        frm = E.Catalogue("straub_frame", (), ("r1", "r2", "r3", "r4", "r5", "V", "H"))
+        perf = "G"
+    rs = [E.ContinuousFunctionalNode(f"R{i}", [E.Model(cap, f"r{i}")], sim) for i in range(1, 6)]
+    frame = E.DiscreteFunctionalNode("E", [E.Model(frm, "G")], perf, sim)
     net = E.EnhancedBayesianNetwork([ur, v, h] + rs + [frame])
     for r in rs:
         E.add_child(net, ur, r)
@@ -281,7 +289,17 @@ def test_straub_end_to_end(E):
     assert isinstance(bn, E.BayesianNetwork) and [n.name for n in bn.nodes] == ["E"]
 
 
-def vehicle_net(E, n, v_dist=None, sim=None):
+VEHICLE_TEXT = [  # demo/vehicle_suspension.jl:17-23, one model per line of the closure
+    ("g1", "1 .- (pi .* m .* df.V .* df.A) ./ (df.b₀ .* df.K .* g .^ 2) .* ((df.Cₖ ./ (m .+ M) .- (df.C ./ M)) .^ 2"
+           " .+ df.C .^ 2 ./ (m .* M) .+ df.Cₖ .* df.K .^ 2 ./ (m .* M .^ 2))"),
+    ("g2", "4000 .* df.C .* Mg15 .- 8.6394"),
+    ("g3", "2 .* sqrt.(M .* g .* (df.K .^ 2 .* df.Cₖ ./ (df.C .* (m .+ M)) .+ df.C)) .- 1"),
+    ("g4", "df.Cₖ .- gMm"),
+    ("y", "minimum([df.g1[1], df.g2, df.g3, df.g4[1]])"),
+]
+
+
+def vehicle_net(E, n, v_dist=None, sim=None, as_text=False):
     """demo/vehicle_suspension.jl restated in the current API (the demo file itself is stale)."""
     M, m, g = 3.2633, 0.8158, 981.0
     consts = (M, m, g, (M * g) ** -1.5, (g * (M + m)) ** 0.877)
@@ -297,8 +315,12 @@ def vehicle_net(E, n, v_dist=None, sim=None):
     Ck = _cont_root(E, "Cₖ", E.Normal(1475.5503, 10))
     K = _cont_root(E, "K", E.Normal(55.0406, 10))
     from ebn_b200 import uq
-    model = E.Model(E.Catalogue("vehicle_suspension", consts, uq.VEHICLE_ARGS), "y")
-    node = E.DiscreteFunctionalNode("E", [model], "y", sim or E.MonteCarlo(n))
+    if as_text:
+        k = dict(M=M, m=m, g=g, Mg15=consts[3], gMm=consts[4])
+        models = [E.Model(E.Expression(text, **k), name) for name, text in VEHICLE_TEXT]
+    else:
+        models = [E.Model(E.Catalogue("vehicle_suspension", consts, uq.VEHICLE_ARGS), "y")]
+    node = E.DiscreteFunctionalNode("E", models, "y", sim or E.MonteCarlo(n))
     net = E.EnhancedBayesianNetwork([A, b0, V, C, Ck, K, node])
     for p in (A, b0, V, C, Ck, K):
         E.add_child(net, p, node)
@@ -328,6 +350,35 @@ def test_vehicle_suspension_network(E):
         warnings.simplefilter("ignore")
         bn = E.dispatch(net)
     assert isinstance(bn, E.BayesianNetwork) and sorted(n.name for n in bn.nodes) == ["A", "E", "V_d", "b₀"]
+
+
+def test_networks_with_models_given_as_text(E):
+    """The two demos with their closures typed in as text (Expression → run-time compiled functor):
+    the CPTs agree with those of the hand-written functors within Monte Carlo error (the input
+    columns follow the parents' order, so the streams differ; bit-level equality on identical streams
+    is in test_gpu_expression.py), and the reference anchors hold."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cpts = []
+        for as_text in (False, True):
+            net = vehicle_net(E, 500_000, sim=E.MonteCarlo(500_000, strict=True), as_text=as_text)
+            E.evaluate(net, True, True)
+            cpts.append(net.node("E"))
+        for r0, r1 in zip(cpts[0].cpt.data, cpts[1].cpt.data):
+            assert {k: v for k, v in r0.items() if k != "Π"} == {k: v for k, v in r1.items() if k != "Π"}
+            p = r0["Π"]
+            assert abs(p - r1["Π"]) < 5 * math.sqrt(2 * p * (1 - p) / 500_000) + 1e-12
+        # the replayed DataFrame carries the model columns of the closure chain
+        smp = next(iter(cpts[1].additional_info.values()))["samples"].fetch(0, 1000)
+        assert sorted(list(smp)[:6]) == sorted(["A", "b₀", "V", "C", "Cₖ", "K"]) and list(smp)[6:] == ["g1", "g2", "g3", "g4", "y", "g"]
+        assert np.array_equal(smp["y"], smp["g"]) and np.array_equal(smp["y"], np.minimum.reduce([smp[f"g{i}"] for i in (1, 2, 3, 4)]))
+        pfs = []
+        for as_text in (False, True):
+            net = straub_net(E, 10**6, as_text=as_text, strict=True)
+            E.evaluate(net)
+            pfs.append(net.node("E").cpt.column("Π"))
+        assert np.allclose(pfs[1], [0.026129, 0.973871], atol=0.01)     # demo/straub_example.jl:71
+        assert np.allclose(pfs[0], pfs[1], atol=1e-3)
 
 
 def test_vehicle_suspension_imprecise(E):
