@@ -359,10 +359,11 @@ struct Prepared {
   int jit_compiles = 0;
 };
 
-// Jobs below this many samples keep the runtime-dispatched plan: compiling (~1 s the first time a
-// plan is seen; kept in memory, and on disk when EBN_JIT_CACHE names a directory) would cost more than
-// it saves.
-constexpr double kJitPlanMinSamples = 2e10;
+// Jobs below this many samples keep the runtime-dispatched plan. Measured on B200 (profiles/
+// r01_k_workloads.txt): 3.6e10 samples/s dispatched vs 7.9e10 compiled, 1-3 s to compile a plan the
+// first time it is seen (then cached in memory, and on disk when EBN_JIT_CACHE names a directory):
+// break-even near 1e11 samples.
+constexpr double kJitPlanMinSamples = 1e11;
 
 int jit_kernel_of(Prepared& P, JitRole role, JitKernel** out) {
   if (!P.jit_kernel[role]) {

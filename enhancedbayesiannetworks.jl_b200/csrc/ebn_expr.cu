@@ -100,10 +100,118 @@ std::string expr_code_key(const double* consts, int n_consts, int d) {
   return key;
 }
 
+// Values that depend on runtime constants and literals only are computed once per thread in
+// setup() and kept in the functor's context: same operations, same rounding, just not per sample.
+// A division by such a value becomes, outside strict mode, a multiplication by its reciprocal.
 std::string expr_codegen(const double* consts, int n_consts, int d) {
   ExprInfo I;
   if (!expr_check(consts, n_consts, d, &I).empty()) return "";
   const double* code = consts + 2 + I.n_params;
+  struct Val {
+    std::string name;  // how eval() refers to it (for an invariant: how setup() refers to it)
+    bool inv;          // depends on runtime constants / literals only
+    bool leaf;         // a constant or literal itself: usable in eval() directly
+  };
+  std::string setup, eval;
+  std::vector<Val> st;
+  int nv = 0, ns = 0, nh = 0, col = d;
+  // name of `v` as seen from eval(): invariants computed in setup() get a context slot
+  auto in_eval = [&](const Val& v) {
+    if (!v.inv || v.leaf) return v.name;
+    setup += fmt("    c.h[%d] = ", nh) + v.name + ";\n";
+    return fmt("c.h[%d]", nh++);
+  };
+  auto pop = [&]() {
+    Val v = st.back();
+    st.pop_back();
+    return v;
+  };
+  // result of an operation on `args`; rhs(names) builds the expression from the operand names
+  auto apply = [&](std::vector<Val> args, auto rhs) {
+    bool inv = true;
+    for (const Val& a : args) inv = inv && a.inv;
+    std::vector<std::string> names;
+    for (const Val& a : args) names.push_back(inv ? a.name : in_eval(a));
+    if (inv) {
+      const std::string v = fmt("s%d", ns++);
+      setup += "    const double " + v + " = " + rhs(names) + ";\n";
+      st.push_back({v, true, false});
+    } else {
+      const std::string v = fmt("v%d", nv++);
+      eval += "    const double " + v + " = " + rhs(names) + ";\n";
+      st.push_back({v, false, false});
+    }
+  };
+  auto call2 = [](const char* f) {
+    return [f](const std::vector<std::string>& n) { return std::string(f) + "(" + n[0] + ", " + n[1] + ")"; };
+  };
+  auto call1 = [](const char* f) {
+    return [f](const std::vector<std::string>& n) { return std::string(f) + "(" + n[0] + ")"; };
+  };
+  for (int i = 0; i < I.n_ops; ++i) {
+    const int op = (int)code[2 * i];
+    const double arg = code[2 * i + 1];
+    Val a, b, c3;
+    if (kShape[op].pops == 3) { b = pop(); a = pop(); c3 = pop(); }
+    else if (kShape[op].pops == 2) { b = pop(); a = pop(); }
+    else if (kShape[op].pops == 1) { a = pop(); }
+    switch (op) {
+      case EBN_OP_INPUT: st.push_back({fmt("x[%d]", (int)arg), false, false}); break;
+      case EBN_OP_PARAM: st.push_back({fmt("c.k[%d]", (int)arg), true, true}); break;
+      case EBN_OP_CONST: st.push_back({lit(arg), true, true}); break;
+      case EBN_OP_ADD: apply({a, b}, call2("Ops::add")); break;
+      case EBN_OP_SUB: apply({a, b}, call2("Ops::sub")); break;
+      case EBN_OP_MUL: apply({a, b}, call2("Ops::mul")); break;
+      case EBN_OP_DIV:
+        if (b.inv && !a.inv) {
+          // strict: a / b. fast: a * (1 / b), the reciprocal taken once in setup()
+          const std::string bn = b.name;
+          setup += fmt("    c.h[%d] = Ops::strict ? ", nh) + bn + " : 1.0 / " + bn + ";\n";
+          const std::string slot = fmt("c.h[%d]", nh++);
+          const std::string an = in_eval(a);
+          const std::string v = fmt("v%d", nv++);
+          eval += "    const double " + v + " = Ops::strict ? Ops::div(" + an + ", " + slot + ") : " + an + " * " + slot + ";\n";
+          st.push_back({v, false, false});
+        } else {
+          apply({a, b}, call2("Ops::div"));
+        }
+        break;
+      case EBN_OP_NEG: apply({a}, [](const std::vector<std::string>& n) { return "-(" + n[0] + ")"; }); break;
+      case EBN_OP_ABS: apply({a}, call1("fabs")); break;
+      case EBN_OP_SQRT: apply({a}, call1("Ops::sqrt")); break;
+      case EBN_OP_EXP: apply({a}, call1("exp")); break;
+      case EBN_OP_LOG: apply({a}, call1("log")); break;
+      case EBN_OP_SIN: apply({a}, call1("sin")); break;
+      case EBN_OP_COS: apply({a}, call1("cos")); break;
+      case EBN_OP_MIN: apply({a, b}, call2("Ops::min")); break;
+      case EBN_OP_MAX: apply({a, b}, call2("Ops::max")); break;
+      case EBN_OP_POW: apply({a, b}, call2("pow")); break;
+      case EBN_OP_POWI: {
+        const int n = (int)arg;
+        apply({a}, [n](const std::vector<std::string>& v) {
+          const std::string& x = v[0];
+          if (n == 0) return std::string("1.0");
+          if (n == 1) return x;
+          if (n == 2) return "Ops::mul(" + x + ", " + x + ")";
+          if (n == 3) return "Ops::mul(Ops::mul(" + x + ", " + x + "), " + x + ")";
+          return "pow(" + x + ", " + fmt("%d.0", n) + ")";
+        });
+        break;
+      }
+      case EBN_OP_LT:
+        apply({a, b}, [](const std::vector<std::string>& n) { return "((" + n[0] + ") < (" + n[1] + ") ? 1.0 : 0.0)"; });
+        break;
+      case EBN_OP_SELECT:
+        apply({c3, a, b}, [](const std::vector<std::string>& n) {
+          return "((" + n[0] + ") != 0.0 ? (" + n[1] + ") : (" + n[2] + "))";
+        });
+        break;
+      case EBN_OP_STORE:
+        eval += fmt("    x[%d] = ", col++) + in_eval(a) + ";\n";
+        break;
+    }
+  }
+  const std::string result = in_eval(st.back());
   std::string s;
   s += "namespace ebn {\ntemplate <class Ops>\nstruct JitExpr {\n";
   s += "  static constexpr int ID = EBN_LS_EXPRESSION;\n";
@@ -112,65 +220,14 @@ std::string expr_codegen(const double* consts, int n_consts, int d) {
   s += fmt("  static constexpr int D = %d;\n", d);
   s += fmt("  static constexpr int XCAP = %d;\n", d + I.n_store);
   s += "  static constexpr int NC = -1;\n";
-  s += fmt("  struct Ctx { double k[%d]; };\n", I.n_params > 0 ? I.n_params : 1);
+  s += fmt("  struct Ctx { double k[%d]; double h[%d]; };\n", I.n_params > 0 ? I.n_params : 1, nh > 0 ? nh : 1);
   s += "  __device__ static void setup(Ctx& c, const double* k, int, int, const FastMathSmem*) {\n";
-  s += fmt("#pragma unroll\n    for (int i = 0; i < %d; ++i) c.k[i] = k[2 + i];\n  }\n", I.n_params);
+  s += fmt("#pragma unroll\n    for (int i = 0; i < %d; ++i) c.k[i] = k[2 + i];\n", I.n_params);
+  s += setup;
+  s += "  }\n";
   s += "  __device__ __forceinline__ static double eval(const Ctx& c, double* x) {\n";
-  std::vector<std::string> st;
-  int nv = 0, col = d;
-  auto def = [&](const std::string& rhs) {
-    const std::string v = fmt("v%d", nv++);
-    s += "    const double " + v + " = " + rhs + ";\n";
-    st.push_back(v);
-  };
-  auto pop = [&]() {
-    std::string v = st.back();
-    st.pop_back();
-    return v;
-  };
-  for (int i = 0; i < I.n_ops; ++i) {
-    const int op = (int)code[2 * i];
-    const double arg = code[2 * i + 1];
-    std::string a, b, c3;
-    if (kShape[op].pops == 3) { b = pop(); a = pop(); c3 = pop(); }
-    else if (kShape[op].pops == 2) { b = pop(); a = pop(); }
-    else if (kShape[op].pops == 1) { a = pop(); }
-    switch (op) {
-      case EBN_OP_INPUT: st.push_back(fmt("x[%d]", (int)arg)); break;
-      case EBN_OP_PARAM: st.push_back(fmt("c.k[%d]", (int)arg)); break;
-      case EBN_OP_CONST: st.push_back(lit(arg)); break;
-      case EBN_OP_ADD: def("Ops::add(" + a + ", " + b + ")"); break;
-      case EBN_OP_SUB: def("Ops::sub(" + a + ", " + b + ")"); break;
-      case EBN_OP_MUL: def("Ops::mul(" + a + ", " + b + ")"); break;
-      case EBN_OP_DIV: def("Ops::div(" + a + ", " + b + ")"); break;
-      case EBN_OP_NEG: def("-(" + a + ")"); break;
-      case EBN_OP_ABS: def("fabs(" + a + ")"); break;
-      case EBN_OP_SQRT: def("Ops::sqrt(" + a + ")"); break;
-      case EBN_OP_EXP: def("exp(" + a + ")"); break;
-      case EBN_OP_LOG: def("log(" + a + ")"); break;
-      case EBN_OP_SIN: def("sin(" + a + ")"); break;
-      case EBN_OP_COS: def("cos(" + a + ")"); break;
-      case EBN_OP_MIN: def("Ops::min(" + a + ", " + b + ")"); break;
-      case EBN_OP_MAX: def("Ops::max(" + a + ", " + b + ")"); break;
-      case EBN_OP_POW: def("pow(" + a + ", " + b + ")"); break;
-      case EBN_OP_POWI: {
-        const int n = (int)arg;
-        if (n == 0) def("1.0");
-        else if (n == 1) def(a);
-        else if (n == 2) def("Ops::mul(" + a + ", " + a + ")");
-        else if (n == 3) def("Ops::mul(Ops::mul(" + a + ", " + a + "), " + a + ")");
-        else def("pow(" + a + ", " + fmt("%d.0", n) + ")");
-        break;
-      }
-      case EBN_OP_LT: def("((" + a + ") < (" + b + ") ? 1.0 : 0.0)"); break;
-      case EBN_OP_SELECT: def("((" + c3 + ") != 0.0 ? (" + a + ") : (" + b + "))"); break;
-      case EBN_OP_STORE:
-        // a value that is still an `x[..]` / constant reference is copied like any other
-        s += fmt("    x[%d] = ", col++) + a + ";\n";
-        break;
-    }
-  }
-  s += "    return " + st.back() + ";\n  }\n};\n}  // namespace ebn\n";
+  s += eval;
+  s += "    return " + result + ";\n  }\n};\n}  // namespace ebn\n";
   return s;
 }
 

@@ -24,13 +24,16 @@ using Distributions
 using DataFrames
 using Libdl
 
-export CudaMonteCarlo, CudaModel, ebn_init, ebn_shutdown
+export CudaMonteCarlo, CudaModel, CudaExprModel, ebn_init, ebn_shutdown
 
 const LIB = Ref{String}(get(ENV, "EBNCUDA_LIB", "libebncuda.so"))
 
 # ---- constants of include/ebncuda.h ------------------------------------------------------------
 const EBN_LS = Dict(:vehicle_suspension => 1, :straub_frame => 2, :hydrogen_radius => 3,
-    :polynomial => 4, :min_affine => 5, :straub_frame_r45 => 6, :straub_capacity => 7)
+    :polynomial => 4, :min_affine => 5, :straub_frame_r45 => 6, :straub_capacity => 7, :expression => 8)
+# EBN_OP_* (expression program)
+const OP_INPUT, OP_PARAM, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_ABS, OP_SQRT, OP_EXP, OP_LOG,
+    OP_SIN, OP_COS, OP_MIN, OP_MAX, OP_POW, OP_POWI, OP_LT, OP_SELECT, OP_STORE = 0:20
 const IN_PARAM, IN_NORMAL, IN_LOGNORMAL, IN_UNIFORM, IN_GUMBEL, IN_GAMMA, IN_EXP_AFFINE, IN_TABULATED = 0:7
 
 # typedef struct ebn_input { int32 kind; int32 flags; double p[4]; double lo; double hi; }  (56 bytes)
@@ -88,18 +91,22 @@ ebn_shutdown() = check(ccall((:ebn_shutdown, LIB[]), Cint, ()))
 
 # ---- the plug-in point: a new AbstractMonteCarlo subtype ---------------------------------------
 """
-    CudaMonteCarlo(n; seed=0x5EED0001, strict=false)
+    CudaMonteCarlo(n; seed=0x5EED0001, strict=false, performance=nothing)
 
 Simulation object routing a functional node to libebncuda. `strict=true` evaluates the limit
 state with one IEEE operation per Julia operation (bit-exact `g`), the default contracts FMAs and
-hoists reciprocals (|Δg| ~ 1e-13, count differences only on ties).
+hoists reciprocals (|Δg| ~ 1e-13, count differences only on ties). For a chain of `CudaExprModel`s,
+`performance` is the node's performance function as a quoted expression (`:(2 .- df.C)`); the
+node's own `performance::Function` cannot be translated. Default: the last model's column.
 """
 struct CudaMonteCarlo <: UncertaintyQuantification.AbstractMonteCarlo
     n::Int
     seed::UInt64
     strict::Bool
+    performance::Any
 end
-CudaMonteCarlo(n::Integer; seed::Integer=0x5EED0001, strict::Bool=false) = CudaMonteCarlo(n, UInt64(seed), strict)
+CudaMonteCarlo(n::Integer; seed::Integer=0x5EED0001, strict::Bool=false, performance=nothing) =
+    CudaMonteCarlo(n, UInt64(seed), strict, performance)
 
 """
     CudaModel(name, limit_state, consts, args)
@@ -113,6 +120,135 @@ struct CudaModel <: UncertaintyQuantification.UQModel
     limit_state::Symbol
     consts::Vector{Float64}
     args::Vector{Symbol}
+end
+
+"""
+    CudaExprModel(name, :(formula); constants...)
+
+A `UQModel` whose closure body is given as a quoted Julia expression over the DataFrame columns
+(written `df.x` or plain `x`) and named constants, e.g.
+
+    CudaExprModel(:g2, :(4000 .* df.C .* Mg15 .- 8.6394); Mg15 = (M * g)^-1.5)
+
+A chain of these (and a quoted `performance`) is compiled, in Julia's evaluation order, into the
+expression program of include/ebncuda.h and then into a GPU kernel at run time (NVRTC).
+`rand(Normal(mu, sigma))` / `randn()` inside a formula become hidden standard-normal inputs.
+"""
+struct CudaExprModel <: UncertaintyQuantification.UQModel
+    name::Symbol
+    formula::Any
+    constants::Dict{Symbol,Float64}
+end
+CudaExprModel(name::Symbol, formula; constants...) =
+    CudaExprModel(name, formula, Dict{Symbol,Float64}(k => Float64(v) for (k, v) in constants))
+
+# -- Julia Expr -> expression program (post-order = Julia's evaluation order) ------------------------
+mutable struct Emitter
+    columns::Dict{Symbol,Int}      # 0-based column of inputs and stored models
+    params::Dict{Symbol,Int}       # 0-based runtime constant
+    hidden_base::Int
+    n_hidden::Int
+    code::Vector{Float64}
+end
+emit!(e::Emitter, op, arg=0.0) = push!(e.code, Float64(op), Float64(arg))
+hidden!(e::Emitter) = (emit!(e, OP_INPUT, e.hidden_base + e.n_hidden); e.n_hidden += 1)
+
+const UNARY = Dict(:sqrt => OP_SQRT, :exp => OP_EXP, :log => OP_LOG, :abs => OP_ABS, :sin => OP_SIN, :cos => OP_COS)
+const BINARY = Dict(:+ => OP_ADD, :- => OP_SUB, :* => OP_MUL, :/ => OP_DIV)
+undot(f::Symbol) = (s = String(f); startswith(s, ".") && length(s) > 1 ? Symbol(s[2:end]) : f)
+
+function emit_expr!(e::Emitter, x)
+    if x isa Real
+        emit!(e, OP_CONST, x)
+    elseif x isa Symbol
+        if haskey(e.columns, x)
+            emit!(e, OP_INPUT, e.columns[x])
+        elseif haskey(e.params, x)
+            emit!(e, OP_PARAM, e.params[x])
+        elseif x === :pi || x === :π
+            emit!(e, OP_CONST, Float64(pi))
+        else
+            error("unknown name $x: not an input column, an earlier model, or a constant")
+        end
+    elseif x isa QuoteNode
+        emit_expr!(e, x.value)
+    elseif x isa Expr && x.head === :. && length(x.args) == 2 && x.args[1] === :df      # df.x
+        emit_expr!(e, x.args[2])
+    elseif x isa Expr && x.head === :. && x.args[2] isa Expr && x.args[2].head === :tuple   # f.(args...)
+        emit_expr!(e, Expr(:call, x.args[1], x.args[2].args...))
+    elseif x isa Expr && x.head === :ref                                                 # g1[1] on a scalar
+        emit_expr!(e, x.args[1])
+    elseif x isa Expr && x.head === :if && length(x.args) == 3                           # c ? a : b
+        emit_expr!(e, x.args[1]); emit_expr!(e, x.args[2]); emit_expr!(e, x.args[3]); emit!(e, OP_SELECT)
+    elseif x isa Expr && x.head === :call
+        f, args = undot(x.args[1]), x.args[2:end]
+        if f === :^ && length(args) == 2
+            emit_expr!(e, args[1])
+            if args[2] isa Integer
+                emit!(e, OP_POWI, args[2])
+            else
+                emit_expr!(e, args[2]); emit!(e, OP_POW)
+            end
+        elseif f === :- && length(args) == 1
+            args[1] isa Real ? emit!(e, OP_CONST, -args[1]) : (emit_expr!(e, args[1]); emit!(e, OP_NEG))
+        elseif haskey(BINARY, f) && length(args) >= 2           # a + b + c is +(a, b, c): folds left
+            emit_expr!(e, args[1])
+            for a in args[2:end]
+                emit_expr!(e, a); emit!(e, BINARY[f])
+            end
+        elseif haskey(UNARY, f) && length(args) == 1
+            emit_expr!(e, args[1]); emit!(e, UNARY[f])
+        elseif f in (:min, :max) && length(args) >= 2
+            emit_expr!(e, args[1])
+            for a in args[2:end]
+                emit_expr!(e, a); emit!(e, f === :min ? OP_MIN : OP_MAX)
+            end
+        elseif f in (:minimum, :maximum) && length(args) == 1 && args[1] isa Expr && args[1].head in (:vect, :tuple)
+            emit_expr!(e, Expr(:call, f === :minimum ? :min : :max, args[1].args...))
+        elseif f === :< && length(args) == 2
+            emit_expr!(e, args[1]); emit_expr!(e, args[2]); emit!(e, OP_LT)
+        elseif f === :> && length(args) == 2
+            emit_expr!(e, args[2]); emit_expr!(e, args[1]); emit!(e, OP_LT)
+        elseif f === :ifelse && length(args) == 3
+            emit_expr!(e, args[1]); emit_expr!(e, args[2]); emit_expr!(e, args[3]); emit!(e, OP_SELECT)
+        elseif f === :randn && isempty(args)
+            hidden!(e)
+        elseif f === :rand && length(args) == 1 && args[1] isa Expr && args[1].head === :call && args[1].args[1] === :Normal
+            pa = args[1].args[2:end]
+            if isempty(pa)
+                hidden!(e)
+            else                                                # mu + sigma * randn(), as Distributions.jl
+                emit_expr!(e, pa[1]); emit_expr!(e, pa[2]); hidden!(e); emit!(e, OP_MUL); emit!(e, OP_ADD)
+            end
+        else
+            error("function $f with $(length(args)) argument(s) has no device translation")
+        end
+    else
+        error("unsupported syntax: $x")
+    end
+end
+
+count_hidden(x) = x isa Expr ? ((x.head === :call && (x.args[1] === :randn || x.args[1] === :rand) ? 1 : 0) +
+                                sum(count_hidden, x.args; init=0)) : 0
+
+"Returns (consts, n_hidden, stored names): the expression program for `inputs` (column order of the job)."
+function compile_program(inputs::Vector{Symbol}, models::Vector{CudaExprModel}, performance)
+    params = Dict{Symbol,Float64}()
+    for m in models, (k, v) in m.constants
+        get!(params, k, v) == v || error("constant $k has two different values in one model chain")
+    end
+    names = collect(keys(params))
+    nh = sum(count_hidden(m.formula) for m in models; init=0) + count_hidden(performance)
+    e = Emitter(Dict(c => i - 1 for (i, c) in enumerate(inputs)), Dict(k => i - 1 for (i, k) in enumerate(names)),
+        length(inputs), 0, Float64[])
+    for (t, m) in enumerate(models)
+        emit_expr!(e, m.formula)
+        emit!(e, OP_STORE)
+        e.columns[m.name] = length(inputs) + nh + t - 1
+    end
+    emit_expr!(e, performance)
+    consts = vcat(Float64(length(names)), Float64(length(e.code) ÷ 2), [params[k] for k in names], e.code)
+    return consts, nh, [m.name for m in models]
 end
 
 # ---- marshalling: UQInput -> ebn_input_t --------------------------------------------------------
@@ -165,6 +301,14 @@ function pf_batch(model::CudaModel, scenario_inputs::Vector{<:Vector}, sim::Cuda
     return counts, pf, var
 end
 
+"Expression chain: all scenarios of a node in one call. `columns` = the input names in DataFrame order."
+function pf_batch(models::Vector{CudaExprModel}, performance, scenario_inputs::Vector{<:Vector}, sim::CudaMonteCarlo)
+    columns = Symbol[i.name for i in scenario_inputs[1]]
+    consts, nh, _ = compile_program(columns, models, performance)
+    return pf_batch(CudaModel(models[end].name, :expression, consts, columns), scenario_inputs, sim;
+        hidden=fill(abi(Normal(), -Inf, Inf), nh))
+end
+
 # the in-model `rand(Normal(...))` draws of the Straub capacities travel as hidden N(0,1) inputs
 const N_HIDDEN = Dict(:straub_frame => 5, :straub_frame_r45 => 3, :straub_capacity => 1)
 hidden_inputs(m::CudaModel) = fill(abi(Normal(), -Inf, Inf), get(N_HIDDEN, m.limit_state, 0))
@@ -189,8 +333,12 @@ function EnhancedBayesianNetworks._evaluate_node(net::EnhancedBayesianNetwork,
     cpt_names = isempty(combos[1]) ? [node.name] : vcat([a.name for a in ancestors], node.name)
     cpt = DiscreteConditionalProbabilityTable{PreciseDiscreteProbability}(cpt_names)
     scen = map(ev -> mapreduce(p -> _uq_inputs(p, ev), vcat, parents(net, node)[3]; init=UQInput[]), evidences)
-    model = node.models[end]::CudaModel
-    _, pf, var = pf_batch(model, scen, sim; hidden=hidden_inputs(model))
+    _, pf, var = if all(m -> m isa CudaExprModel, node.models)
+        pf_batch(Vector{CudaExprModel}(node.models), something(sim.performance, node.models[end].name), scen, sim)
+    else
+        model = node.models[end]::CudaModel
+        pf_batch(model, scen, sim; hidden=hidden_inputs(model))
+    end
     info = Dict{AbstractVector{Symbol},Dict}()
     for (s, ev) in enumerate(evidences)
         fail_ev = copy(ev); fail_ev[node.name] = Symbol(string(node.name) * "_fail")

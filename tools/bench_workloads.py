@@ -36,7 +36,33 @@ run("W5 vehicle grid, 1024 scenarios", W.w5_vehicle_grid(n=4 * 10**6))
 run("W4 vehicle, V fixed: 4 states x 25 outer-loop values", W.w4_vehicle_fixed_v(np.linspace(7, 12, 25), n=2 * 10**7))
 j = W.w1_vehicle(n=10**8)
 j.inputs[:, 3]["lo"] = 400.0   # truncated normals: inverse-CDF path through the generic plan
-run("W1 with C truncated at 400 (generic plan)", j)
+j.jit_plan = False
+run("W1 with C truncated at 400 (runtime-dispatched plan)", j)
+j.jit_plan = True
+run("W1 with C truncated at 400 (plan compiled at run time)", j)
+from ebn_b200 import expr  # noqa: E402
+k = W.vehicle_consts()
+VEHICLE_TEXT = [
+    ("g1", "1 .- (pi .* m .* df.V .* df.A) ./ (df.b0 .* df.K .* g .^ 2) .* ((df.Ck ./ (m .+ M) .- (df.C ./ M)) .^ 2"
+           " .+ df.C .^ 2 ./ (m .* M) .+ df.Ck .* df.K .^ 2 ./ (m .* M .^ 2))"),
+    ("g2", "4000 .* df.C .* Mg15 .- 8.6394"),
+    ("g3", "2 .* sqrt(M .* g .* (df.K .^ 2 .* df.Ck ./ (df.C .* (m .+ M)) .+ df.C)) .- 1"),
+    ("g4", "df.Ck .- gMm"),
+    ("y", "minimum([g1[1], g2, g3, g4[1]])"),
+]
+vp = expr.compile_program(["A", "b0", "V", "C", "Ck", "K"], VEHICLE_TEXT, "y",
+                          params={"M": k[0], "m": k[1], "g": k[2], "Mg15": k[3], "gMm": k[4]})
+w1 = W.w1_vehicle(n=10**8)
+run("W1 vehicle, closures as text (run-time compiled, fast)",
+    ebn_b200.Job(ebn_b200._lib.LS_EXPRESSION, vp.consts, w1.inputs, n=10**8, seed=w1.seed))
+run("W1 vehicle, closures as text (run-time compiled, strict)",
+    ebn_b200.Job(ebn_b200._lib.LS_EXPRESSION, vp.consts, w1.inputs, n=10**8, seed=w1.seed, strict=True))
+lam, zeta = W.lognormal_params(150.0, 30.0)
+cap = "exp(rand(Normal(lam + rho * zeta * df.Ur, sqrt((1 - rho^2) * zeta^2))))"
+sp = expr.compile_program(["Ur", "V", "H"], [(f"r{i}", cap) for i in range(1, 6)] + [("G", "minimum([r1 + r2 + r4 + r5 - 5 * df.H, r2 + 2 * r3 + r4 - 5 * df.V, r1 + 2 * r3 + 2 * r4 + r5 - 5 * df.H - 5 * df.V])")], "df.G", params={"lam": lam, "zeta": zeta, "rho": W.STRAUB_RHO})
+w2 = W.w2_straub(n=10**9)
+run("W2 Straub, closures as text (run-time compiled, fast)",
+    ebn_b200.Job(ebn_b200._lib.LS_EXPRESSION, sp.consts, w2.inputs, n=10**9, seed=w2.seed))
 prog = np.array([1, 2, 1.0, 1, 0, 1.0, 1, 1])
 rows = [[(0, a, 0, 0, 0, -np.inf, np.inf), (1, 0.0, 1.0, 0, 0, -np.inf, np.inf)] for a in np.linspace(0, 3, 20)]
 hj = ebn_b200.Job(ebn_b200._lib.LS_POLYNOMIAL, prog, ebn_b200.make_inputs(rows), n=10**8, seed=3)
