@@ -477,7 +477,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
   // plan fits, every scenario has the same marginal kinds, and the job is large (or asks for it).
   {
     const bool expr = job->limit_state == EBN_LS_EXPRESSION;
-    bool uniform = !copula;
+    bool uniform = true;
     for (int s = 1; s < S && uniform; ++s)
       for (int j = 0; j < d; ++j)
         if (P.plan[(size_t)s * d + j].kind != P.plan[j].kind) { uniform = false; break; }
@@ -485,7 +485,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
     const bool forced = (job->flags & EBN_JOB_JIT_PLAN) != 0;
     if (never && forced) return fail(EBN_EINVAL, "EBN_JOB_JIT_PLAN and EBN_JOB_NO_JIT_PLAN are exclusive");
     bool plan_jit = false;
-    if (!expr && P.plan_class == PLAN_DYNAMIC && uniform && !never) {
+    if (!expr && (P.plan_class == PLAN_DYNAMIC || P.plan_class == PLAN_COPULA) && uniform && !never) {
       const char* env = getenv("EBN_JIT_PLAN");  // "0": never, "1": always (experiments)
       const bool big = (double)job->n_per_scenario * S >= kJitPlanMinSamples;
       if (forced || (env && env[0] == '1')) {
@@ -506,7 +506,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
       P.jit_spec.n_consts = job->n_consts;
       if (uniform && !(expr && never))
         for (int j = 0; j < d; ++j) P.jit_spec.kinds.push_back(P.plan[j].kind);
-      if (!P.jit_spec.kinds.empty()) P.plan_class = PLAN_STATIC;
+      if (!P.jit_spec.kinds.empty() && !copula) P.plan_class = PLAN_STATIC;
     }
   }
   P.world = jw * (ndev_override > 0 ? ndev_override : (int)g.devs.size());
@@ -740,7 +740,7 @@ int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, i
   g.stats.samples = my_samples;
   g.stats.launches = (int)nd * (mode == 1 ? 2 : 1);
   g.stats.devices = (int)nd;
-  g.stats.specialised = P.plan_class == PLAN_STATIC || P.plan_class == PLAN_STATIC2;
+  g.stats.specialised = P.plan_class == PLAN_STATIC || P.plan_class == PLAN_STATIC2 || !P.jit_spec.kinds.empty();
   g.stats.jit_compiles = P.jit_compiles;
   return EBN_OK;
 }

@@ -177,10 +177,9 @@ bool make_unit(const JitSpec& spec, JitRole role, Unit* u, std::string* err) {
   }
   const std::string functor = fmt("ebn::%s<ebn::%s>", ls, spec.strict ? "StrictOps" : "FastOps");
   std::string plan;
-  if (spec.copula) plan = "ebn::CopulaPlan";
-  else if (spec.kinds.empty()) plan = "ebn::DynamicPlan";
+  if (spec.kinds.empty()) plan = spec.copula ? "ebn::CopulaPlan" : "ebn::DynamicPlan";
   else {
-    plan = "ebn::StaticPlan<";
+    plan = spec.copula ? "ebn::StaticCopulaPlan<" : "ebn::StaticPlan<";
     for (size_t j = 0; j < spec.kinds.size(); ++j) plan += fmt(j ? ",%d" : "%d", spec.kinds[j]);
     plan += ">";
   }

@@ -33,14 +33,31 @@ constexpr int kPairUnroll = EBN_UNROLL;  // pairs per trip of the static count l
 template <int... K>
 struct StaticPlan {
   static constexpr bool is_static = true;
+  static constexpr bool is_copula = false;
+  static constexpr bool is_static_copula = false;
   static constexpr int n = sizeof...(K);
   static constexpr int kinds[sizeof...(K) ? sizeof...(K) : 1] = {K...};
 };
 struct DynamicPlan {
   static constexpr bool is_static = false;
+  static constexpr bool is_copula = false;
+  static constexpr bool is_static_copula = false;
 };
 struct CopulaPlan {
   static constexpr bool is_static = false;
+  static constexpr bool is_copula = true;
+  static constexpr bool is_static_copula = false;
+};
+// Gaussian copula with the marginal kinds known at compile time (instantiated at run time only,
+// ebn_jit.cu): the eps draws, the triangular product z = L eps and the marginal transforms are
+// unrolled over registers instead of looping over local-memory arrays.
+template <int... K>
+struct StaticCopulaPlan {
+  static constexpr bool is_static = false;  // uses the generic sample loop
+  static constexpr bool is_copula = true;
+  static constexpr bool is_static_copula = true;
+  static constexpr int n = sizeof...(K);
+  static constexpr int kinds[sizeof...(K) ? sizeof...(K) : 1] = {K...};
 };
 
 struct NoStaticPlan {
@@ -59,6 +76,69 @@ template <class Plan>
 __host__ __device__ constexpr int static_calls() {
   return (static_word_offset<Plan, Plan::n>() + 3) / 4;
 }
+
+// Under a copula every random input owns the 3 words of its Box-Muller pair.
+template <class Plan, int J>
+__host__ __device__ constexpr int copula_word_offset() {
+  int off = 0;
+  for (int i = 0; i < J; ++i) off += Plan::kinds[i] == DK_CONST ? 0 : 3;
+  return off;
+}
+template <class Plan, int J>
+struct CopulaEps {
+  __device__ __forceinline__ static void run(const Philox4* ph, const FastMathSmem& sm, double* e0, double* e1) {
+    if constexpr (J < Plan::n) {
+      if constexpr (Plan::kinds[J] != DK_CONST) {
+        StaticWords<copula_word_offset<Plan, J>()> ws{ph};
+        box_muller_words(ws.template w<0>(), ws.template w<1>(), ws.template w<2>(), sm, e0[J], e1[J]);
+      } else {
+        e0[J] = 0.0;
+        e1[J] = 0.0;
+      }
+      CopulaEps<Plan, J + 1>::run(ph, sm, e0, e1);
+    }
+  }
+};
+template <class Plan, int J>
+struct CopulaMarginals {
+  __device__ __forceinline__ static void run(const DevInput* sp, const double* L, const double* tables,
+                                             const FastMathSmem& sm, const double* e0, const double* e1,
+                                             double* x0, double* x1) {
+    if constexpr (J < Plan::n) {
+      constexpr int KIND = Plan::kinds[J];
+      const DevInput in = sp[J];
+      if constexpr (KIND == DK_CONST) {
+        x0[J] = in.a;
+        x1[J] = in.a;
+      } else {
+        // same accumulation order as draw_pair_copula (a Parameter column contributes exactly 0)
+        double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+        for (int k = 0; k <= J; ++k) {
+          if (Plan::kinds[k] != DK_CONST) {
+            const double l = L[J * Plan::n + k];
+            z0 = fma(l, e0[k], z0);
+            z1 = fma(l, e1[k], z1);
+          }
+        }
+        if constexpr (KIND == DK_NORMAL_BM) {
+          x0[J] = fma(z0, in.b, in.a);
+          x1[J] = fma(z1, in.b, in.a);
+        } else if constexpr (KIND == DK_LOGNORMAL_BM) {
+          x0[J] = exp_fast(fma(z0, in.b, in.a), sm);
+          x1[J] = exp_fast(fma(z1, in.b, in.a), sm);
+        } else if constexpr (KIND == DK_UNIFORM) {
+          x0[J] = fma(phi_clamped(z0), in.b, in.a);
+          x1[J] = fma(phi_clamped(z1), in.b, in.a);
+        } else {
+          x0[J] = icdf<KIND>(in, tables, sm, phi_clamped(z0));
+          x1[J] = icdf<KIND>(in, tables, sm, phi_clamped(z1));
+        }
+      }
+      CopulaMarginals<Plan, J + 1>::run(sp, L, tables, sm, e0, e1, x0, x1);
+    }
+  }
+};
 
 template <class Plan, int XCAP, int J>
 struct DrawAll {
@@ -85,7 +165,16 @@ __device__ __forceinline__ void draw_inputs(const DevInput* sp, const double* sL
     for (int c = 0; c < NC; ++c)
       ph[c] = philox4x32_10(pc.qlo, pc.qhi, pc.stream, (uint32_t)c, pc.k0, pc.k1);
     DrawAll<Plan, XCAP, 0>::run(sp, ph, pc, tables, sm, x0, x1);
-  } else if constexpr (std::is_same<Plan, CopulaPlan>::value) {
+  } else if constexpr (Plan::is_static_copula) {
+    constexpr int NC = (copula_word_offset<Plan, Plan::n>() + 3) / 4;
+    Philox4 ph[NC > 0 ? NC : 1];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      ph[c] = philox4x32_10(pc.qlo, pc.qhi, pc.stream, (uint32_t)c, pc.k0, pc.k1);
+    double e0[Plan::n], e1[Plan::n];
+    CopulaEps<Plan, 0>::run(ph, sm, e0, e1);
+    CopulaMarginals<Plan, 0>::run(sp, sL, tables, sm, e0, e1, x0, x1);
+  } else if constexpr (Plan::is_copula) {
     draw_pair_copula(sp, sL, d, pc, tables, sm, x0, x1);
   } else {
     Philox4 cache;
@@ -221,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
   constexpr int XCAP = LS::XCAP;
   __shared__ FastMathSmem s_fm;
   __shared__ DevInput s_plan[EBN_MAX_INPUTS];
-  __shared__ double s_chol[std::is_same<Plan, CopulaPlan>::value ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
+  __shared__ double s_chol[Plan::is_copula ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
   __shared__ unsigned int s_red[kWarps];
   __shared__ double s_sum[MODE == 1 ? 2 * kWarps : 1];
   extern __shared__ unsigned char s_dyn[];  // MODE 1: edges (double) then bins (u32)
@@ -244,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
 
     __syncthreads();  // previous item's readers are done with s_plan / s_bins
     if (tid < p.d) s_plan[tid] = p.plan[(int64_t)s * p.d + tid];
-    if (std::is_same<Plan, CopulaPlan>::value) {
+    if (Plan::is_copula) {
       const double* L = p.chol + (p.chol_shared ? 0 : (int64_t)s * p.d * p.d);
       for (int i = tid; i < p.d * p.d; i += kThreads) s_chol[i] = L[i];
     }
@@ -357,12 +446,12 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
   constexpr int XCAP = LS::XCAP;
   __shared__ FastMathSmem s_fm;
   __shared__ DevInput s_plan[EBN_MAX_INPUTS];
-  __shared__ double s_chol[std::is_same<Plan, CopulaPlan>::value ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
+  __shared__ double s_chol[Plan::is_copula ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
   typename LS::Ctx ctx;
   LS::setup(ctx, p.consts, p.n_consts, p.d, &s_fm);
   fastmath_init(s_fm, threadIdx.x, kThreads);
   if (threadIdx.x < p.d) s_plan[threadIdx.x] = p.plan[(int64_t)scenario * p.d + threadIdx.x];
-  if (std::is_same<Plan, CopulaPlan>::value) {
+  if (Plan::is_copula) {
     const double* L = p.chol + (p.chol_shared ? 0 : (int64_t)scenario * p.d * p.d);
     for (int i = threadIdx.x; i < p.d * p.d; i += kThreads) s_chol[i] = L[i];
   }

@@ -151,6 +151,35 @@ def test_jit_sampling_plan_matches_dynamic_plan(ebn):
     assert np.array_equal(ebn.sample_matrix(a, 1, 0, 5000), ebn.sample_matrix(b, 1, 0, 5000))
 
 
+def test_jit_copula_plan_matches_runtime_copula(ebn):
+    """BASELINE config 3 shape (Gaussian copula over 5 lognormals, a tabulated Gamma and a Gumbel): the
+    copula plan unrolled at run time draws exactly the samples of the looping one, and the three frame
+    mechanisms written as a formula count like the min-affine functor."""
+    from ebn_b200 import expr, workloads as W
+    n = 200_001
+    base = W.w3_straub_copula(n=n, bits=3, strict=True)
+    kw = dict(n=n, seed=base.seed, strict=True, corr_chol=base.corr_chol, tables=base.tables)
+    loop = ebn.Job(base.limit_state, base.consts, base.inputs, jit_plan=False, **kw)
+    unrolled = ebn.Job(base.limit_state, base.consts, base.inputs, jit_plan=True, **kw)
+    c_loop, _, _ = ebn.pf_batch(loop)
+    assert ebn.last_stats()["specialised"] == 0
+    c_unr, _, _ = ebn.pf_batch(unrolled)
+    assert ebn.last_stats()["specialised"] == 1
+    assert np.array_equal(c_loop, c_unr) and c_loop.min() > 0
+    Xa, Xb = ebn.sample_matrix(loop, 5, 3, 4099), ebn.sample_matrix(unrolled, 5, 3, 4099)
+    assert np.array_equal(Xa, Xb)
+    prog = expr.compile_program(
+        ["r1", "r2", "r3", "r4", "r5", "V", "H"], [],
+        "min(r1 + r2 + r4 + r5 - 5 * H, r2 + 2 * r3 + r4 - 5 * V, r1 + 2 * r3 + 2 * r4 + r5 - 5 * H - 5 * V)")
+    as_text = ebn.Job(ebn._lib.LS_EXPRESSION, prog.consts, base.inputs, **kw)
+    c_txt, _, _ = ebn.pf_batch(as_text)
+    assert ebn.last_stats()["specialised"] == 1
+    # the affine functor accumulates 0 + c*x terms in column order, the formula in its own order:
+    # g agrees to rounding, counts to ties
+    assert np.max(np.abs(c_txt - c_loop)) <= 2
+    assert np.array_equal(ebn.sample_matrix(as_text, 5, 3, 4099), Xa)
+
+
 def test_expression_errors(ebn):
     from ebn_b200 import expr
     L = ebn._lib

@@ -31,7 +31,15 @@ def run(name, job, reps=3, hist_edges=None):
 run("W1 vehicle (fast)", W.w1_vehicle(n=10**8))
 run("W1 vehicle (strict: Julia-order g, 6 div + sqrt)", W.w1_vehicle(n=10**8, strict=True))
 run("W2 Straub frame S=1", W.w2_straub(n=10**9))
-run("W3 Straub-style copula, 64 scenarios", W.w3_straub_copula(n=2 * 10**7))
+w3 = W.w3_straub_copula(n=2 * 10**7)
+w3.jit_plan = False
+run("W3 Straub-style copula, 64 scenarios (looping copula plan)", w3)
+w3.jit_plan = True
+run("W3 copula, plan unrolled at run time", w3)
+from ebn_b200 import expr  # noqa: E402
+w3p = expr.compile_program(["r1", "r2", "r3", "r4", "r5", "V", "H"], [], "min(r1 + r2 + r4 + r5 - 5 * H, r2 + 2 * r3 + r4 - 5 * V, r1 + 2 * r3 + 2 * r4 + r5 - 5 * H - 5 * V)")
+run("W3 copula, unrolled plan + frame mechanisms as a formula",
+    ebn_b200.Job(ebn_b200._lib.LS_EXPRESSION, w3p.consts, w3.inputs, n=w3.n, seed=w3.seed, corr_chol=w3.corr_chol, tables=w3.tables))
 run("W5 vehicle grid, 1024 scenarios", W.w5_vehicle_grid(n=4 * 10**6))
 run("W4 vehicle, V fixed: 4 states x 25 outer-loop values", W.w4_vehicle_fixed_v(np.linspace(7, 12, 25), n=2 * 10**7))
 j = W.w1_vehicle(n=10**8)
@@ -40,7 +48,6 @@ j.jit_plan = False
 run("W1 with C truncated at 400 (runtime-dispatched plan)", j)
 j.jit_plan = True
 run("W1 with C truncated at 400 (plan compiled at run time)", j)
-from ebn_b200 import expr  # noqa: E402
 k = W.vehicle_consts()
 VEHICLE_TEXT = [
     ("g1", "1 .- (pi .* m .* df.V .* df.A) ./ (df.b0 .* df.K .* g .^ 2) .* ((df.Ck ./ (m .+ M) .- (df.C ./ M)) .^ 2"
