@@ -25,7 +25,7 @@ from . import uq
 from .distributions import EmpiricalDistribution, Exponential, ProbabilityBox, Uniform
 from .network import (BayesianNetwork, CredalNetwork, EnhancedBayesianNetwork, _add_node, _is_cyclic_dfs,
                       _remove_node, add_child, children, discrete_ancestors, order, parents)
-from .nodes import (PI, AbstractMonteCarlo, ApproximatedDiscretization, ContinuousConditionalProbabilityTable,
+from .nodes import (FORM, PI, AbstractMonteCarlo, ApproximatedDiscretization, ContinuousConditionalProbabilityTable,
                     ContinuousFunctionalNode, ContinuousNode, CudaDoubleLoop, CudaRandomSlicing,
                     DiscreteConditionalProbabilityTable, DiscreteFunctionalNode, DiscreteNode, ExactDiscretization,
                     FunctionalNode, UnamedProbabilityBox, _truncate, interval_symbol, isprecise)
@@ -199,6 +199,13 @@ def _evaluate_discrete(net, node: DiscreteFunctionalNode, collect_samples=True) 
             cpt[{**ev, node.name: safe}] = 1 - float(pf[s])
             if collect_samples:
                 info[tuple(ev.values())] = {"cov": float(sd[s]), "samples": samples[s]}
+    elif isinstance(sim, FORM):     # evaluate_node.jl:97-102
+        for inp, ev in zip(scen, evidences):
+            pf, beta, dp, alpha = uq.form(node.models, node.performance, inp, sim)
+            cpt[{**ev, node.name: fail}] = pf
+            cpt[{**ev, node.name: safe}] = 1 - pf
+            if collect_samples:
+                info[tuple(ev.values())] = {"β": beta, "design_point": dp, "α": alpha}
     elif isinstance(sim, CudaDoubleLoop):
         res = uq.double_loop(node.models, node.performance, scen, sim)
         for (lb, ub), ev in zip(res, evidences):

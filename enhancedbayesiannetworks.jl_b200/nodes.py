@@ -459,6 +459,18 @@ DoubleLoop = CudaDoubleLoop
 
 
 @dataclass(frozen=True)
+class FORM:
+    """UQ.jl `FORM(n, tol)`: first-order reliability method (Hasofer-Lind / Rackwitz-Fiessler
+    iteration in standard-normal space). Not a sampling method: each iteration evaluates the limit
+    state on 2d+1 points, which go to the device in one `ebn_eval_matrix` call (strict arithmetic).
+    The result lands in the reference's FORM branch (evaluate_node.jl:97-102): pf plus β, design
+    point and α in `additional_info`."""
+    n: int = 10
+    tol: float = 1e-3
+    h: float = 1e-4      # central finite-difference step in standard-normal space
+
+
+@dataclass(frozen=True)
 class CudaRandomSlicing:
     """UQ.jl `RandomSlicing(sim)`: per sample, the p-box/interval inputs become boxes and the model
     is bounded over them; supported on the device for models that are monotone in each imprecise

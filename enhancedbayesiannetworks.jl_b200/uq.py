@@ -20,7 +20,7 @@ from . import _lib as L
 from .distributions import (INF, Gamma, Interval, JointDistribution, NeedsTable, Normal, Parameter,
                             ProbabilityBox, RandomVariable, Truncated, table_for)
 from . import expr as _expr
-from .nodes import Catalogue, CudaDoubleLoop, CudaMonteCarlo, CudaRandomSlicing, Expression, Model, Poly
+from .nodes import FORM, Catalogue, CudaDoubleLoop, CudaMonteCarlo, CudaRandomSlicing, Expression, Model, Poly
 
 VEHICLE_ARGS = ("A", "b₀", "V", "C", "Cₖ", "K")
 HIST_BINS = 2048  # fine grid a ContinuousFunctionalNode's output is histogrammed on
@@ -299,11 +299,68 @@ def probability_of_failure(models, performance, inputs, sim):
             raise AssertionError("imprecise inputs need DoubleLoop or RandomSlicing")
         pf, sd, smp, _ = pf_scenarios(models, performance, [inputs], sim)
         return float(pf[0]), float(sd[0]), smp[0]
+    if isinstance(sim, FORM):
+        return form(models, performance, inputs, sim)
     if isinstance(sim, CudaDoubleLoop):
         return double_loop(models, performance, [inputs], sim)[0]
     if isinstance(sim, CudaRandomSlicing):
         return random_slicing(models, performance, [inputs], sim)[0]
     raise TypeError(f"simulation {sim!r} has no device path (MonteCarlo, DoubleLoop and RandomSlicing do)")
+
+
+# ---- FORM ------------------------------------------------------------------------------------
+def form(models, performance, inputs, sim: FORM):
+    """UQ.jl `probability_of_failure(models, performance, inputs, ::FORM)` → (pf, β, design point, α).
+    HL-RF: y ← (∇G·y − G(y)) ∇G / |∇G|² with G(y) = g(x(y)), x_j = Q_j(Φ(y_j)); central differences.
+    All evaluations of g run on the device (ebn_eval_matrix, strict); the iteration itself is host
+    logic on d numbers."""
+    from scipy.special import ndtr
+    flat, _, copulas = _flatten(inputs)
+    if copulas:
+        raise UnsupportedModel("FORM under a copula is not implemented")
+    if any(_is_imprecise(i) for i in flat):
+        raise AssertionError("imprecise inputs need DoubleLoop or RandomSlicing")
+    low = lower(models, performance, [i.name for i in flat])
+    by_name = {i.name: i for i in flat}
+    cols = [by_name[c] for c in low.columns]
+    rv = [j for j, c in enumerate(cols) if isinstance(c, RandomVariable)]
+    n_hidden = len(low.hidden)
+    d = len(rv) + n_hidden
+
+    def to_x(Y):
+        X = np.empty((Y.shape[0], len(cols) + n_hidden))
+        for j, c in enumerate(cols):
+            if isinstance(c, Parameter):
+                X[:, j] = c.value
+        for k, j in enumerate(rv):
+            u = np.clip(ndtr(Y[:, k]), 1e-300, 1.0 - 1e-16)
+            X[:, j] = [cols[j].dist.quantile(float(v)) for v in u]
+        X[:, len(cols):] = Y[:, len(rv):]          # in-model standard normals
+        return X
+
+    def G(Y):
+        return L.eval_matrix(low.limit_state, low.consts, to_x(Y), strict=True, want_g=True)[1]
+
+    y = np.zeros(d)
+    alpha = np.zeros(d)
+    beta = 0.0
+    for _ in range(max(1, sim.n)):
+        pts = np.vstack([y] + [y + sgn * sim.h * np.eye(d)[k] for k in range(d) for sgn in (1.0, -1.0)])
+        g = G(pts)
+        grad = (g[1::2] - g[2::2]) / (2.0 * sim.h)
+        nrm2 = float(grad @ grad)
+        if not (nrm2 > 0.0) or not np.all(np.isfinite(g)):
+            raise ValueError("FORM: the limit state has no usable gradient at the current point")
+        y_new = (float(grad @ y) - float(g[0])) * grad / nrm2
+        alpha = -grad / math.sqrt(nrm2)
+        beta_new = float(alpha @ y_new)
+        done = abs(beta_new - beta) < sim.tol and np.linalg.norm(y_new - y) < sim.tol * max(1.0, np.linalg.norm(y_new))
+        y, beta = y_new, beta_new
+        if done:
+            break
+    pf = float(ndtr(-beta))
+    dp = dict(zip([low.columns[j] for j in rv] + [f"__randn{i + 1}" for i in range(n_hidden)], to_x(y[None, :])[0][rv + list(range(len(cols), len(cols) + n_hidden))]))
+    return pf, beta, dp, dict(zip(dp.keys(), alpha))
 
 
 # ---- imprecise inputs ------------------------------------------------------------------------

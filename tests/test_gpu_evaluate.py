@@ -113,6 +113,44 @@ def test_evaluate_continuous_functional_node(E):
         ev._evaluate_node(net, cf3)
 
 
+def test_form_branch(E):
+    """test/networks/ebn/evaluate/evaluate_node.jl:141-158: FORM on C = 1 + B, performance 2 - C, B ~ N(0,1):
+    Π ≈ [0.1587, 0.8413] (atol 0.1 in the reference; a linear limit state makes FORM exact: β = 1)."""
+    b = _cont_root(E, "B", E.Normal())
+    node = E.DiscreteFunctionalNode("C", [E.Model(E.Expression("1 .+ df.B"), "C")], E.Expression("2 .- df.C"), E.FORM())
+    net = E.EnhancedBayesianNetwork([b, node])
+    E.add_child(net, b, node)
+    E.order(net)
+    from ebn_b200.evaluation import _evaluate_node
+    ev = _evaluate_node(net, node)
+    assert isinstance(ev, E.DiscreteNode) and ev.isroot() and ev.name == "C"
+    assert ev.cpt.column("C") == ["C_fail", "C_safe"]
+    pi = ev.cpt.column("Π")
+    assert abs(pi[0] - ndtr(-1.0)) < 1e-9 and pi[1] == 1 - pi[0]
+    info = ev.additional_info[()]
+    assert abs(info["β"] - 1.0) < 1e-9 and abs(info["design_point"]["B"] - 1.0) < 1e-6 and abs(info["α"]["B"] - 1.0) < 1e-9
+    # curved limit state with a non-normal marginal: against a Monte Carlo estimate on the same functor
+    a, b2 = _ab_roots(E)
+    u = _cont_root(E, "U", E.Gumbel(1.0, 0.5))
+    models = [E.Model(E.Expression("df.A .* df.B .+ df.U .^ 2 ./ 4"), "C")]
+    perf = E.Expression("4.5 .- df.C")
+    nf = E.DiscreteFunctionalNode("C", models, perf, E.FORM(n=30, tol=1e-8))
+    nm = E.DiscreteFunctionalNode("C", models, perf, E.MonteCarlo(4_000_000))
+    out = []
+    for nd in (nf, nm):
+        net = E.EnhancedBayesianNetwork([a, b2, u, nd])
+        for p in (a, b2, u):
+            E.add_child(net, p, nd)
+        E.order(net)
+        out.append(_evaluate_node(net, nd))
+    pf_form = [r["Π"] for r in out[0].cpt.data if r["C"] == "C_fail"]
+    pf_mc = [r["Π"] for r in out[1].cpt.data if r["C"] == "C_fail"]
+    assert len(pf_form) == 2
+    for f, m in zip(pf_form, pf_mc):     # first-order approximation: right order of magnitude, not exact
+        assert 0.5 < f / m < 2.0, (f, m)
+    assert set(out[0].additional_info) == {("a1",), ("a2",)} and set(out[0].additional_info[("a1",)]) == {"β", "design_point", "α"}
+
+
 def _imprecise_net(E, sim):
     a = _root(E, "A", ["a1", "a2"], [0.5, 0.5], {"a1": [E.Parameter(1, "A")], "a2": [E.Parameter(2, "A")]})
     b = _cont_root(E, "B", (0.10, 1.30), kind="interval")
