@@ -21,8 +21,19 @@ def test_single_process_multi_device_counts_match_one_gpu():
     hjob = ebn_b200.Job(ebn_b200._lib.LS_POLYNOMIAL, prog, ebn_b200.make_inputs(rows), n=1_000_001, seed=3)
     edges = np.linspace(-3, 7, 41)
     hbase = ebn_b200.hist_batch(hjob, edges)
+    # run-time compiled kernels: one module per device (an expression limit state and a plan compiled on demand)
+    from ebn_b200 import expr
+    ep = expr.compile_program(["A", "B"], [("C", "df.A .+ df.B")], "2 .- df.C")
+    ejob = ebn_b200.Job(ebn_b200._lib.LS_EXPRESSION, ep.consts, hjob.inputs, n=1_000_001, seed=3)
+    ebase = ebn_b200.pf_batch(ejob)[0]
+    tjob = W.w1_vehicle(n=1_000_001)
+    tjob.inputs[:, 3]["lo"] = 400.0
+    tjob.jit_plan = True
+    tbase = ebn_b200.pf_batch(tjob)[0]
     for devs in ([0, 1], list(range(ndev))):
         ebn_b200.init(devs)
+        assert np.array_equal(ebn_b200.pf_batch(ejob)[0], ebase), devs
+        assert np.array_equal(ebn_b200.pf_batch(tjob)[0], tbase), devs
         got = ebn_b200.pf_batch(job)[0]
         st = ebn_b200.last_stats()
         assert np.array_equal(got, base), devs
