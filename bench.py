@@ -31,14 +31,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# FP64-pipe instructions per sample of the W1 kernel: (DFMA 101.2 + DMUL 32.0 + DADD 16.1) warp
+# FP64-pipe instructions per sample of the W1 kernel: (DFMA 98.1 + DMUL 32.0 + DADD 13.1) warp
 # instructions per sample PAIR executed in the hot loop, from the ncu source page of
-# profiles/r01_f_* (= sm__inst_executed_pipe_fp64), i.e. 74.65 per sample. See DESIGN.md
+# profiles/r01_m_* (= sm__inst_executed_pipe_fp64), i.e. 71.6 per sample. See DESIGN.md
 # "Roofline". The SURVEY's ceiling for this figure is 339; the first version executed 151.5.
-F_ALG_W1 = 74.65
+F_ALG_W1 = 71.6
 # dram__bytes_read.sum + dram__bytes_write.sum of one mc_kernel launch (ncu --set full,
-# profiles/r01_f_ncu_full_w1_n1e7_summary.txt): 38.9 KB read, 0 B written — the plan and tables.
-DRAM_TRAFFIC_BYTES_PER_LAUNCH = 38912
+# profiles/r01_m_ncu_full_w1_n1e7_summary.txt): 36.9 KB read, 0 B written — the plan and tables.
+DRAM_TRAFFIC_BYTES_PER_LAUNCH = 36864
 METRIC = "limit_state_mc_samples_per_sec"
 UNIT = "samples/s"
 

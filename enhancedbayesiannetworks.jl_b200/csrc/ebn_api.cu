@@ -444,14 +444,14 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
                         job->n_tables);
       if (rc) return rc;
     }
-  // word offsets in the pair's Philox stream (layout v2): inputs consume words in order;
-  // under a copula every random input takes the 3 words of its Box-Muller pair
+  // word offsets in the pair's Philox stream (layout v3): inputs consume words in order;
+  // under a copula every random input takes the 2 words of its Box-Muller pair
   for (int s = 0; s < S; ++s) {
     int off = 0;
     for (int j = 0; j < d; ++j) {
       DevInput& di = P.plan[(size_t)s * d + j];
       di.woff = off;
-      off += copula ? (di.kind == DK_CONST ? 0 : 3) : words_of_kind(di.kind);
+      off += copula ? (di.kind == DK_CONST ? 0 : 2) : words_of_kind(di.kind);
     }
   }
   if (copula) {

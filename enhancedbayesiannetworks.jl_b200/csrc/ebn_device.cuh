@@ -2,6 +2,15 @@
 #pragma once
 #include "ebn_rtc_compat.h"
 
+// Threads per block of every kernel. Measured on B200 with the vehicle kernel at 16 warps per SM
+// (profiles/r01_m_tune_block_shape.txt): 64x8 1.466e11, 128x4 1.471e11, 256x2 1.424e11 samples/s —
+// smaller blocks lose less at the per-item reduction barrier.
+#ifndef EBN_THREADS
+#define EBN_THREADS 128
+#endif
+// blocks per SM that give `warps` resident warps per SM
+#define EBN_BLOCKS_FOR_WARPS(warps) ((warps) * 32 / EBN_THREADS)
+
 namespace ebn {
 
 // Canonical per-input sampling recipe, produced on the host from ebn_input_t
@@ -28,14 +37,14 @@ struct DevInput {
   int32_t woff;  // first word of this input in the pair's Philox word stream
 };
 
-// Philox words one input consumes per sample pair (stream layout v2).
+// Philox words one input consumes per sample pair (stream layout v3).
 #ifdef __CUDACC__
 __host__ __device__
 #endif
 constexpr int words_of_kind(int kind) {
   return kind == DK_CONST ? 0
        : kind == DK_UNIFORM ? 2
-       : (kind == DK_NORMAL_BM || kind == DK_LOGNORMAL_BM) ? 3
+       : (kind == DK_NORMAL_BM || kind == DK_LOGNORMAL_BM) ? 2
        : kind == DK_GAMMA_MT ? 0
        : 4;
 }

@@ -216,7 +216,7 @@ std::string expr_codegen(const double* consts, int n_consts, int d) {
   s += "namespace ebn {\ntemplate <class Ops>\nstruct JitExpr {\n";
   s += "  static constexpr int ID = EBN_LS_EXPRESSION;\n";
   s += "  static constexpr bool HAS_FAILS = false;\n";
-  s += "  static constexpr int MIN_BLOCKS = 2;\n";
+  s += "  static constexpr int MIN_BLOCKS = EBN_BLOCKS_FOR_WARPS(16);\n";
   s += fmt("  static constexpr int D = %d;\n", d);
   s += fmt("  static constexpr int XCAP = %d;\n", d + I.n_store);
   s += "  static constexpr int NC = -1;\n";

@@ -144,9 +144,10 @@ __device__ __forceinline__ void sincos_quadrant(double v, double& cps, double& c
   cms = c - s;
 }
 
-// Box-Muller for the sample pair from three 32-bit words:
-//   radius  u = mantissa(w1 & 0xfffff : w0) in (0,1)   (52 bits; the top 12 bits of w1 are free)
-//   angle   first-quadrant angle from all 32 bits of w2 (low 20 bits most significant)
+// Box-Muller for the sample pair from two 32-bit words (64 bits = 42 + 20 + 2):
+//   radius  u = (M + 1/2) 2^-42 in (0,1), M = 42 bits: all of w0 (low 20 bits most significant)
+//           followed by bits 0..9 of w1; reaches 7.6 sigma, P(lost tail) = 2^-43 per draw
+//   angle   first-quadrant angle (pi/2)(A + 1/2) 2^-20, A = bits 10..29 of w1
 //   signs   bits 31 and 30 of w1
 // z0 = s0*R*sin(phi), z1 = s1*R*cos(phi) with R = sqrt(-2 ln u), phi uniform in (0, pi/2):
 // a uniformly random direction, so (z0, z1) are independent standard normals.
@@ -157,15 +158,16 @@ __device__ __forceinline__ void sincos_quadrant(double v, double& cps, double& c
 struct BmFront {
   double r;       // m*rc - 1 of the -ln(u) reduction
   double base;    // -e*ln2 + ln(rc)
-  uint32_t w1;    // sign bits
-  uint32_t w2;    // angle word
+  uint32_t w1;    // angle and sign bits
 };
 
-__device__ __forceinline__ BmFront box_muller_front(uint32_t w0, uint32_t w1, uint32_t w2,
-                                                    const FastMathSmem& sm) {
-  // Mask-only bit placement (one LOP3 per word half, no shifts: the integer ALU is the
-  // scarce pipe next to the fp64 pipe): the low 20 bits of a word become the high mantissa bits.
-  const double u = __hiloint2double((int)((w1 & 0x000FFFFFu) | 0x3FF00000u), (int)w0) - 0x1.fffffffffffffp-1;
+__device__ __forceinline__ BmFront box_muller_front(uint32_t w0, uint32_t w1, const FastMathSmem& sm) {
+  // Bit placement with two LOP3 and one shift (the integer ALU is the scarce pipe next to the
+  // fp64 pipe): the low 20 bits of w0 become the high mantissa bits, its top 12 bits stay in
+  // place in the low word, bits 0..9 of w1 land right below them; the low 10 mantissa bits are 0.
+  const double u = __hiloint2double((int)((w0 & 0x000FFFFFu) | 0x3FF00000u),
+                                    (int)((w0 & 0xFFF00000u) | ((w1 << 10) & 0x000FFFFFu))) -
+                   (1.0 - 0x1p-43);
   const int hi = __double2hiint(u);
   const int ne = 1023 - (hi >> 20);
   const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(u));
@@ -174,7 +176,6 @@ __device__ __forceinline__ BmFront box_muller_front(uint32_t w0, uint32_t w1, ui
   f.r = fma(m, t.x, -1.0);
   f.base = fma(__hiloint2double(0x43380000, ne) - 6755399441055744.0, kFm.ln2, t.y);
   f.w1 = w1;
-  f.w2 = w2;
   return f;
 }
 
@@ -185,8 +186,10 @@ __device__ __forceinline__ void box_muller_back(const BmFront& f, double& z0, do
   p = fma(r, p, kFm.ln1p[1]);
   p = fma(r, p, kFm.ln1p[0]);
   const double t = fma(r * r, p, f.base - r);          // -ln u
-  const double v = __hiloint2double((int)((f.w2 & 0x000FFFFFu) | 0x3FF00000u), (int)(f.w2 & 0xFFF00000u)) -
-                   (1.5 - 0x1p-33);                     // [-1/2, 1/2), centred
+  // angle bits stay where they are (bits 10..29 of the low mantissa word): d = 1 + A 2^-42,
+  // v = (A + 1/2) 2^-20 - 1/2 = d 2^22 - (2^22 + 1/2 - 2^-21), exact, in [-1/2, 1/2)
+  const double v = fma(__hiloint2double(0x3FF00000, (int)(f.w1 & 0x3FFFFC00u)), 4194304.0,
+                       -(4194304.5 - 0x1p-21));
   const double rr = sqrt_pos(t);                        // sqrt(-ln u) = R / sqrt(2)
   double cps, cms;
   sincos_quadrant(v, cps, cms);
@@ -196,9 +199,9 @@ __device__ __forceinline__ void box_muller_back(const BmFront& f, double& z0, do
   z1 = __hiloint2double(__double2hiint(b) ^ (int)((f.w1 << 1) & 0x80000000u), __double2loint(b));
 }
 
-__device__ __forceinline__ void box_muller_words(uint32_t w0, uint32_t w1, uint32_t w2,
-                                                 const FastMathSmem& sm, double& z0, double& z1) {
-  box_muller_back(box_muller_front(w0, w1, w2, sm), z0, z1);
+__device__ __forceinline__ void box_muller_words(uint32_t w0, uint32_t w1, const FastMathSmem& sm,
+                                                 double& z0, double& z1) {
+  box_muller_back(box_muller_front(w0, w1, sm), z0, z1);
 }
 
 }  // namespace ebn

@@ -4,9 +4,6 @@
 
 namespace ebn {
 
-#ifndef EBN_THREADS
-#define EBN_THREADS 256
-#endif
 constexpr int kThreads = EBN_THREADS;
 
 // Fixed-order reduction of the per-item moment partials: one thread per

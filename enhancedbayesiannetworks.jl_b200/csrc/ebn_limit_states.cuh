@@ -60,9 +60,9 @@ struct VehicleSuspension {
   static constexpr int NC = 5;
   static constexpr bool HAS_FAILS = !Ops::strict;  // sign-only test in fast mode
 #ifndef EBN_VEHICLE_BLOCKS
-#define EBN_VEHICLE_BLOCKS 2
+#define EBN_VEHICLE_BLOCKS EBN_BLOCKS_FOR_WARPS(16)
 #endif
-  static constexpr int MIN_BLOCKS = EBN_VEHICLE_BLOCKS;  // blocks of 256 threads per SM: 128 registers, no spills; throughput is issue-bound, not occupancy-bound
+  static constexpr int MIN_BLOCKS = EBN_VEHICLE_BLOCKS;  // 16 warps per SM: 128 registers, no spills; throughput is issue-bound, not occupancy-bound
   struct Ctx {
     double M, m, gg, pow_a, pow_b;     // strict
     double pim, mM, iM, imM, immM, mpM, Mg;
@@ -169,7 +169,7 @@ struct StraubFrame {
   static constexpr int ID = EBN_LS_STRAUB_FRAME;
   static constexpr bool HAS_FAILS = false;
 #ifndef EBN_STRAUB_BLOCKS
-#define EBN_STRAUB_BLOCKS 2
+#define EBN_STRAUB_BLOCKS EBN_BLOCKS_FOR_WARPS(8)  // measured: 8 warps/SM 3.39e10, 16 warps/SM 3.28e10 samples/s
 #endif
   static constexpr int MIN_BLOCKS = EBN_STRAUB_BLOCKS;
   static constexpr int D = 8;
@@ -216,7 +216,7 @@ template <class Ops>
 struct StraubFrameR45 {
   static constexpr int ID = EBN_LS_STRAUB_FRAME_R45;
   static constexpr bool HAS_FAILS = false;
-  static constexpr int MIN_BLOCKS = 2;
+  static constexpr int MIN_BLOCKS = EBN_STRAUB_BLOCKS;
   static constexpr int D = 8;
   static constexpr int XCAP = 8;
   static constexpr int NC = 3;
@@ -254,7 +254,7 @@ template <class Ops>
 struct StraubCapacity {
   static constexpr int ID = EBN_LS_STRAUB_CAPACITY;
   static constexpr bool HAS_FAILS = false;
-  static constexpr int MIN_BLOCKS = 3;
+  static constexpr int MIN_BLOCKS = EBN_BLOCKS_FOR_WARPS(24);
   static constexpr int D = 2;
   static constexpr int XCAP = 2;
   static constexpr int NC = 3;
@@ -277,7 +277,7 @@ template <class Ops>
 struct HydrogenRadius {
   static constexpr int ID = EBN_LS_HYDROGEN_RADIUS;
   static constexpr bool HAS_FAILS = false;
-  static constexpr int MIN_BLOCKS = 3;
+  static constexpr int MIN_BLOCKS = EBN_BLOCKS_FOR_WARPS(24);
   static constexpr int D = 4;
   static constexpr int XCAP = 4;
   static constexpr int NC = 0;
@@ -301,7 +301,7 @@ template <class Ops>
 struct PolynomialProgram {
   static constexpr int ID = EBN_LS_POLYNOMIAL;
   static constexpr bool HAS_FAILS = false;
-  static constexpr int MIN_BLOCKS = 3;
+  static constexpr int MIN_BLOCKS = EBN_BLOCKS_FOR_WARPS(24);
   static constexpr int D = -1;  // variadic
   static constexpr int XCAP = EBN_MAX_INPUTS;
   static constexpr int NC = -1;
@@ -344,7 +344,7 @@ template <class Ops>
 struct MinAffine {
   static constexpr int ID = EBN_LS_MIN_AFFINE;
   static constexpr bool HAS_FAILS = false;
-  static constexpr int MIN_BLOCKS = 3;
+  static constexpr int MIN_BLOCKS = EBN_BLOCKS_FOR_WARPS(24);
   static constexpr int D = -1;
   static constexpr int XCAP = EBN_MAX_INPUTS;
   static constexpr int NC = -1;

@@ -19,9 +19,6 @@
 
 namespace ebn {
 
-#ifndef EBN_THREADS
-#define EBN_THREADS 256
-#endif
 constexpr int kThreads = EBN_THREADS;
 constexpr int kWarps = kThreads / 32;
 #ifndef EBN_UNROLL
@@ -77,11 +74,11 @@ __host__ __device__ constexpr int static_calls() {
   return (static_word_offset<Plan, Plan::n>() + 3) / 4;
 }
 
-// Under a copula every random input owns the 3 words of its Box-Muller pair.
+// Under a copula every random input owns the 2 words of its Box-Muller pair.
 template <class Plan, int J>
 __host__ __device__ constexpr int copula_word_offset() {
   int off = 0;
-  for (int i = 0; i < J; ++i) off += Plan::kinds[i] == DK_CONST ? 0 : 3;
+  for (int i = 0; i < J; ++i) off += Plan::kinds[i] == DK_CONST ? 0 : 2;
   return off;
 }
 template <class Plan, int J>
@@ -90,7 +87,7 @@ struct CopulaEps {
     if constexpr (J < Plan::n) {
       if constexpr (Plan::kinds[J] != DK_CONST) {
         StaticWords<copula_word_offset<Plan, J>()> ws{ph};
-        box_muller_words(ws.template w<0>(), ws.template w<1>(), ws.template w<2>(), sm, e0[J], e1[J]);
+        box_muller_words(ws.template w<0>(), ws.template w<1>(), sm, e0[J], e1[J]);
       } else {
         e0[J] = 0.0;
         e1[J] = 0.0;

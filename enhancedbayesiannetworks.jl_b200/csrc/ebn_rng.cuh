@@ -2,7 +2,7 @@
 //
 // key = (seed lo32, seed hi32); counter = (pair lo32, pair hi32, stream id of the
 // scenario, call index); pair = global sample index >> 1. How the words are
-// consumed is defined in ebn_sampling.cuh (stream layout v2).
+// consumed is defined in ebn_sampling.cuh (stream layout v3).
 // The replacement for `rand(dist, n)` inside UQ.jl's `sample(inputs, n)`
 // (called from reference src/networks/ebn/evaluation/evaluate_node.jl:24,83).
 #pragma once

@@ -3,19 +3,19 @@
 // (reference call sites src/networks/ebn/evaluation/evaluate_node.jl:24,83;
 // the marginals that reach it are listed in SURVEY.md F7 / rows 2 and 5).
 //
-// Random streams, layout v2: for scenario stream s and sample pair
+// Random streams, layout v3: for scenario stream s and sample pair
 // q = sample index >> 1 the word stream is
 //     W[4c .. 4c+3] = Philox4x32-10(counter = (q lo, q hi, s, c), key = seed)
 // and the inputs consume words in input order:
 //     Parameter                         0 words
 //     Uniform                           2 words  (one 32-bit uniform per sample)
-//     untruncated Normal / LogNormal    3 words  (Box-Muller across the pair:
-//                                       52-bit radius, 32-bit angle, 2 sign bits)
+//     untruncated Normal / LogNormal    2 words  (Box-Muller across the pair:
+//                                       42-bit radius, 20-bit angle, 2 sign bits; box_muller_front)
 // Bit placement: U52(lo, hi) = ((hi & 0xfffff) * 2^32 + lo + 0.5) * 2^-52,
 //                U32(w) = (rotl(w, 12) + 0.5) * 2^-32.
 //     inverse-CDF marginals             4 words  (one 52-bit uniform per sample)
 //     Gamma (Marsaglia-Tsang)           0 words  (own counters, see gamma_mt)
-// Under a Gaussian copula every random input takes 3 words (its Box-Muller pair).
+// Under a Gaussian copula every random input takes 2 words (its Box-Muller pair).
 #pragma once
 #include "../../include/ebncuda.h"
 #include "ebn_device.cuh"
@@ -90,7 +90,7 @@ __device__ __forceinline__ bool gamma_attempt(double dd, double cc, uint32_t qlo
                                               uint32_t k1, const FastMathSmem& sm, double& v) {
   const Philox4 w = philox4x32_10(qlo, qhi, stream, slot, k0, k1);
   double z, z_unused;
-  box_muller_words(w.w0, w.w1, w.w2, sm, z, z_unused);
+  box_muller_words(w.w0, w.w1, sm, z, z_unused);
   const double t1 = fma(cc, z, 1.0);
   v = t1 * t1 * t1;
   const double u = u32w(w.w3);
@@ -172,7 +172,7 @@ __device__ __forceinline__ InState draw_front(const WS& ws, const FastMathSmem& 
     st.w0 = ws.template w<0>();
     st.w1 = ws.template w<1>();
   } else if (KIND == DK_NORMAL_BM || KIND == DK_LOGNORMAL_BM) {
-    st.bm = box_muller_front(ws.template w<0>(), ws.template w<1>(), ws.template w<2>(), sm);
+    st.bm = box_muller_front(ws.template w<0>(), ws.template w<1>(), sm);
   } else if (KIND != DK_CONST && KIND != DK_GAMMA_MT) {
     st.w0 = ws.template w<0>();
     st.w1 = ws.template w<1>();
@@ -248,7 +248,7 @@ __device__ __forceinline__ double phi_clamped(double z) {
 }
 
 // Gaussian copula (UQ.jl JointDistribution + GaussianCopula): eps ~ N(0,I) by
-// Box-Muller (3 words per random input, in.woff), z = L*eps, then per marginal
+// Box-Muller (2 words per random input, in.woff), z = L*eps, then per marginal
 // x = a + b*z for the normal family and x = Q(Phi(z)) otherwise. L is row-major
 // lower-triangular [d*d].
 static __device__ __noinline__ void draw_pair_copula(const DevInput* plan, const double* L, int d,
@@ -263,8 +263,8 @@ static __device__ __noinline__ void draw_pair_copula(const DevInput* plan, const
     e1[j] = 0.0;
     if (plan[j].kind != DK_CONST) {
       DynWords ws{&pc, &cache, &cached_call, plan[j].woff};
-      const uint32_t a = ws.at(0), b = ws.at(1), c = ws.at(2);
-      box_muller_words(a, b, c, sm, e0[j], e1[j]);
+      const uint32_t a = ws.at(0), b = ws.at(1);
+      box_muller_words(a, b, sm, e0[j], e1[j]);
     }
   }
   for (int j = 0; j < d; ++j) {

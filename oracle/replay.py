@@ -1,7 +1,7 @@
 """NumPy twin of the device sampler (test infrastructure, see oracle/__init__.py).
 
 Restates, independently of the CUDA sources, the stream layout of DESIGN.md
-("Random streams, layout v2") so that the uniforms the GPU consumed can be
+("Random streams, layout v3") so that the uniforms the GPU consumed can be
 regenerated on the CPU:
 
     key     = (seed & 0xffffffff, seed >> 32)
@@ -9,19 +9,21 @@ regenerated on the CPU:
     W[4c .. 4c+3] = Philox4x32-10(counter = (pair lo, pair hi, stream id, c), key)
 
     inputs consume words of W in input order:
-      Parameter 0 | Uniform 2 | untruncated Normal/LogNormal 3 | Gamma 0 | other marginals 4
+      Parameter 0 | Uniform 2 | untruncated Normal/LogNormal 2 | Gamma 0 | other marginals 4
     U52(lo, hi) = ((((hi & 0xfffff) << 32) | lo) + 0.5) * 2**-52    U32(w) = (rotl(w, 12) + 0.5) * 2**-32
 
     Uniform            : sample 2q uses U32(W[o]), sample 2q+1 uses U32(W[o+1])
     inverse-CDF kinds  : sample 2q uses U52(W[o], W[o+1]), sample 2q+1 uses U52(W[o+2], W[o+3])
-    (Log)Normal        : Box-Muller across the pair: R = sqrt(-2 ln U52(W[o], W[o+1])),
-                         phi = (pi/2) * U32(W[o+2]);  z(2q) = s0 R sin(phi), z(2q+1) = s1 R cos(phi),
-                         s0 = -1 if W[o+1] bit 31, s1 = -1 if W[o+1] bit 30
+    (Log)Normal        : Box-Muller across the pair from 64 bits (w0, w1) = (W[o], W[o+1]):
+                         R = sqrt(-2 ln u), u = (M + 1/2) 2^-42, M = rotl(w0, 12) * 2^10 + (w1 & 0x3ff);
+                         phi = (pi/2) (A + 1/2) 2^-20, A = (w1 >> 10) & 0xfffff;
+                         z(2q) = s0 R sin(phi), z(2q+1) = s1 R cos(phi),
+                         s0 = -1 if w1 bit 31, s1 = -1 if w1 bit 30
     Gamma (Marsaglia-Tsang): attempt t of sample e of input j is the Philox call with counter
                          word 3 = 0x80000000 | j << 16 | e << 15 | t: normal = first Box-Muller
-                         output of (w0, w1, w2), acceptance uniform U32(w3); the shape < 1 boost
+                         output of (w0, w1), acceptance uniform U32(w3); the shape < 1 boost
                          uniform is U52(w0, w1) of call t = 0x7fff
-    Gaussian copula    : every random input takes 3 words (its Box-Muller pair), z = L eps
+    Gaussian copula    : every random input takes 2 words (its Box-Muller pair), z = L eps
 
 Philox4x32-10 itself is pinned by the Random123 known-answer vectors in
 tests/test_oracle.py.
@@ -90,9 +92,13 @@ class _Words:
         return self.calls[c][k & 3]
 
 
-def _box_muller(w0, w1, w2):
-    R = np.sqrt(-2.0 * np.log(_u52(w0, w1)))
-    phi = (np.pi / 2) * _u32(w2)
+def _box_muller(w0, w1):
+    rot = ((w0 << np.uint64(12)) & _MASK) | (w0 >> np.uint64(20))  # rotate left by 12
+    M = (rot << np.uint64(10)) | (w1 & np.uint64(0x3FF))             # 42 bits
+    u = (M.astype(np.float64) + 0.5) * 2.0**-42
+    A = (w1 >> np.uint64(10)) & np.uint64(0xFFFFF)                   # 20 bits
+    R = np.sqrt(-2.0 * np.log(u))
+    phi = (np.pi / 2) * ((A.astype(np.float64) + 0.5) * 2.0**-20)
     s0 = np.where(w1 & np.uint64(0x80000000), -1.0, 1.0)
     s1 = np.where(w1 & np.uint64(0x40000000), -1.0, 1.0)
     return s0 * R * np.sin(phi), s1 * R * np.cos(phi)
@@ -106,7 +112,7 @@ def words_of(inp) -> int:
     if kind == IN_UNIFORM:
         return 2
     if kind in (IN_NORMAL, IN_LOGNORMAL) and not trunc:
-        return 3
+        return 2
     return 4
 
 
@@ -120,7 +126,7 @@ def _gamma_mt(pairs, e: int, shape: float, scale: float, stream: int, j: int, se
     t = 0
     while len(todo):
         w0, w1, w2, w3 = _call(pairs[todo], stream, base | t, seed)
-        z, _ = _box_muller(w0, w1, w2)
+        z, _ = _box_muller(w0, w1)
         t1 = 1.0 + cc * z
         v = t1 * t1 * t1
         u = _u32(w3)
@@ -211,8 +217,8 @@ def sample_matrix(inputs_row, stream: int, seed: int, first: int, n: int, tables
             a, b = max(p[0], lo), min(p[1], hi)
             u = np.where(odd, _u32(W[off + 1])[inv], _u32(W[off])[inv])
             X[:, j] = a + u * (b - a)
-        elif nw == 3:
-            z0, z1 = _box_muller(W[off], W[off + 1], W[off + 2])
+        elif kind in (IN_NORMAL, IN_LOGNORMAL) and nw == 2:
+            z0, z1 = _box_muller(W[off], W[off + 1])
             v = p[0] + p[1] * np.where(odd, z1[inv], z0[inv])
             X[:, j] = np.exp(v) if kind == IN_LOGNORMAL else v
         elif kind == IN_GAMMA:
@@ -228,7 +234,7 @@ def sample_matrix(inputs_row, stream: int, seed: int, first: int, n: int, tables
 
 
 def copula_sample_matrix(inputs_row, L, stream: int, seed: int, first: int, n: int, tables=None):
-    """Gaussian-copula variant: eps by Box-Muller per random input (3 words each), z = L eps,
+    """Gaussian-copula variant: eps by Box-Muller per random input (2 words each), z = L eps,
     x = a + b z for the (log)normal family, x = Q(Phi(z)) otherwise."""
     d = len(inputs_row)
     L = np.asarray(L, dtype=np.float64).reshape(d, d)
@@ -239,9 +245,9 @@ def copula_sample_matrix(inputs_row, L, stream: int, seed: int, first: int, n: i
     for j in range(d):
         if int(inputs_row[j]["kind"]) == IN_PARAM:
             continue
-        z0, z1 = _box_muller(W[off], W[off + 1], W[off + 2])
+        z0, z1 = _box_muller(W[off], W[off + 1])
         eps[:, j] = np.where(odd, z1[inv], z0[inv])
-        off += 3
+        off += 2
     Z = eps @ L.T
     X = np.empty((n, d))
     for j in range(d):

@@ -55,7 +55,7 @@ def main():
     blocks = {}
     for first in (0, 7, 2**33 + 5):
         blocks[f"first_{first}"] = replay.sample_matrix(inputs[0], 3, seed, first, 64, tables=TABLE)
-    np.savez_compressed(os.path.join(HERE, "stream_v2.npz"), inputs=inputs, table=TABLE, seed=np.uint64(seed),
+    np.savez_compressed(os.path.join(HERE, "stream_v3.npz"), inputs=inputs, table=TABLE, seed=np.uint64(seed),
                         stream=np.uint32(3), **blocks)
     print("vehicle count", cv, "straub count", cs)
 

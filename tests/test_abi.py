@@ -77,7 +77,7 @@ def test_partition_is_host_logic_and_covers_every_pair_once():
             assert tot == ips * job.S
             pairs = ((off + n + 1) >> 1) - (off >> 1)
             assert (ips - 1) * ppi < pairs <= ips * ppi and base == off >> 1
-            assert ppi % 256 == 0
+            assert ppi % 128 == 0   # a multiple of the block size (EBN_THREADS)
 
 
 def test_partition_validates_jobs_without_a_gpu():

@@ -36,7 +36,7 @@ def test_golden_limit_states():
 
 
 def test_golden_stream_layout():
-    z = np.load(os.path.join(GOLD, "stream_v2.npz"))
+    z = np.load(os.path.join(GOLD, "stream_v3.npz"))
     inputs = z["inputs"].view(ocpu.INPUT_DTYPE).reshape(1, -1)
     for first in (0, 7, 2**33 + 5):
         X = replay.sample_matrix(inputs[0], int(z["stream"]), int(z["seed"]), first, 64, tables=z["table"])
