@@ -354,6 +354,70 @@ function EnhancedBayesianNetworks._evaluate_node(net::EnhancedBayesianNetwork,
     return DiscreteNode(node.name, cpt, node.parameters, info)
 end
 
+# ---- ContinuousFunctionalNode: histogram instead of a KDE over n outputs ---------------------------
+
+"ebn_hist_batch for all scenarios: (counts[S, nedges+1], sum[S], sumsq[S]); first/last column = under/overflow."
+function hist_batch(model::CudaModel, scenario_inputs::Vector{<:Vector}, sim::CudaMonteCarlo, edges::Vector{Float64};
+    hidden::Vector{EbnInput}=EbnInput[])
+    M, S, d = input_matrix(scenario_inputs, model.args, hidden)
+    consts = model.consts
+    nb = length(edges) + 1
+    counts = zeros(Int64, nb, S)            # column-major: scenario-major rows of the C layout
+    s1 = zeros(Float64, S)
+    s2 = zeros(Float64, S)
+    GC.@preserve M consts begin
+        job = Ref(EbnJob(EBN_LS[model.limit_state], length(consts), pointer(consts), S, d, pointer(M), sim.n,
+            sim.seed, sim.strict ? 1 : 0, 0, C_NULL, C_NULL, C_NULL, 0, 0, 0, 1))
+        check(ccall((:ebn_hist_batch, LIB[]), Cint,
+            (Ref{EbnJob}, Ptr{Float64}, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+            job, edges, length(edges), counts, s1, s2))
+    end
+    return permutedims(counts), s1, s2
+end
+
+"Piecewise-uniform distribution of a histogram: what stands where the reference puts `EmpiricalDistribution(y)`."
+function histogram_distribution(edges::Vector{Float64}, inner_counts::Vector{Int64})
+    keep = findall(>(0), inner_counts)
+    w = inner_counts[keep] ./ sum(inner_counts[keep])
+    return MixtureModel([Uniform(edges[i], edges[i+1]) for i in keep], w)
+end
+
+# Like the Python mirror (uq.output_histograms): a pilot of <= 65536 samples per scenario gives the
+# output range from the moments, then ONE call histograms every scenario on a shared grid.
+function EnhancedBayesianNetworks._evaluate_node(net::EnhancedBayesianNetwork,
+    node::ContinuousFunctionalNode, collect_samples::Bool, sim::CudaMonteCarlo)
+    all(EnhancedBayesianNetworks.isprecise.(parents(net, node)[3])) ||
+        error("node $(node.name) is a continuousfunctionalnode with at least one parent with Interval or p-boxes in its distributions. No method for extracting failure probability p-box have been implemented yet")
+    ancestors = discrete_ancestors(net, node)
+    combos = sort(vec(collect(Iterators.product(states.(ancestors)...))))
+    owner(s) = filter(n -> s ∈ states(n), filter(x -> isa(x, DiscreteNode), net.nodes))[1].name
+    evidences = map(c -> Evidence(owner(s) => s for s in c), combos)
+    if isempty(combos[1])
+        cpt = ContinuousConditionalProbabilityTable{PreciseContinuousInput}()
+        discretization = ExactDiscretization(node.discretization.intervals)
+    else
+        cpt = ContinuousConditionalProbabilityTable{PreciseContinuousInput}([i.name for i in ancestors])
+        discretization = node.discretization
+    end
+    scen = map(ev -> mapreduce(p -> _uq_inputs(p, ev), vcat, parents(net, node)[3]; init=UQInput[]), evidences)
+    model = node.models[end]::CudaModel
+    hid = hidden_inputs(model)
+    pilot = CudaMonteCarlo(min(sim.n, 1 << 16), sim.seed, sim.strict, nothing)
+    _, s1, s2 = hist_batch(model, scen, pilot, [0.0]; hidden=hid)          # moments only
+    μ = s1 ./ pilot.n
+    σ = sqrt.(max.(s2 ./ pilot.n .- μ .^ 2, 0.0))
+    lo, hi = minimum(μ .- 8 .* σ), maximum(μ .+ 8 .* σ)
+    hi > lo || ((lo, hi) = (lo - 1.0, hi + 1.0))
+    edges = collect(range(lo, hi; length=1025))
+    counts, _, _ = hist_batch(model, scen, sim, edges; hidden=hid)         # ONE call, all scenarios
+    info = Dict{Vector{Symbol},Dict}()
+    for (s, ev) in enumerate(evidences)
+        cpt[ev] = histogram_distribution(edges, counts[s, 2:end-1])
+        collect_samples && (info[collect(values(ev))] = Dict(:samples => DataFrame()))
+    end
+    return ContinuousNode(node.name, cpt, discretization, info)
+end
+
 # dispatch hook: called from _evaluate_node(net, node::DiscreteFunctionalNode, collect_samples)
 # when `node.simulation isa CudaMonteCarlo` (one-line patch in evaluate_node.jl, see INTEGRATION.md)
 
