@@ -352,6 +352,38 @@ def test_tiny_and_ragged_sizes(ebn):
         assert X.shape == (n, 6)
 
 
+def test_many_scenarios_and_far_offsets(ebn):
+    """Maximum-size ends of the domain: 100 000 scenarios in one call (a scenario then owns a single
+    work item), and sample indices beyond 2^40 (the pair index fills both Philox counter words)."""
+    from ebn_b200 import workloads as W
+    S, n = 100_000, 999
+    rng = np.random.default_rng(9)
+    rows = [W._veh_row(float(a), float(b), -INF, INF) for a, b in zip(rng.uniform(0.1, 1.0, S), rng.uniform(0.2, 0.6, S))]
+    big = ebn.Job(ebn._lib.LS_VEHICLE_SUSPENSION, W.vehicle_consts(), ebn.make_inputs(rows), n=n, seed=77, strict=True)
+    cnt = ebn.pf_batch(big)[0]
+    assert cnt.shape == (S,) and ebn.last_stats()["specialised"] == 1
+    pick = [0, 1, 4097, 65_535, 65_536, S - 1]
+    sub = ebn.Job(big.limit_state, big.consts, big.inputs[pick], n=n, seed=77, strict=True,
+                  stream_id=np.array(pick, dtype=np.uint32))
+    assert np.array_equal(ebn.pf_batch(sub)[0], cnt[pick])
+    for s in (4097, S - 1):
+        X = ebn.sample_matrix(big, s, 0, n)
+        assert int(cnt[s]) == ocpu.eval_matrix(ocpu.LS_VEHICLE, big.consts, X)
+    # far offset: [2^40 + 3, 2^40 + 3 + n) in one piece equals two resumed pieces, and the oracle on the replay
+    off = 2**40 + 3
+    job = W.w1_vehicle(n=5001, strict=True)
+    job.sample_offset = off
+    whole = ebn.pf_batch(job)[0]
+    a = W.w1_vehicle(n=2000, strict=True)
+    a.sample_offset = off
+    b = W.w1_vehicle(n=3001, strict=True)
+    b.sample_offset = off + 2000
+    assert np.array_equal(whole, ebn.pf_batch(a)[0] + ebn.pf_batch(b)[0])
+    X = ebn.sample_matrix(job, 4, off, 5001)
+    assert int(whole[4]) == ocpu.eval_matrix(ocpu.LS_VEHICLE, job.consts, X)
+    assert np.allclose(X, replay.sample_matrix(job.inputs[4], 4, job.seed, off, 5001), rtol=1e-11, atol=0)
+
+
 # ---------------------------------------------------------------------------
 # 5. independent-RNG estimates within 3 standard errors of the oracle
 # ---------------------------------------------------------------------------
