@@ -19,33 +19,35 @@ namespace ebn {
 #include "ebn_fastmath_tables.inc"
 
 struct FastMathConst {
-  double sinc[7];
-  double cosc[8];
   double ln1p[5];   // -1/2, 1/3, -1/4, 1/5, -1/6  (negated for -ln)
   double ln2;
   double expc[4];   // 1/2, 1/6, 1/24, 1/120
   double inv_ln2_64, ln2_64_hi, ln2_64_lo;
+  double sind[3];   // sin(delta) = t*(d0 + d1 t^2 + d2 t^4), delta = (pi/2) t inside a table cell
+  double cosd[2];   // cos(delta) - 1 = t^2*(e0 + e1 t^2)
 };
 __constant__ FastMathConst kFm = {
-    {EBN_SIN_COEFS},
-    {EBN_COS_COEFS},
     {0.5, -0.33333333333333331483, 0.25, -0.2000000000000000111, 0.16666666666666665741},
     0.69314718055994528623,
     {0.5, 0.16666666666666665741, 0.041666666666666664354, 0.0083333333333333332177},
     92.332482616893656877,          // 64/ln2
     0x1.62e42fef00000p-7,           // ln2/64, high 33 bits (n * hi is exact for |n| < 2^20)
     0x1.473de6af278edp-40,          // ln2/64 - high part
+    {EBN_SIND_COEFS},
+    {EBN_COSD_COEFS},
 };
 
 // Shared-memory copy of the log table (per-lane random index: shared memory,
 // not the constant cache, which serialises divergent addresses).
 struct FastMathSmem {
   double2 logtab[128];
+  double2 sctab[128];   // sqrt(2)*(sin, cos) at the centres of 128 cells of the first quadrant
   double exptab[64];
 };
 
 __device__ __forceinline__ void fastmath_init(FastMathSmem& sm, int tid, int nthreads) {
   for (int i = tid; i < 128; i += nthreads) sm.logtab[i] = kLogTab[i];
+  for (int i = tid; i < 128; i += nthreads) sm.sctab[i] = kSinCosTab[i];
   for (int i = tid; i < 64; i += nthreads) sm.exptab[i] = kExpTab[i];
 }
 
@@ -129,21 +131,6 @@ __device__ __forceinline__ double sqrt_pos(double t) {
   return fma(a * e, c, a);
 }
 
-// (cos a + sin a, cos a - sin a) for a = (pi/2)*v, v in [-1/2, 1/2):
-// sqrt(2)*(sin, cos) of the first-quadrant angle (pi/2)*(v + 1/2).
-__device__ __forceinline__ void sincos_quadrant(double v, double& cps, double& cms) {
-  const double w = v * v;
-  double s = fma(w, kFm.sinc[6], kFm.sinc[5]);
-  double c = fma(w, kFm.cosc[7], kFm.cosc[6]);
-#pragma unroll
-  for (int i = 4; i >= 0; --i) s = fma(w, s, kFm.sinc[i]);
-#pragma unroll
-  for (int i = 5; i >= 0; --i) c = fma(w, c, kFm.cosc[i]);
-  s *= v;
-  cps = c + s;
-  cms = c - s;
-}
-
 // Box-Muller for the sample pair from two 32-bit words (64 bits = 42 + 20 + 2):
 //   radius  u = (M + 1/2) 2^-42 in (0,1), M = 42 bits: all of w0 (low 20 bits most significant)
 //           followed by bits 0..9 of w1; reaches 7.6 sigma, P(lost tail) = 2^-43 per draw
@@ -179,20 +166,28 @@ __device__ __forceinline__ BmFront box_muller_front(uint32_t w0, uint32_t w1, co
   return f;
 }
 
-__device__ __forceinline__ void box_muller_back(const BmFront& f, double& z0, double& z1) {
+__device__ __forceinline__ void box_muller_back(const BmFront& f, const FastMathSmem& sm, double& z0, double& z1) {
   const double r = f.r;
   double p = fma(r, kFm.ln1p[4], kFm.ln1p[3]);
   p = fma(r, p, kFm.ln1p[2]);
   p = fma(r, p, kFm.ln1p[1]);
   p = fma(r, p, kFm.ln1p[0]);
   const double t = fma(r * r, p, f.base - r);          // -ln u
-  // angle bits stay where they are (bits 10..29 of the low mantissa word): d = 1 + A 2^-42,
-  // v = (A + 1/2) 2^-20 - 1/2 = d 2^22 - (2^22 + 1/2 - 2^-21), exact, in [-1/2, 1/2)
-  const double v = fma(__hiloint2double(0x3FF00000, (int)(f.w1 & 0x3FFFFC00u)), 4194304.0,
-                       -(4194304.5 - 0x1p-21));
+  // Angle phi = (pi/2)(A + 1/2) 2^-20: the top 7 bits of A pick one of 128 cells whose centre
+  // carries sqrt(2)*(sin, cos) in shared memory; the low 13 bits give the offset inside the cell,
+  // delta = (pi/2) t with |t| <= 2^-8, short enough for two 2-3 term polynomials (11 fp64
+  // operations instead of the 20 of a full-quadrant polynomial pair). The offset bits stay where
+  // they are (bits 10..22 of the low mantissa word): d = 1 + r 2^-42,
+  // t = (r + 1/2) 2^-20 - 2^-8 = d 2^22 - (2^22 + 2^-8 - 2^-21), exact.
+  const double2 sc = sm.sctab[(f.w1 >> 23) & 0x7Fu];
+  const double td = fma(__hiloint2double(0x3FF00000, (int)(f.w1 & 0x007FFC00u)), 4194304.0,
+                        -(4194304.0 + 0x1p-8 - 0x1p-21));
+  const double w = td * td;
+  const double sd = td * fma(w, fma(w, kFm.sind[2], kFm.sind[1]), kFm.sind[0]);  // sin(delta)
+  const double cm = w * fma(w, kFm.cosd[1], kFm.cosd[0]);                        // cos(delta) - 1
+  const double cps = fma(sc.y, sd, fma(sc.x, cm, sc.x));    // sqrt(2) sin(phi)
+  const double cms = fma(-sc.x, sd, fma(sc.y, cm, sc.y));   // sqrt(2) cos(phi)
   const double rr = sqrt_pos(t);                        // sqrt(-ln u) = R / sqrt(2)
-  double cps, cms;
-  sincos_quadrant(v, cps, cms);
   const double a = rr * cps;  // R*sin(phi)
   const double b = rr * cms;  // R*cos(phi)
   z0 = __hiloint2double(__double2hiint(a) ^ (int)(f.w1 & 0x80000000u), __double2loint(a));
@@ -201,7 +196,7 @@ __device__ __forceinline__ void box_muller_back(const BmFront& f, double& z0, do
 
 __device__ __forceinline__ void box_muller_words(uint32_t w0, uint32_t w1, const FastMathSmem& sm,
                                                  double& z0, double& z1) {
-  box_muller_back(box_muller_front(w0, w1, sm), z0, z1);
+  box_muller_back(box_muller_front(w0, w1, sm), sm, z0, z1);
 }
 
 }  // namespace ebn

@@ -196,7 +196,7 @@ __device__ __forceinline__ void draw_back(const DevInput& in, const InState& st,
     x1 = fma(u32w_raw(st.w1), in.b, in.c);
   } else if (KIND == DK_NORMAL_BM || KIND == DK_LOGNORMAL_BM) {
     double z0, z1;
-    box_muller_back(st.bm, z0, z1);
+    box_muller_back(st.bm, sm, z0, z1);
     x0 = fma(z0, in.b, in.a);
     x1 = fma(z1, in.b, in.a);
     if (KIND == DK_LOGNORMAL_BM) {
