@@ -7,8 +7,8 @@ to describe itself as an `ebn_input_t` row for the C ABI. Sampling never happens
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
-from typing import List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Sequence, Tuple
 
 import numpy as np
 from scipy import special, stats

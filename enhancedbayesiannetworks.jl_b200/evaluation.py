@@ -25,7 +25,7 @@ from . import uq
 from .distributions import EmpiricalDistribution, Exponential, ProbabilityBox, Uniform
 from .network import (BayesianNetwork, CredalNetwork, EnhancedBayesianNetwork, _add_node, _is_cyclic_dfs,
                       _remove_node, add_child, children, discrete_ancestors, order, parents)
-from .nodes import (FORM, PI, AbstractMonteCarlo, ApproximatedDiscretization, ContinuousConditionalProbabilityTable,
+from .nodes import (FORM, PI, AbstractMonteCarlo, ContinuousConditionalProbabilityTable,
                     ContinuousFunctionalNode, ContinuousNode, CudaDoubleLoop, CudaRandomSlicing,
                     DiscreteConditionalProbabilityTable, DiscreteFunctionalNode, DiscreteNode, ExactDiscretization,
                     FunctionalNode, UnamedProbabilityBox, _truncate, interval_symbol, isprecise)

@@ -17,8 +17,7 @@ from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 
-from .nodes import (AbstractContinuousNode, AbstractDiscreteNode, ContinuousNode, DiscreteNode,
-                    FunctionalNode, PI)
+from .nodes import AbstractContinuousNode, AbstractDiscreteNode, DiscreteNode, FunctionalNode
 
 
 def _is_cyclic_dfs(adj: np.ndarray) -> bool:

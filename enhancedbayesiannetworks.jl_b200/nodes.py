@@ -16,10 +16,10 @@ from __future__ import annotations
 
 import math
 import warnings
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
-from .distributions import (Distribution, Interval, Parameter, ProbabilityBox, RandomVariable, Truncated)
+from .distributions import (Interval, Parameter, ProbabilityBox, RandomVariable, Truncated)
 
 PI = "Π"
 Evidence = Dict[str, str]

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib as L
 from .distributions import (INF, Gamma, Interval, JointDistribution, NeedsTable, Normal, Parameter,
-                            ProbabilityBox, RandomVariable, Truncated, table_for)
+                            ProbabilityBox, RandomVariable, table_for)
 from . import expr as _expr
 from .nodes import FORM, Catalogue, CudaDoubleLoop, CudaMonteCarlo, CudaRandomSlicing, Expression, Model, Poly
 

@@ -4,7 +4,6 @@ import math
 import os
 
 import numpy as np
-import pytest
 from scipy import special, stats
 
 from oracle import cpu as ocpu
