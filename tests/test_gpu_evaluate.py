@@ -419,6 +419,23 @@ def test_networks_with_models_given_as_text(E):
         assert np.allclose(pfs[0], pfs[1], atol=1e-3)
 
 
+def test_examples_run(E):
+    """examples/ mirror the reference's two demos end to end."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mods = {}
+    for name in ("vehicle_suspension", "straub_example"):
+        spec = importlib.util.spec_from_file_location(f"example_{name}", os.path.join(root, "examples", f"{name}.py"))
+        mods[name] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[name])
+    e = mods["vehicle_suspension"].main(500_000)
+    pf = {(r["A"], r["b₀"], r["V_d"]): r["Π"] for r in e.cpt.data if r["E"] == "E_fail"}
+    assert len(pf) == 20 and abs(pf[("offroad", "normal_load", "[11.5, 12.0]")] - 0.7373) < 0.005
+    pi = mods["straub_example"].main(10**6)
+    assert np.allclose(pi, [0.026129, 0.973871], atol=0.01)
+
+
 def test_vehicle_suspension_imprecise(E):
     """BASELINE config 4 (demo/vehicle_suspension_imprecise.jl): V an interval (7, 13), discretised into
     interval bins; DoubleLoop sweeps V over each bin. pf is monotone in V, so the bounds are the pf at
