@@ -483,19 +483,44 @@ def _poly_monotone(models, performance, name: str) -> bool:
     return True
 
 
+def _monotone_on_replay(models, performance, inputs, dims, k: int, seed: int, rows: int = 2048, grid: int = 9) -> bool:
+    """Numerical check for limit states that are not polynomial programs: is g monotone, in ONE
+    direction for all samples, in imprecise dimension k of this scenario? The other imprecise
+    dimensions sit at their midpoints; the scenario is replayed on the device at `grid` values of
+    dimension k with common random numbers (same stream, same seed), `rows` samples each.
+    A sufficient condition checked on a sample, not a proof: stated in `random_slicing`."""
+    mid = np.array([0.5 * (d[2] + d[3]) for d in dims])
+    G = []
+    for v in np.linspace(dims[k][2], dims[k][3], grid):
+        x = mid.copy()
+        x[k] = v
+        real = _realise(inputs, dims, x)
+        low = lower(models, performance, input_names(real))
+        job = build_job(low, [real], CudaMonteCarlo(rows, seed, True))
+        G.append(L.sample_matrix(job, 0, 0, rows, want_g=True)[1])
+    D = np.diff(np.array(G), axis=0)
+    D = D[:, np.all(np.isfinite(D), axis=0)]
+    return bool(np.all(D >= 0.0) or np.all(D <= 0.0))
+
+
 def random_slicing(models, performance, scenario_inputs, sim: CudaRandomSlicing):
     """UQ.jl RandomSlicing (A6) for limit states monotone in each imprecise input: the per-sample
     extremes over the input boxes are then attained at the box vertices, so
     pf_lb / pf_ub are the extreme vertex probabilities (evaluated with common random numbers).
     Returns [((lb, ub), (std_lb, Samples), (std_ub, Samples))] per scenario."""
     inner = sim.lb
-    for inputs in scenario_inputs:
+    dims_per_s = [_imprecise_dims(inp) for inp in scenario_inputs]
+    for inputs, dims in zip(scenario_inputs, dims_per_s):
         for i in inputs:
-            if _is_imprecise(i) and not _poly_monotone(models, performance, i.name):
-                raise UnsupportedModel(f"RandomSlicing on the device needs a limit state monotone in '{i.name}'")
             if isinstance(i, ProbabilityBox) and len(i.parameters) > 1:
                 raise UnsupportedModel("RandomSlicing on the device supports p-boxes with one interval parameter")
-    dims_per_s = [_imprecise_dims(inp) for inp in scenario_inputs]
+        for k, d in enumerate(dims):
+            name = inputs[d[0]].name
+            # polynomial programs are checked syntactically; anything else (formulas, catalogue
+            # functors) numerically on replayed samples (2048 rows x 9 values per dimension)
+            if not (_poly_monotone(models, performance, name)
+                    or _monotone_on_replay(models, performance, inputs, dims, k, inner.seed)):
+                raise UnsupportedModel(f"RandomSlicing on the device needs a limit state monotone in '{name}'")
     cands = [[np.array(v) for v in itertools.product(*[(d[2], d[3]) for d in dims])] for dims in dims_per_s]
     pf = _eval_candidates(models, performance, scenario_inputs, dims_per_s, cands, inner)
     out = []

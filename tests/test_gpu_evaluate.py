@@ -221,6 +221,26 @@ def test_random_slicing_and_child_intervals(E):
           ("d2", "a1"): (ndtr(0.1), ndtr(0.3)), ("d2", "a2"): (ndtr(0.7), ndtr(0.8))}
     for (dd, aa), w in ex.items():
         assert np.allclose(out.cpt[{"D": dd, "A": aa, "F1": "F1_fail"}], w, atol=0.006)
+    # the same node with its closures as text: monotonicity is then checked numerically on replayed
+    # samples; a limit state that is not monotone in the interval input is refused
+    fe = E.DiscreteFunctionalNode("F1", [E.Model(E.Expression("df.D .+ df.C1 .+ df.B"), "C2")], E.Expression("2 .- df.C2"), sim)
+    net = E.EnhancedBayesianNetwork([a, b, d, c1, fe])
+    E.add_child(net, a, c1)
+    for par in (b, d, c1):
+        E.add_child(net, par, fe)
+    E.order(net)
+    oute = ev._evaluate_node(net, fe)
+    for (dd, aa), w in ex.items():
+        assert np.allclose(oute.cpt[{"D": dd, "A": aa, "F1": "F1_fail"}], w, atol=0.006)
+    fbad = E.DiscreteFunctionalNode("F1", [E.Model(E.Expression("df.D .+ (df.C1 .- 0.2) .^ 2 .+ df.B"), "C2")],
+                                    E.Expression("2 .- df.C2"), sim)
+    net = E.EnhancedBayesianNetwork([a, b, d, c1, fbad])
+    E.add_child(net, a, c1)
+    for par in (b, d, c1):
+        E.add_child(net, par, fbad)
+    E.order(net)
+    with pytest.raises(E.UnsupportedModel, match="monotone"):
+        ev._evaluate_node(net, fbad)
 
 
 def test_evaluate_net_chain_and_error_messages(E):
