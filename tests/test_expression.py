@@ -2,6 +2,7 @@
 generator behind the C ABI (no GPU needed), run-time compilation itself (NVRTC compiles without a
 device), and the oracle's two stack machines against the hand-written limit states."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -180,3 +181,19 @@ def test_lowering_of_expression_models():
         lower([Model(Expression("df.Z"), "C")], "C", ["A"])
     with pytest.raises(UnsupportedModel, match="Expression"):
         lower([Model(lambda df: df, "C")], "C", ["A"])
+
+
+def test_kernel_cache_on_disk_is_opt_in(tmp_path):
+    """EBN_JIT_CACHE=dir persists compiled kernels across processes; without it nothing is written."""
+    import subprocess
+    import sys
+    if not L.jit_available():
+        pytest.skip("libnvrtc not loadable here")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from ebn_b200 import workloads as W, _lib as L\n"
+            "j = W.w1_vehicle(n=1000); j.inputs[:, 5]['hi'] = 90.0; j.jit_plan = True\n"
+            "assert L.jit_compile(j, 0) > 10000; print(L.last_stats()['jit_compiles'])\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, EBN_JIT_CACHE=str(tmp_path))
+    runs = [subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True) for _ in range(2)]
+    assert [r.stdout.strip() for r in runs] == ["1", "0"], [r.stderr[-300:] for r in runs]
+    assert len(list(tmp_path.iterdir())) == 1
