@@ -270,6 +270,21 @@ def main():
             },
             "pf_first_scenarios": [float(x) for x in pf[:5]],
         }
+        if world == 1 and args.workload == "w1" and not args.strict:
+            # reported separately, outside the timed region (north star: "FP32 where tolerated"): the same
+            # workload with the untruncated normals drawn through the fp32 Box-Muller (same random words)
+            job.fp32_sampling = True
+            step()
+            ms32 = 0.0
+            for _ in range(3):
+                flush.fill_(1)
+                _, pf32, st32 = step()
+                ms32 += st32["kernel_ms"]
+            job.fp32_sampling = False
+            line["fp32_sampling_variant"] = {
+                "value": total_samples * 3 / (ms32 * 1e-3), "unit": UNIT,
+                "max_abs_pf_diff_vs_fp64": float(np.max(np.abs(pf32 - pf))),
+                "note": "EBN_JOB_FP32_SAMPLING: sampling transform in fp32, limit state in fp64; not the headline"}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             v, dt, _ = cpu_reference_run(args.cpu_n, cores)

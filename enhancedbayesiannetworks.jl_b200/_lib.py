@@ -47,6 +47,7 @@ JOB_COPULA_SHARED = 1
 JOB_PARTIAL = 2
 JOB_JIT_PLAN = 4
 JOB_NO_JIT_PLAN = 8
+JOB_FP32_SAMPLING = 16
 
 ERROR_NAMES = {0: "EBN_OK", -1: "EBN_EINVAL", -2: "EBN_ELIMITSTATE", -3: "EBN_EMARGINAL",
                -4: "EBN_ECUDA", -5: "EBN_ENCCL", -6: "EBN_ENODEV", -7: "EBN_ENOMEM", -8: "EBN_ESTATE",
@@ -234,6 +235,7 @@ class Job:
     shard_world: int = 1
     partial: bool = False          # EBN_JOB_PARTIAL: this shard's counts only
     jit_plan: Optional[bool] = None  # True: EBN_JOB_JIT_PLAN, False: EBN_JOB_NO_JIT_PLAN, None: library decides
+    fp32_sampling: bool = False    # EBN_JOB_FP32_SAMPLING: untruncated normals through the fp32 Box-Muller
 
     def __post_init__(self):
         self.consts = np.ascontiguousarray(self.consts, dtype=np.float64).ravel()
@@ -270,6 +272,8 @@ class Job:
         j.flags = JOB_PARTIAL if self.partial else 0
         if self.jit_plan is not None:
             j.flags |= JOB_JIT_PLAN if self.jit_plan else JOB_NO_JIT_PLAN
+        if self.fp32_sampling:
+            j.flags |= JOB_FP32_SAMPLING
         if self.corr_chol is not None:
             j.corr_chol = self.corr_chol.ctypes.data
             if self.corr_chol.ndim == 2:

@@ -150,7 +150,7 @@ const double kInf = std::numeric_limits<double>::infinity();
 double norm_cdf(double z) { return 0.5 * erfc(-z * 0.70710678118654752440); }
 
 // Maps one ABI input to the device recipe. Returns EBN_OK or an error.
-int canonicalise(const ebn_input_t& in, bool copula, DevInput& o, int s, int j,
+int canonicalise(const ebn_input_t& in, bool copula, bool fp32, DevInput& o, int s, int j,
                  int64_t n_tables) {
   o = DevInput{};
   const double lo = in.lo, hi = in.hi;
@@ -188,7 +188,8 @@ int canonicalise(const ebn_input_t& in, bool copula, DevInput& o, int s, int j,
       o.a = mu;
       o.b = sd;
       if (!trunc) {
-        o.kind = logn ? DK_LOGNORMAL_BM : DK_NORMAL_BM;
+        o.kind = (fp32 && !copula) ? (logn ? DK_LOGNORMAL_BM32 : DK_NORMAL_BM32)
+                                   : (logn ? DK_LOGNORMAL_BM : DK_NORMAL_BM);
         o.c = 0.0;
         o.d = 1.0;
         return EBN_OK;
@@ -428,7 +429,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
   if (!job->inputs) return fail(EBN_EINVAL, "inputs is NULL");
   if (job->n_per_scenario < 1) return fail(EBN_EINVAL, "n_per_scenario must be >= 1");
   if (job->sample_offset < 0) return fail(EBN_EINVAL, "sample_offset must be >= 0");
-  if (job->flags & ~(EBN_JOB_COPULA_SHARED | EBN_JOB_PARTIAL | EBN_JOB_JIT_PLAN | EBN_JOB_NO_JIT_PLAN)) return fail(EBN_EINVAL, "unknown job flags 0x%x", job->flags);
+  if (job->flags & ~(EBN_JOB_COPULA_SHARED | EBN_JOB_PARTIAL | EBN_JOB_JIT_PLAN | EBN_JOB_NO_JIT_PLAN | EBN_JOB_FP32_SAMPLING)) return fail(EBN_EINVAL, "unknown job flags 0x%x", job->flags);
   int rc = check_limit_state(job->limit_state, job->consts, job->n_consts, job->n_inputs);
   if (rc) return rc;
   const int jw = job->shard_world <= 1 ? 1 : job->shard_world;
@@ -440,8 +441,8 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
   P.plan.resize((size_t)S * d);
   for (int s = 0; s < S; ++s)
     for (int j = 0; j < d; ++j) {
-      rc = canonicalise(job->inputs[(size_t)s * d + j], copula, P.plan[(size_t)s * d + j], s, j,
-                        job->n_tables);
+      rc = canonicalise(job->inputs[(size_t)s * d + j], copula, (job->flags & EBN_JOB_FP32_SAMPLING) != 0,
+                        P.plan[(size_t)s * d + j], s, j, job->n_tables);
       if (rc) return rc;
     }
   // word offsets in the pair's Philox stream (layout v3): inputs consume words in order;
@@ -470,8 +471,9 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
       }
     }
     P.plan_class = PLAN_COPULA;
-  } else if (const int which = static_plan_matches(job->limit_state, P.plan.data(), S, d)) {
-    P.plan_class = which == 1 ? PLAN_STATIC : PLAN_STATIC2;
+  } else {
+    const int which = static_plan_matches(job->limit_state, P.plan.data(), S, d);
+    if (which >= 0) P.plan_class = PLAN_STATIC0 + which;
   }
   // Run-time compilation: always for an expression limit state; for the others when no compiled-in
   // plan fits, every scenario has the same marginal kinds, and the job is large (or asks for it).
@@ -506,7 +508,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
       P.jit_spec.n_consts = job->n_consts;
       if (uniform && !(expr && never))
         for (int j = 0; j < d; ++j) P.jit_spec.kinds.push_back(P.plan[j].kind);
-      if (!P.jit_spec.kinds.empty() && !copula) P.plan_class = PLAN_STATIC;
+      if (!P.jit_spec.kinds.empty() && !copula) P.plan_class = PLAN_STATIC0;
     }
   }
   P.world = jw * (ndev_override > 0 ? ndev_override : (int)g.devs.size());
@@ -740,7 +742,7 @@ int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, i
   g.stats.samples = my_samples;
   g.stats.launches = (int)nd * (mode == 1 ? 2 : 1);
   g.stats.devices = (int)nd;
-  g.stats.specialised = P.plan_class == PLAN_STATIC || P.plan_class == PLAN_STATIC2 || !P.jit_spec.kinds.empty();
+  g.stats.specialised = P.plan_class >= PLAN_STATIC0 || !P.jit_spec.kinds.empty();
   g.stats.jit_compiles = P.jit_compiles;
   return EBN_OK;
 }

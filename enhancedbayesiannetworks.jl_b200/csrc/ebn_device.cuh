@@ -26,7 +26,9 @@ enum DevKind : int32_t {
   DK_EXP_AFFINE = 7,      // x = a - b*log1p(-(c + u*d))    (b carries sign*theta)
   DK_GAMMA_MT = 8,        // Marsaglia-Tsang, shape a, scale b (untruncated)
   DK_TABLE = 9,           // x = Q(c + u*d), Q linear on a uniform grid of npts points
-  DK_NKINDS = 10
+  DK_NORMAL_BM32 = 10,    // as DK_NORMAL_BM, the Box-Muller transform evaluated in fp32
+  DK_LOGNORMAL_BM32 = 11, // (EBN_JOB_FP32_SAMPLING; same words, z agrees to ~1e-6)
+  DK_NKINDS = 12
 };
 
 struct DevInput {
@@ -44,7 +46,7 @@ __host__ __device__
 constexpr int words_of_kind(int kind) {
   return kind == DK_CONST ? 0
        : kind == DK_UNIFORM ? 2
-       : (kind == DK_NORMAL_BM || kind == DK_LOGNORMAL_BM) ? 2
+       : (kind == DK_NORMAL_BM || kind == DK_LOGNORMAL_BM || kind == DK_NORMAL_BM32 || kind == DK_LOGNORMAL_BM32) ? 2
        : kind == DK_GAMMA_MT ? 0
        : 4;
 }

@@ -75,18 +75,16 @@ const LsVTable* ls_vtable(int limit_state) {
 
 int static_plan_matches(int limit_state, const DevInput* plan, int S, int d) {
   const LsVTable* v = ls_vtable(limit_state);
-  if (!v) return 0;
-  const int* kinds[2] = {v->static_kinds, v->static_kinds2};
-  const int n[2] = {v->n_static, v->n_static2};
-  for (int which = 0; which < 2; ++which) {
-    if (!kinds[which] || n[which] != d) continue;
+  if (!v) return -1;
+  for (int which = 0; which < v->n_plans; ++which) {
+    if (v->n_static[which] != d) continue;
     bool ok = true;
     for (int s = 0; s < S && ok; ++s)
       for (int j = 0; j < d; ++j)
-        if (plan[(int64_t)s * d + j].kind != kinds[which][j]) { ok = false; break; }
-    if (ok) return which + 1;
+        if (plan[(int64_t)s * d + j].kind != v->static_kinds[which][j]) { ok = false; break; }
+    if (ok) return which;
   }
-  return 0;
+  return -1;
 }
 
 cudaError_t moments_launch(const double* partial, int64_t local_items, int64_t items_per_scenario,

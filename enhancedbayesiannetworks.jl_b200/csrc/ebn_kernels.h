@@ -6,11 +6,14 @@
 
 namespace ebn {
 
-enum PlanClass { PLAN_DYNAMIC = 0, PLAN_STATIC = 1, PLAN_COPULA = 2, PLAN_STATIC2 = 3 };
+// PLAN_STATIC0 + i: the i-th compile-time plan of the limit state (or, for a run-time compiled kernel,
+// the job's own kinds)
+enum PlanClass { PLAN_DYNAMIC = 0, PLAN_COPULA = 1, PLAN_STATIC0 = 2 };
+constexpr int kMaxStaticPlans = 4;
 
 #ifndef __CUDACC_RTC__
 int threads_per_block();
-// 0: no compile-time plan matches every scenario; 1 / 2: the limit state's first / second plan does.
+// -1: no compile-time plan matches every scenario; i >= 0: the limit state's i-th plan does.
 int static_plan_matches(int limit_state, const DevInput* plan, int S, int d);
 
 // Launchers of one limit state (filled by its translation unit).
@@ -23,10 +26,9 @@ struct LsVTable {
   cudaError_t (*matrix)(int strict, const double* consts, int n_consts, const double* X, int64_t n,
                         int d, int64_t ld, unsigned long long* count, double* g_out, int blocks,
                         cudaStream_t st);
-  const int* static_kinds;  // compile-time sampling plan, if the limit state has one
-  int n_static;
-  const int* static_kinds2;  // an optional second one
-  int n_static2;
+  const int* static_kinds[kMaxStaticPlans];  // compile-time sampling plans of the limit state
+  int n_static[kMaxStaticPlans];
+  int n_plans;
 };
 const LsVTable* ls_vtable(int limit_state);
 

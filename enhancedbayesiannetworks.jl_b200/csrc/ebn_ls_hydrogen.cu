@@ -3,5 +3,5 @@
 
 namespace ebn {
 
-LsVTable vt_hydrogen() { return LsLaunch<HydrogenRadius, NoStaticPlan>::vtable(); }
+LsVTable vt_hydrogen() { return LsLaunch<HydrogenRadius>::vtable(); }
 }  // namespace ebn

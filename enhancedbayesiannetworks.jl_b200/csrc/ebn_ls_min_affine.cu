@@ -3,5 +3,5 @@
 
 namespace ebn {
 
-LsVTable vt_min_affine() { return LsLaunch<MinAffine, NoStaticPlan>::vtable(); }
+LsVTable vt_min_affine() { return LsLaunch<MinAffine>::vtable(); }
 }  // namespace ebn

@@ -3,5 +3,5 @@
 
 namespace ebn {
 
-LsVTable vt_polynomial() { return LsLaunch<PolynomialProgram, NoStaticPlan>::vtable(); }
+LsVTable vt_polynomial() { return LsLaunch<PolynomialProgram>::vtable(); }
 }  // namespace ebn

@@ -2,6 +2,6 @@
 #include "ebn_mc_impl.cuh"
 
 namespace ebn {
-LsVTable vt_straub_r45() { return LsLaunch<StraubFrameR45, NoStaticPlan>::vtable(); }
-LsVTable vt_straub_capacity() { return LsLaunch<StraubCapacity, NoStaticPlan>::vtable(); }
+LsVTable vt_straub_r45() { return LsLaunch<StraubFrameR45>::vtable(); }
+LsVTable vt_straub_capacity() { return LsLaunch<StraubCapacity>::vtable(); }
 }  // namespace ebn

@@ -6,9 +6,12 @@ namespace ebn {
 // again uniform), C, Ck, K untruncated normals.
 // Second plan: V a Parameter as well — what the imprecise outer loop (DoubleLoop over an interval V,
 // demo/vehicle_suspension_imprecise.jl) and `probability_of_failure` with a fixed V produce.
+// Plans 3 and 4: the same two with the normals drawn in fp32 (EBN_JOB_FP32_SAMPLING).
 LsVTable vt_vehicle() {
   return LsLaunch<VehicleSuspension,
                   StaticPlan<DK_CONST, DK_CONST, DK_UNIFORM, DK_NORMAL_BM, DK_NORMAL_BM, DK_NORMAL_BM>,
-                  StaticPlan<DK_CONST, DK_CONST, DK_CONST, DK_NORMAL_BM, DK_NORMAL_BM, DK_NORMAL_BM>>::vtable();
+                  StaticPlan<DK_CONST, DK_CONST, DK_CONST, DK_NORMAL_BM, DK_NORMAL_BM, DK_NORMAL_BM>,
+                  StaticPlan<DK_CONST, DK_CONST, DK_UNIFORM, DK_NORMAL_BM32, DK_NORMAL_BM32, DK_NORMAL_BM32>,
+                  StaticPlan<DK_CONST, DK_CONST, DK_CONST, DK_NORMAL_BM32, DK_NORMAL_BM32, DK_NORMAL_BM32>>::vtable();
 }
 }  // namespace ebn

@@ -57,11 +57,6 @@ struct StaticCopulaPlan {
   static constexpr int kinds[sizeof...(K) ? sizeof...(K) : 1] = {K...};
 };
 
-struct NoStaticPlan {
-  static constexpr bool is_static = false;
-  static constexpr int n = 0;
-};
-
 // Word offset of input J in a static plan, and the number of Philox calls a pair needs.
 template <class Plan, int J>
 __host__ __device__ constexpr int static_word_offset() {
@@ -527,7 +522,9 @@ __global__ void __launch_bounds__(kThreads) matrix_kernel(const double* consts, 
 // per-limit-state table of launchers (one translation unit per limit state so
 // the build parallelises)
 // ---------------------------------------------------------------------------
-template <template <class> class LST, class SPlan, class SPlan2 = NoStaticPlan>
+// LST: the limit-state functor template; SPlans: its compile-time sampling plans, tried in order.
+// plan_class = PLAN_DYNAMIC, PLAN_COPULA, or PLAN_STATIC0 + index into SPlans.
+template <template <class> class LST, class... SPlans>
 struct LsLaunch {
   template <class LS, class Plan>
   static cudaError_t occ2(int mode, size_t dyn, int* out) {
@@ -548,55 +545,51 @@ struct LsLaunch {
     return cudaGetLastError();
   }
 
-  template <class LS>
-  static cudaError_t occ1(int plan_class, int mode, size_t dyn, int* out) {
-    if (plan_class == PLAN_COPULA) return occ2<LS, CopulaPlan>(mode, dyn, out);
-    if constexpr (SPlan::is_static) {
-      if (plan_class == PLAN_STATIC) return occ2<LS, SPlan>(mode, dyn, out);
-    }
-    if constexpr (SPlan2::is_static) {
-      if (plan_class == PLAN_STATIC2) return occ2<LS, SPlan2>(mode, dyn, out);
-    }
-    return occ2<LS, DynamicPlan>(mode, dyn, out);
+  // Calls f.template operator()<Plan>() for the plan plan_class names.
+  template <class F, class First, class... Rest>
+  static cudaError_t pick_static(int index, F&& f) {
+    if (index == 0) return f.template operator()<First>();
+    if constexpr (sizeof...(Rest) > 0) return pick_static<F, Rest...>(index - 1, static_cast<F&&>(f));
+    return f.template operator()<DynamicPlan>();
   }
-  template <class LS>
-  static cudaError_t launch1(int plan_class, int mode, const McParams& p, int blocks, size_t dyn,
-                             cudaStream_t st) {
-    if (plan_class == PLAN_COPULA) return launch2<LS, CopulaPlan>(mode, p, blocks, dyn, st);
-    if constexpr (SPlan::is_static) {
-      if (plan_class == PLAN_STATIC) return launch2<LS, SPlan>(mode, p, blocks, dyn, st);
+  template <class F>
+  static cudaError_t with_plan(int plan_class, F&& f) {
+    if (plan_class == PLAN_COPULA) return f.template operator()<CopulaPlan>();
+    if constexpr (sizeof...(SPlans) > 0) {
+      if (plan_class >= PLAN_STATIC0) return pick_static<F, SPlans...>(plan_class - PLAN_STATIC0, static_cast<F&&>(f));
     }
-    if constexpr (SPlan2::is_static) {
-      if (plan_class == PLAN_STATIC2) return launch2<LS, SPlan2>(mode, p, blocks, dyn, st);
-    }
-    return launch2<LS, DynamicPlan>(mode, p, blocks, dyn, st);
-  }
-  template <class LS>
-  static cudaError_t replay1(int plan_class, const McParams& p, int scenario, int64_t n, double* X,
-                             double* g, int blocks, cudaStream_t st) {
-    if (plan_class == PLAN_COPULA) return replay2<LS, CopulaPlan>(p, scenario, n, X, g, blocks, st);
-    if constexpr (SPlan::is_static) {
-      if (plan_class == PLAN_STATIC) return replay2<LS, SPlan>(p, scenario, n, X, g, blocks, st);
-    }
-    if constexpr (SPlan2::is_static) {
-      if (plan_class == PLAN_STATIC2) return replay2<LS, SPlan2>(p, scenario, n, X, g, blocks, st);
-    }
-    return replay2<LS, DynamicPlan>(p, scenario, n, X, g, blocks, st);
+    return f.template operator()<DynamicPlan>();
   }
 
+  template <class LS>
+  struct Occ {
+    int mode; size_t dyn; int* out;
+    template <class Plan> cudaError_t operator()() const { return occ2<LS, Plan>(mode, dyn, out); }
+  };
+  template <class LS>
+  struct Launch {
+    int mode; const McParams& p; int blocks; size_t dyn; cudaStream_t st;
+    template <class Plan> cudaError_t operator()() const { return launch2<LS, Plan>(mode, p, blocks, dyn, st); }
+  };
+  template <class LS>
+  struct Replay {
+    const McParams& p; int scenario; int64_t n; double* X; double* g; int blocks; cudaStream_t st;
+    template <class Plan> cudaError_t operator()() const { return replay2<LS, Plan>(p, scenario, n, X, g, blocks, st); }
+  };
+
   static cudaError_t occupancy(int strict, int plan_class, int mode, size_t dyn, int* out) {
-    return strict ? occ1<LST<StrictOps>>(plan_class, mode, dyn, out)
-                  : occ1<LST<FastOps>>(plan_class, mode, dyn, out);
+    return strict ? with_plan(plan_class, Occ<LST<StrictOps>>{mode, dyn, out})
+                  : with_plan(plan_class, Occ<LST<FastOps>>{mode, dyn, out});
   }
   static cudaError_t launch(int strict, int plan_class, int mode, const McParams& p, int blocks,
                             size_t dyn, cudaStream_t st) {
-    return strict ? launch1<LST<StrictOps>>(plan_class, mode, p, blocks, dyn, st)
-                  : launch1<LST<FastOps>>(plan_class, mode, p, blocks, dyn, st);
+    return strict ? with_plan(plan_class, Launch<LST<StrictOps>>{mode, p, blocks, dyn, st})
+                  : with_plan(plan_class, Launch<LST<FastOps>>{mode, p, blocks, dyn, st});
   }
   static cudaError_t replay(int strict, int plan_class, const McParams& p, int scenario, int64_t n,
                             double* X, double* g, int blocks, cudaStream_t st) {
-    return strict ? replay1<LST<StrictOps>>(plan_class, p, scenario, n, X, g, blocks, st)
-                  : replay1<LST<FastOps>>(plan_class, p, scenario, n, X, g, blocks, st);
+    return strict ? with_plan(plan_class, Replay<LST<StrictOps>>{p, scenario, n, X, g, blocks, st})
+                  : with_plan(plan_class, Replay<LST<FastOps>>{p, scenario, n, X, g, blocks, st});
   }
   static cudaError_t matrix(int strict, const double* consts, int n_consts, const double* X,
                             int64_t n, int d, int64_t ld, unsigned long long* count, double* g_out,
@@ -608,24 +601,18 @@ struct LsLaunch {
     return cudaGetLastError();
   }
   static LsVTable vtable() {
-    LsVTable v;
+    static_assert(sizeof...(SPlans) <= kMaxStaticPlans, "raise kMaxStaticPlans");
+    LsVTable v{};
     v.occupancy = &occupancy;
     v.launch = &launch;
     v.replay = &replay;
     v.matrix = &matrix;
-    if constexpr (SPlan::is_static) {
-      v.static_kinds = SPlan::kinds;
-      v.n_static = SPlan::n;
-    } else {
-      v.static_kinds = nullptr;
-      v.n_static = 0;
-    }
-    if constexpr (SPlan2::is_static) {
-      v.static_kinds2 = SPlan2::kinds;
-      v.n_static2 = SPlan2::n;
-    } else {
-      v.static_kinds2 = nullptr;
-      v.n_static2 = 0;
+    const int* kinds[] = {SPlans::kinds..., nullptr};
+    const int ns[] = {SPlans::n..., 0};
+    v.n_plans = (int)sizeof...(SPlans);
+    for (int i = 0; i < v.n_plans; ++i) {
+      v.static_kinds[i] = kinds[i];
+      v.n_static[i] = ns[i];
     }
     return v;
   }

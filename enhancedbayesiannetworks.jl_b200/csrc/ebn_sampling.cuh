@@ -173,6 +173,9 @@ __device__ __forceinline__ InState draw_front(const WS& ws, const FastMathSmem& 
     st.w1 = ws.template w<1>();
   } else if (KIND == DK_NORMAL_BM || KIND == DK_LOGNORMAL_BM) {
     st.bm = box_muller_front(ws.template w<0>(), ws.template w<1>(), sm);
+  } else if (KIND == DK_NORMAL_BM32 || KIND == DK_LOGNORMAL_BM32) {
+    st.w0 = ws.template w<0>();
+    st.w1 = ws.template w<1>();
   } else if (KIND != DK_CONST && KIND != DK_GAMMA_MT) {
     st.w0 = ws.template w<0>();
     st.w1 = ws.template w<1>();
@@ -200,6 +203,15 @@ __device__ __forceinline__ void draw_back(const DevInput& in, const InState& st,
     x0 = fma(z0, in.b, in.a);
     x1 = fma(z1, in.b, in.a);
     if (KIND == DK_LOGNORMAL_BM) {
+      x0 = exp_fast(x0, sm);
+      x1 = exp_fast(x1, sm);
+    }
+  } else if (KIND == DK_NORMAL_BM32 || KIND == DK_LOGNORMAL_BM32) {
+    double z0, z1;
+    box_muller_words_f32(st.w0, st.w1, z0, z1);
+    x0 = fma(z0, in.b, in.a);
+    x1 = fma(z1, in.b, in.a);
+    if (KIND == DK_LOGNORMAL_BM32) {
       x0 = exp_fast(x0, sm);
       x1 = exp_fast(x1, sm);
     }
@@ -237,6 +249,8 @@ static __device__ __noinline__ void draw_pair_dyn(const DevInput& in, const Pair
     case DK_GUMBEL: draw_pair<DK_GUMBEL>(in, ws, pc, j, tables, sm, x0, x1); break;
     case DK_EXP_AFFINE: draw_pair<DK_EXP_AFFINE>(in, ws, pc, j, tables, sm, x0, x1); break;
     case DK_GAMMA_MT: draw_pair<DK_GAMMA_MT>(in, ws, pc, j, tables, sm, x0, x1); break;
+    case DK_NORMAL_BM32: draw_pair<DK_NORMAL_BM32>(in, ws, pc, j, tables, sm, x0, x1); break;
+    case DK_LOGNORMAL_BM32: draw_pair<DK_LOGNORMAL_BM32>(in, ws, pc, j, tables, sm, x0, x1); break;
     default: draw_pair<DK_TABLE>(in, ws, pc, j, tables, sm, x0, x1); break;
   }
 }

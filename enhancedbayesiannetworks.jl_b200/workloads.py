@@ -50,10 +50,11 @@ def vehicle_scenarios():
     return rows, labels
 
 
-def w1_vehicle(n: int = 10**8, seed: int = 0x5EED0001, strict: bool = False) -> L.Job:
+def w1_vehicle(n: int = 10**8, seed: int = 0x5EED0001, strict: bool = False, fp32_sampling: bool = False) -> L.Job:
     """W1 = BASELINE config 2: vehicle suspension, S=20, n per scenario."""
     rows, _ = vehicle_scenarios()
-    return L.Job(L.LS_VEHICLE_SUSPENSION, vehicle_consts(), L.make_inputs(rows), n, seed, strict)
+    return L.Job(L.LS_VEHICLE_SUSPENSION, vehicle_consts(), L.make_inputs(rows), n, seed, strict,
+                 fp32_sampling=fp32_sampling)
 
 
 def w5_vehicle_grid(n: int = 10**10, seed: int = 0x5EED0005, side: int = 32, strict: bool = False) -> L.Job:

@@ -104,6 +104,21 @@ def _box_muller(w0, w1):
     return s0 * R * np.sin(phi), s1 * R * np.cos(phi)
 
 
+def _box_muller_f32(w0, w1):
+    """EBN_JOB_FP32_SAMPLING: the same bit fields, the transform in float32 (radius from the 32 bits
+    of w0 only). NumPy's float32 log/sqrt/sin/cos are correctly rounded to ~1 ulp, the device uses the
+    MUFU approximations: agreement ~1e-6 in z."""
+    f32 = np.float32
+    rot = ((w0 << np.uint64(12)) & _MASK) | (w0 >> np.uint64(20))
+    u = rot.astype(f32) * f32(2.0**-32) + f32(2.0**-33)
+    R = np.sqrt(f32(-2.0) * np.log(u))
+    A = (w1 >> np.uint64(10)) & np.uint64(0xFFFFF)
+    phi = f32(np.pi / 2) * ((A.astype(f32) + f32(0.5)) * f32(2.0**-20))
+    s0 = np.where(w1 & np.uint64(0x80000000), -1.0, 1.0)
+    s1 = np.where(w1 & np.uint64(0x40000000), -1.0, 1.0)
+    return s0 * (R * np.sin(phi)).astype(np.float64), s1 * (R * np.cos(phi)).astype(np.float64)
+
+
 def words_of(inp) -> int:
     kind = int(inp["kind"])
     trunc = np.isfinite(float(inp["lo"])) or np.isfinite(float(inp["hi"]))
@@ -199,8 +214,9 @@ def _pairs_of(first, n):
     return upairs, inv, odd
 
 
-def sample_matrix(inputs_row, stream: int, seed: int, first: int, n: int, tables=None) -> np.ndarray:
-    """The n samples [first, first+n) of one scenario, (n, d), as the device draws them."""
+def sample_matrix(inputs_row, stream: int, seed: int, first: int, n: int, tables=None, fp32: bool = False) -> np.ndarray:
+    """The n samples [first, first+n) of one scenario, (n, d), as the device draws them
+    (fp32: with EBN_JOB_FP32_SAMPLING)."""
     d = len(inputs_row)
     upairs, inv, odd = _pairs_of(first, n)
     W = _Words(upairs, stream, seed)
@@ -218,7 +234,7 @@ def sample_matrix(inputs_row, stream: int, seed: int, first: int, n: int, tables
             u = np.where(odd, _u32(W[off + 1])[inv], _u32(W[off])[inv])
             X[:, j] = a + u * (b - a)
         elif kind in (IN_NORMAL, IN_LOGNORMAL) and nw == 2:
-            z0, z1 = _box_muller(W[off], W[off + 1])
+            z0, z1 = (_box_muller_f32 if fp32 else _box_muller)(W[off], W[off + 1])
             v = p[0] + p[1] * np.where(odd, z1[inv], z0[inv])
             X[:, j] = np.exp(v) if kind == IN_LOGNORMAL else v
         elif kind == IN_GAMMA:

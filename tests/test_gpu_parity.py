@@ -291,6 +291,44 @@ def test_fused_count_equals_oracle_vehicle_fixed_v_plan(ebn):
     assert np.array_equal(cnt_dyn[:3], cnt[:3])
 
 
+def test_fp32_sampling_is_the_same_stream_at_lower_precision(ebn):
+    """EBN_JOB_FP32_SAMPLING ("FP32 where tolerated"): the untruncated normals come from the same random
+    words through an fp32 Box-Muller. Every sample agrees with the fp64 draw to ~1e-6 sigma, the fused
+    count equals the oracle on the replayed matrix bit for bit (the limit state stays fp64), the count
+    differs from the fp64 job only by near-ties, and the NumPy float32 twin reproduces the draws."""
+    from ebn_b200 import workloads as W
+    n = 400_001
+    j64 = W.w1_vehicle(n=n, strict=True)
+    j32 = W.w1_vehicle(n=n, strict=True, fp32_sampling=True)
+    c64 = ebn.pf_batch(j64)[0]
+    c32, pf32, _ = ebn.pf_batch(j32)
+    assert ebn.last_stats()["specialised"] == 1
+    for s in (0, 9, 19):
+        X32 = ebn.sample_matrix(j32, s, 0, n)
+        assert int(c32[s]) == ocpu.eval_matrix(ocpu.LS_VEHICLE, j32.consts, X32), s
+        X64 = ebn.sample_matrix(j64, s, 0, n)
+        assert np.array_equal(X32[:, :3], X64[:, :3])                      # Parameters and the uniform: untouched
+        dz = np.abs(X32[:, 3:] - X64[:, 3:]) / 10.0                        # sigma = 10
+        # measured (tools/fp32_diff_stats.py): median 1e-7, 99.99 % below 1.4e-6, max 6e-5 (tiny radii,
+        # where the absolute error of MUFU.LG2 passes through the square root)
+        assert np.percentile(dz, 99.9) < 2e-6 and dz.max() < 5e-4
+        twin = replay.sample_matrix(j32.inputs[s], s, j32.seed, 0, 5000, fp32=True)
+        dt = np.abs(twin[:, 3:] - X32[:5000, 3:]) / 10.0
+        assert np.percentile(dt, 99.9) < 2e-6 and dt.max() < 5e-4
+    # counts: only samples whose g sits within ~1e-5 of zero can flip
+    assert np.max(np.abs(c32 - c64)) <= 0.002 * n * 1e-2 + 8, (c32 - c64)
+    # the runtime-dispatched plan draws the same fp32 samples (mixed kinds: no compile-time plan)
+    mixed = W.w1_vehicle(n=n, strict=True, fp32_sampling=True)
+    mixed.inputs[0, 3]["lo"] = 0.0            # scenario 0 gets a (far) truncated C: kinds differ between scenarios
+    cm = ebn.pf_batch(mixed)[0]
+    assert ebn.last_stats()["specialised"] == 0 and np.array_equal(cm[1:], c32[1:])
+    # independent check: within 4 SE of the fp64 estimate at a larger n
+    big32 = ebn.pf_batch(W.w1_vehicle(n=20_000_000, fp32_sampling=True))
+    big64 = ebn.pf_batch(W.w1_vehicle(n=20_000_000, seed=1234))
+    z = (big32[1] - big64[1]) / np.sqrt(big32[2] + big64[2])
+    assert np.abs(z).max() < 4.0, z
+
+
 def test_fused_dynamic_plan_all_kinds(ebn):
     """Generic (runtime-dispatched) sampling plan: fused count == oracle on the replayed matrix."""
     inputs = ebn.make_inputs([ALL_KINDS_ROW, ALL_KINDS_ROW[::-1][1:] + [ALL_KINDS_ROW[-1]]])

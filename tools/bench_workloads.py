@@ -29,8 +29,12 @@ def run(name, job, reps=3, hist_edges=None):
 
 
 run("W1 vehicle (fast)", W.w1_vehicle(n=10**8))
+run("W1 vehicle, normals drawn in fp32 (EBN_JOB_FP32_SAMPLING)", W.w1_vehicle(n=10**8, fp32_sampling=True))
 run("W1 vehicle (strict: Julia-order g, 6 div + sqrt)", W.w1_vehicle(n=10**8, strict=True))
 run("W2 Straub frame S=1", W.w2_straub(n=10**9))
+w2f = W.w2_straub(n=10**9)
+w2f.fp32_sampling = True
+run("W2 Straub frame, normals drawn in fp32", w2f)
 w3 = W.w3_straub_copula(n=2 * 10**7)
 w3.jit_plan = False
 run("W3 Straub-style copula, 64 scenarios (looping copula plan)", w3)
