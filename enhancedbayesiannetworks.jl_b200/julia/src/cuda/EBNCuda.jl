@@ -91,22 +91,25 @@ ebn_shutdown() = check(ccall((:ebn_shutdown, LIB[]), Cint, ()))
 
 # ---- the plug-in point: a new AbstractMonteCarlo subtype ---------------------------------------
 """
-    CudaMonteCarlo(n; seed=0x5EED0001, strict=false, performance=nothing)
+    CudaMonteCarlo(n; seed=0x5EED0001, strict=false, performance=nothing, fp32_sampling=false)
 
 Simulation object routing a functional node to libebncuda. `strict=true` evaluates the limit
 state with one IEEE operation per Julia operation (bit-exact `g`), the default contracts FMAs and
 hoists reciprocals (|Δg| ~ 1e-13, count differences only on ties). For a chain of `CudaExprModel`s,
 `performance` is the node's performance function as a quoted expression (`:(2 .- df.C)`); the
 node's own `performance::Function` cannot be translated. Default: the last model's column.
+`fp32_sampling=true` sets EBN_JOB_FP32_SAMPLING (untruncated normals drawn in fp32, limit state in fp64).
 """
 struct CudaMonteCarlo <: UncertaintyQuantification.AbstractMonteCarlo
     n::Int
     seed::UInt64
     strict::Bool
     performance::Any
+    fp32_sampling::Bool
 end
-CudaMonteCarlo(n::Integer; seed::Integer=0x5EED0001, strict::Bool=false, performance=nothing) =
-    CudaMonteCarlo(n, UInt64(seed), strict, performance)
+CudaMonteCarlo(n::Integer; seed::Integer=0x5EED0001, strict::Bool=false, performance=nothing, fp32_sampling::Bool=false) =
+    CudaMonteCarlo(n, UInt64(seed), strict, performance, fp32_sampling)
+job_flags(sim::CudaMonteCarlo) = sim.fp32_sampling ? UInt32(16) : UInt32(0)   # EBN_JOB_FP32_SAMPLING
 
 """
     CudaModel(name, limit_state, consts, args)
@@ -294,7 +297,7 @@ function pf_batch(model::CudaModel, scenario_inputs::Vector{<:Vector}, sim::Cuda
     var = zeros(Float64, S)
     GC.@preserve M consts begin
         job = Ref(EbnJob(EBN_LS[model.limit_state], length(consts), pointer(consts), S, d, pointer(M), sim.n,
-            sim.seed, sim.strict ? 1 : 0, 0, C_NULL, C_NULL, C_NULL, 0, 0, 0, 1))
+            sim.seed, sim.strict ? 1 : 0, job_flags(sim), C_NULL, C_NULL, C_NULL, 0, 0, 0, 1))
         check(ccall((:ebn_pf_batch, LIB[]), Cint, (Ref{EbnJob}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
             job, counts, pf, var))
     end
@@ -367,7 +370,7 @@ function hist_batch(model::CudaModel, scenario_inputs::Vector{<:Vector}, sim::Cu
     s2 = zeros(Float64, S)
     GC.@preserve M consts begin
         job = Ref(EbnJob(EBN_LS[model.limit_state], length(consts), pointer(consts), S, d, pointer(M), sim.n,
-            sim.seed, sim.strict ? 1 : 0, 0, C_NULL, C_NULL, C_NULL, 0, 0, 0, 1))
+            sim.seed, sim.strict ? 1 : 0, job_flags(sim), C_NULL, C_NULL, C_NULL, 0, 0, 0, 1))
         check(ccall((:ebn_hist_batch, LIB[]), Cint,
             (Ref{EbnJob}, Ptr{Float64}, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
             job, edges, length(edges), counts, s1, s2))
@@ -402,7 +405,7 @@ function EnhancedBayesianNetworks._evaluate_node(net::EnhancedBayesianNetwork,
     scen = map(ev -> mapreduce(p -> _uq_inputs(p, ev), vcat, parents(net, node)[3]; init=UQInput[]), evidences)
     model = node.models[end]::CudaModel
     hid = hidden_inputs(model)
-    pilot = CudaMonteCarlo(min(sim.n, 1 << 16), sim.seed, sim.strict, nothing)
+    pilot = CudaMonteCarlo(min(sim.n, 1 << 16), sim.seed, sim.strict, nothing, sim.fp32_sampling)
     _, s1, s2 = hist_batch(model, scen, pilot, [0.0]; hidden=hid)          # moments only
     μ = s1 ./ pilot.n
     σ = sqrt.(max.(s2 ./ pilot.n .- μ .^ 2, 0.0))

@@ -439,6 +439,7 @@ class CudaMonteCarlo:
     n: int
     seed: int = 0x5EED0001
     strict: bool = False
+    fp32_sampling: bool = False   # EBN_JOB_FP32_SAMPLING: untruncated normals through the fp32 Box-Muller
 
 
 MonteCarlo = CudaMonteCarlo  # the only AbstractMonteCarlo this package implements

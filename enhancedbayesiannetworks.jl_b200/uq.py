@@ -253,7 +253,8 @@ def build_job(low: Lowered, scenario_inputs: Sequence[Sequence], sim: CudaMonteC
         else:
             chols.append(np.eye(d))
     return L.Job(low.limit_state, low.consts, L.make_inputs(rows), int(sim.n), int(sim.seed), bool(sim.strict),
-                 stream_id=stream_id, tables=pool.array(), corr_chol=np.stack(chols) if any_copula else None)
+                 stream_id=stream_id, tables=pool.array(), corr_chol=np.stack(chols) if any_copula else None,
+                 fp32_sampling=bool(getattr(sim, "fp32_sampling", False)))
 
 
 class Samples:
