@@ -37,6 +37,19 @@ ALL_KINDS_ROW = [
 TABLE = np.array([-1.0, 0.0, 0.5, 2.0, 10.0])
 
 
+VEHICLE_TEXT = [  # demo/vehicle_suspension.jl:17-23
+    ("g1", "1 .- (π .* m .* df.V .* df.A) ./ (df.b₀ .* df.K .* g .^ 2) .* ((df.Cₖ ./ (m .+ M) .- (df.C ./ M)) .^ 2"
+           " .+ df.C .^ 2 ./ (m .* M) .+ df.Cₖ .* df.K .^ 2 ./ (m .* M .^ 2))"),
+    ("g2", "4000 .* df.C .* Mg15 .- 8.6394"),
+    ("g3", "2 .* sqrt.(M .* g .* (df.K .^ 2 .* df.Cₖ ./ (df.C .* (m .+ M)) .+ df.C)) .- 1"),
+    ("g4", "df.Cₖ .- gMm"),
+    ("y", "minimum([g1[1], g2, g3, g4[1]])"),
+]
+CAPACITY_TEXT = "exp(rand(Normal(λ + ρ * ζ * df.Uᵣ, sqrt((1 - ρ^2) * ζ^2))))"      # demo/straub_example.jl:16-27
+FRAME_TEXT = ("minimum([r1 + r2 + r4 + r5 - 5 * df.H, r2 + 2 * r3 + r4 - 5 * df.V, "
+              "r1 + 2 * r3 + 2 * r4 + r5 - 5 * df.H - 5 * df.V])")                  # :35-40
+
+
 def main():
     rng = np.random.default_rng(20261019)
     n = 2048
@@ -57,7 +70,19 @@ def main():
         blocks[f"first_{first}"] = replay.sample_matrix(inputs[0], 3, seed, first, 64, tables=TABLE)
     np.savez_compressed(os.path.join(HERE, "stream_v3.npz"), inputs=inputs, table=TABLE, seed=np.uint64(seed),
                         stream=np.uint32(3), **blocks)
-    print("vehicle count", cv, "straub count", cs)
+    # expression programs: the two demos' closures as text, compiled by the product's text compiler
+    # (pins the compiler's instruction order) and evaluated by the oracle's stack machine on the same
+    # matrices; g must equal the hand-written restatements above bit for bit
+    from ebn_b200 import expr
+    veh = expr.compile_program(["A", "b₀", "V", "C", "Cₖ", "K"], VEHICLE_TEXT, "df.y",
+                               params={"M": VEH_K[0], "m": VEH_K[1], "g": VEH_K[2], "Mg15": VEH_K[3], "gMm": VEH_K[4]})
+    stb = expr.compile_program(["Uᵣ", "V", "H"], [(f"r{i}", CAPACITY_TEXT) for i in range(1, 6)] + [("G", FRAME_TEXT)],
+                               "df.G", params={"λ": STRAUB_K[0], "ζ": STRAUB_K[1], "ρ": STRAUB_K[2]})
+    cve, gve = ocpu.eval_matrix(ocpu.LS_EXPRESSION, veh.consts, Xv, want_g=True)
+    cse, gse = ocpu.eval_matrix(ocpu.LS_EXPRESSION, stb.consts, Xs, want_g=True)
+    assert cve == cv and np.array_equal(gve, gv) and cse == cs and np.array_equal(gse, gs)
+    np.savez_compressed(os.path.join(HERE, "expression.npz"), vehicle_program=veh.consts, straub_program=stb.consts)
+    print("vehicle count", cv, "straub count", cs, "program sizes", veh.consts.size, stb.consts.size)
 
 
 if __name__ == "__main__":

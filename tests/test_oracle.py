@@ -34,6 +34,31 @@ def test_golden_limit_states():
     assert np.allclose(replay.g_straub(z["straub_X"], z["straub_k"]), z["straub_g"], rtol=0, atol=1e-10)
 
 
+def test_golden_expression_programs():
+    """The committed programs (the demos' closures compiled from text) reproduce the golden g of the
+    hand-written limit states through both stack machines, and today's text compiler still emits
+    exactly these programs."""
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_golden as mg
+    from ebn_b200 import expr
+    z = np.load(os.path.join(GOLD, "limit_states.npz"))
+    e = np.load(os.path.join(GOLD, "expression.npz"))
+    c, g = ocpu.eval_matrix(ocpu.LS_EXPRESSION, e["vehicle_program"], z["vehicle_X"], want_g=True)
+    assert c == int(z["vehicle_count"]) and np.array_equal(g, z["vehicle_g"])
+    assert np.array_equal(replay.g_expression(z["vehicle_X"], e["vehicle_program"]), z["vehicle_g"])
+    c, g = ocpu.eval_matrix(ocpu.LS_EXPRESSION, e["straub_program"], z["straub_X"], want_g=True)
+    assert c == int(z["straub_count"]) and np.array_equal(g, z["straub_g"])
+    k = z["vehicle_k"]
+    veh = expr.compile_program(["A", "b₀", "V", "C", "Cₖ", "K"], mg.VEHICLE_TEXT, "df.y",
+                               params={"M": k[0], "m": k[1], "g": k[2], "Mg15": k[3], "gMm": k[4]})
+    assert np.array_equal(veh.consts, e["vehicle_program"])
+    sk = z["straub_k"]
+    stb = expr.compile_program(["Uᵣ", "V", "H"], [(f"r{i}", mg.CAPACITY_TEXT) for i in range(1, 6)] + [("G", mg.FRAME_TEXT)],
+                               "df.G", params={"λ": sk[0], "ζ": sk[1], "ρ": sk[2]})
+    assert np.array_equal(stb.consts, e["straub_program"])
+
+
 def test_golden_stream_layout():
     z = np.load(os.path.join(GOLD, "stream_v3.npz"))
     inputs = z["inputs"].view(ocpu.INPUT_DTYPE).reshape(1, -1)
