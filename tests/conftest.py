@@ -12,6 +12,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built library (it is git-ignored): build it once (nvcc cross-compiles
+    without a GPU, ~30 s) instead of failing every test that loads it."""
+    if not os.path.exists(os.path.join(ROOT, "enhancedbayesiannetworks.jl_b200", "libebncuda.so")):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 @pytest.fixture(scope="session")
 def ebn():
     """The product package, initialised on cuda:0. Fails loudly without the CUDA library/GPU."""
