@@ -445,7 +445,9 @@ def test_examples_run(E):
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     mods = {}
-    for name in ("vehicle_suspension", "straub_example"):
+    import sys
+    sys.path.insert(0, os.path.join(root, "examples"))
+    for name in ("vehicle_suspension", "straub_example", "vehicle_suspension_imprecise"):
         spec = importlib.util.spec_from_file_location(f"example_{name}", os.path.join(root, "examples", f"{name}.py"))
         mods[name] = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mods[name])
@@ -454,6 +456,13 @@ def test_examples_run(E):
     assert len(pf) == 20 and abs(pf[("offroad", "normal_load", "[11.5, 12.0]")] - 0.7373) < 0.005
     pi = mods["straub_example"].main(10**6)
     assert np.allclose(pi, [0.026129, 0.973871], atol=0.01)
+    ei = mods["vehicle_suspension_imprecise"].main(200_000)
+    assert not ei.isprecise()
+    bounds = {r["V_d"]: r["Π"] for r in ei.cpt.data
+              if r["E"] == "E_fail" and (r["A"], r["b₀"]) == ("offroad", "normal_load")}
+    assert len(bounds) == 5 and all(lb < ub for lb, ub in bounds.values())
+    lbs = [bounds[k][0] for k in ("[7.0, 8.5]", "[8.5, 9.5]", "[9.5, 10.5]", "[10.5, 11.5]", "[11.5, 13.0]")]
+    assert lbs == sorted(lbs)                      # pf grows with V: the lower bounds are the left bin ends
 
 
 def test_vehicle_suspension_imprecise(E):
