@@ -205,6 +205,65 @@ def test_replay_matches_numpy_twin(ebn, first, n):
     assert not np.allclose(ebn.sample_matrix(job, 0, first, n)[:, 1], ebn.sample_matrix(job, 1, first, n)[:, 1])
 
 
+def _random_marginal(rng):
+    """One random ebn_input_t row: kind, parameters and (half of the time) a truncation window that
+    keeps at least ~1 % of the mass inside +-3.5 standard scales."""
+    kind = int(rng.choice([0, 1, 1, 2, 3, 4, 5, 6]))
+    trunc = rng.random() < 0.5
+    if kind == 0:
+        return (0, float(rng.normal(0, 5)), 0, 0, 0, -INF, INF)
+    if kind in (1, 2):
+        mu, sd = (float(rng.normal(0, 3)), float(rng.uniform(0.2, 3))) if kind == 1 else (float(rng.normal(0, 0.5)), float(rng.uniform(0.05, 0.5)))
+        if not trunc:
+            return (kind, mu, sd, 0, 0, -INF, INF)
+        a = float(rng.uniform(-3.0, 2.0))
+        b = a + float(rng.uniform(0.3, 3.0))
+        lo, hi = mu + sd * a, mu + sd * b
+        if rng.random() < 0.3:
+            hi = INF
+        return (kind, mu, sd, 0, 0, math.exp(lo), math.exp(hi) if hi < INF else INF) if kind == 2 else (kind, mu, sd, 0, 0, lo, hi)
+    if kind == 3:
+        a = float(rng.normal(0, 5))
+        b = a + float(rng.uniform(0.5, 10))
+        if trunc:
+            return (3, a, b, 0, 0, a + 0.2 * (b - a), a + 0.7 * (b - a))
+        return (3, a, b, 0, 0, -INF, INF)
+    if kind == 4:
+        mu, beta = float(rng.normal(10, 5)), float(rng.uniform(0.5, 5))
+        if trunc:
+            return (4, mu, beta, 0, 0, mu - 1.0 * beta, mu + float(rng.uniform(0.5, 4)) * beta)
+        return (4, mu, beta, 0, 0, -INF, INF)
+    if kind == 5:
+        return (5, float(rng.choice([0.4, 0.9, 1.0, 2.5, 25.0, 180.0])), float(rng.uniform(0.2, 3)), 0, 0, -INF, INF)
+    theta, sign, shift = float(rng.uniform(0.3, 3)), float(rng.choice([-1.0, 1.0])), float(rng.normal(0, 2))
+    if trunc:
+        lo, hi = (shift + 0.1 * theta, shift + 2.5 * theta) if sign > 0 else (shift - 2.5 * theta, shift - 0.1 * theta)
+        return (6, theta, sign, shift, 0, lo, hi)
+    return (6, theta, sign, shift, 0, -INF, INF)
+
+
+def test_random_marginal_rows_against_the_twin(ebn):
+    """Randomised version of the twin comparison: 16 random scenario rows (kinds, parameters,
+    truncation windows), drawn by the runtime-dispatched plan, equal the NumPy twin to 5e-12; and for
+    each row the plan compiled at run time for exactly these kinds draws the same bits."""
+    rng = np.random.default_rng(777)
+    seed = 0x1234_5678_9ABC_DEF0
+    for trial in range(16):
+        d = int(rng.integers(2, 9))
+        row = [_random_marginal(rng) for _ in range(d)]
+        inputs = ebn.make_inputs([row, row])
+        job = ebn.Job(ebn._lib.LS_MIN_AFFINE, _min_affine_all(d), inputs, n=5000, seed=seed, jit_plan=False)
+        first = int(rng.choice([0, 3, 2**35 + 1]))
+        X = ebn.sample_matrix(job, 1, first, 3000)
+        ref = replay.sample_matrix(inputs[1], 1, seed, first, 3000)
+        err = np.max(np.abs(X - ref) / np.maximum(np.abs(ref), 1.0), axis=0)
+        assert np.all(err < 5e-12), (trial, row, err)
+        if trial % 4 == 0:      # a compile per row: every fourth row is enough
+            jit = ebn.Job(job.limit_state, job.consts, inputs, n=5000, seed=seed, jit_plan=True)
+            assert np.array_equal(ebn.sample_matrix(jit, 1, first, 3000), X), (trial, row)
+            assert np.array_equal(ebn.pf_batch(jit)[0], ebn.pf_batch(job)[0])
+
+
 def test_replay_moments(ebn):
     """Distribution sanity of the sampler on 2e6 draws (means within 5 standard errors)."""
     n = 2_000_000
