@@ -651,6 +651,40 @@ def test_gaussian_copula_sampler_and_count(ebn):
                              corr_chol=np.eye(2)))
 
 
+def test_random_copulas_against_the_twin(ebn):
+    """Random correlation matrices over random marginal rows (Gamma excluded: it must be tabulated
+    under a copula): the looping copula plan equals the NumPy twin, and the plan unrolled at run time
+    draws the same bits."""
+    rng = np.random.default_rng(4242)
+    for trial in range(6):
+        d = int(rng.integers(2, 7))
+        row = []
+        while len(row) < d:
+            m = _random_marginal(rng)
+            if m[0] != 5:
+                row.append(m)
+        B = rng.normal(0, 1, (d, 2))
+        R = B @ B.T + np.diag(rng.uniform(0.5, 1.5, d))
+        sdv = np.sqrt(np.diag(R))
+        R = R / sdv[:, None] / sdv[None, :]
+        for j, m in enumerate(row):          # Parameter rows/columns must be identity
+            if m[0] == 0:
+                R[j, :] = 0.0
+                R[:, j] = 0.0
+                R[j, j] = 1.0
+        Lc = np.linalg.cholesky(R)
+        inputs = ebn.make_inputs([row, row])
+        kw = dict(n=4000, seed=31337, corr_chol=Lc)
+        loop = ebn.Job(ebn._lib.LS_MIN_AFFINE, _min_affine_all(d), inputs, jit_plan=False, **kw)
+        X = ebn.sample_matrix(loop, 1, 5, 3000)
+        ref = replay.copula_sample_matrix(inputs[1], Lc, 1, 31337, 5, 3000)
+        err = np.max(np.abs(X - ref) / np.maximum(np.abs(ref), 1.0), axis=0)
+        assert np.all(err < 1e-9), (trial, row, err)
+        if trial % 2 == 0:
+            unrolled = ebn.Job(ebn._lib.LS_MIN_AFFINE, _min_affine_all(d), inputs, jit_plan=True, **kw)
+            assert np.array_equal(ebn.sample_matrix(unrolled, 1, 5, 3000), X), (trial, row)
+
+
 def test_w3_straub_copula_and_w5_grid(ebn):
     """BASELINE configs 3 and 5 at test size."""
     from ebn_b200 import workloads as W
