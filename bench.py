@@ -31,16 +31,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# FP64-pipe instructions per sample of the W1 kernel: (DFMA 74.1 + DMUL 38.0 + DADD 13.1) warp
+# FP64-pipe instructions per sample of the W1 kernel: (DFMA 68.1 + DMUL 38.0 + DADD 13.1) warp
 # instructions per sample PAIR executed in the hot loop, from the ncu source page of
-# profiles/r01_o_* (= sm__inst_executed_pipe_fp64), i.e. 62.6 per sample. See DESIGN.md
+# profiles/r01_s_* (= sm__inst_executed_pipe_fp64), i.e. 59.6 per sample. See DESIGN.md
 # "Roofline". The SURVEY's ceiling for this figure is 339; the first version executed 151.5.
 # The figure is re-frozen whenever the kernel changes: removing fp64 work raises samples/s and
 # LOWERS the fraction, which is why DESIGN.md tabulates both for every version.
-F_ALG_W1 = 62.6
+F_ALG_W1 = 59.6
 # dram__bytes_read.sum + dram__bytes_write.sum of one mc_kernel launch (ncu --set full,
-# profiles/r01_o_ncu_full_w1_n1e7_summary.txt): 37.9 KB read, 0 B written — the plan and tables.
-DRAM_TRAFFIC_BYTES_PER_LAUNCH = 37888
+# profiles/r01_s_ncu_full_w1_n1e7_summary.txt): 52.0 KB read, 0 B written — the plan and tables.
+DRAM_TRAFFIC_BYTES_PER_LAUNCH = 51968
 METRIC = "limit_state_mc_samples_per_sec"
 UNIT = "samples/s"
 

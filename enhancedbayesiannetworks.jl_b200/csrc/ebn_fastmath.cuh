@@ -23,7 +23,7 @@ struct FastMathConst {
   double ln2;
   double expc[4];   // 1/2, 1/6, 1/24, 1/120
   double inv_ln2_64, ln2_64_hi, ln2_64_lo;
-  double sind[3];   // sin(delta) = t*(d0 + d1 t^2 + d2 t^4), delta = (pi/2) t inside a table cell
+  double sind[EBN_SC_TAB_BITS < 10 ? 3 : 2];   // sin(delta) = t*(d0 + d1 t^2 [+ d2 t^4]), delta = (pi/2) t inside a table cell
   double cosd[2];   // cos(delta) - 1 = t^2*(e0 + e1 t^2)
 };
 __constant__ FastMathConst kFm = {
@@ -40,15 +40,29 @@ __constant__ FastMathConst kFm = {
 // Shared-memory copy of the log table (per-lane random index: shared memory,
 // not the constant cache, which serialises divergent addresses).
 struct FastMathSmem {
-  double2 logtab[128];
-  double2 sctab[128];   // sqrt(2)*(sin, cos) at the centres of 128 cells of the first quadrant
+  double2 logtab[1 << EBN_LOG_TAB_BITS];
+  double2 sctab[1 << EBN_SC_TAB_BITS];   // sqrt(2)*(sin, cos) at the cell centres of the first quadrant
   double exptab[64];
 };
 
 __device__ __forceinline__ void fastmath_init(FastMathSmem& sm, int tid, int nthreads) {
-  for (int i = tid; i < 128; i += nthreads) sm.logtab[i] = kLogTab[i];
-  for (int i = tid; i < 128; i += nthreads) sm.sctab[i] = kSinCosTab[i];
+  for (int i = tid; i < (1 << EBN_LOG_TAB_BITS); i += nthreads) sm.logtab[i] = kLogTab[i];
+  for (int i = tid; i < (1 << EBN_SC_TAB_BITS); i += nthreads) sm.sctab[i] = kSinCosTab[i];
   for (int i = tid; i < 64; i += nthreads) sm.exptab[i] = kExpTab[i];
+}
+
+// Index of the log-table cell from the high word of a double, and the polynomial
+// p(r) with log1p(r) = r - r^2 p(r): 1/2 - r/3 + r^2/4 [- r^3/5 + r^4/6 when the cells are wide].
+__device__ __forceinline__ int log_cell(int hi) { return (hi >> (20 - EBN_LOG_TAB_BITS)) & ((1 << EBN_LOG_TAB_BITS) - 1); }
+__device__ __forceinline__ double log1p_poly(double r) {
+  if (EBN_LOG_TAB_BITS >= 10) {      // |r| <= 2^-11: the r^5/5 term is below 6e-18
+    return fma(r, fma(r, kFm.ln1p[2], kFm.ln1p[1]), kFm.ln1p[0]);
+  } else {
+    double p = fma(r, kFm.ln1p[4], kFm.ln1p[3]);
+    p = fma(r, p, kFm.ln1p[2]);
+    p = fma(r, p, kFm.ln1p[1]);
+    return fma(r, p, kFm.ln1p[0]);
+  }
 }
 
 // -ln(u) for a normal double u in (0,1).
@@ -63,17 +77,14 @@ __device__ __forceinline__ double neg_log01(double u, const FastMathSmem& sm) {
   // sigma*z only ever needs z to absolute accuracy, so nothing is lost.
   const int ne = 1023 - (hi >> 20);                                   // -e in [1, 53]
   const int mhi = (hi & 0x000FFFFF) | 0x3FF00000;                     // m in [1,2)
-  const int idx = (hi >> 13) & 0x7F;                                  // top 7 mantissa bits
+  const int idx = log_cell(hi);                                       // top mantissa bits
   const double m = __hiloint2double(mhi, lo);
   const double2 t = sm.logtab[idx];
   const double r = fma(m, t.x, -1.0);
   // int -> double without a conversion instruction: 2^52+2^51 magic (ne >= 0)
   const double ned = __hiloint2double(0x43380000, ne) - 6755399441055744.0;
   // log1p(r) = r - r^2*(1/2 - r*(1/3 - r*(1/4 - r*(1/5 - r/6))))
-  double p = fma(r, kFm.ln1p[4], kFm.ln1p[3]);
-  p = fma(r, p, kFm.ln1p[2]);
-  p = fma(r, p, kFm.ln1p[1]);
-  p = fma(r, p, kFm.ln1p[0]);          // 1/2 - r/3 + r^2/4 - r^3/5 + r^4/6
+  const double p = log1p_poly(r);      // 1/2 - r/3 + r^2/4 ...
   const double r2 = r * r;
   const double base = fma(ned, kFm.ln2, t.y);   // -e*ln2 + ln(rc)
   return fma(r2, p, base - r);                   // ... - r + r^2*(...)
@@ -85,16 +96,13 @@ __device__ __forceinline__ double neg_log_pos(double t, const FastMathSmem& sm) 
   const int lo = __double2loint(t);
   const int ne = 1023 - (hi >> 20);
   const int mhi = (hi & 0x000FFFFF) | 0x3FF00000;
-  const int idx = (hi >> 13) & 0x7F;
+  const int idx = log_cell(hi);
   const double m = __hiloint2double(mhi, lo);
   const double2 tb = sm.logtab[idx];
   const double r = fma(m, tb.x, -1.0);
   // signed int -> double: bias by 2^31 inside the 2^52+2^51 magic
   const double ned = __hiloint2double(0x43380000, ne ^ (int)0x80000000) - 6755401588539392.0;
-  double p = fma(r, kFm.ln1p[4], kFm.ln1p[3]);
-  p = fma(r, p, kFm.ln1p[2]);
-  p = fma(r, p, kFm.ln1p[1]);
-  p = fma(r, p, kFm.ln1p[0]);
+  const double p = log1p_poly(r);
   const double r2 = r * r;
   const double base = fma(ned, kFm.ln2, tb.y);
   return fma(r2, p, base - r);
@@ -158,7 +166,7 @@ __device__ __forceinline__ BmFront box_muller_front(uint32_t w0, uint32_t w1, co
   const int hi = __double2hiint(u);
   const int ne = 1023 - (hi >> 20);
   const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(u));
-  const double2 t = sm.logtab[(hi >> 13) & 0x7F];
+  const double2 t = sm.logtab[log_cell(hi)];
   BmFront f;
   f.r = fma(m, t.x, -1.0);
   f.base = fma(__hiloint2double(0x43380000, ne) - 6755399441055744.0, kFm.ln2, t.y);
@@ -168,22 +176,24 @@ __device__ __forceinline__ BmFront box_muller_front(uint32_t w0, uint32_t w1, co
 
 __device__ __forceinline__ void box_muller_back(const BmFront& f, const FastMathSmem& sm, double& z0, double& z1) {
   const double r = f.r;
-  double p = fma(r, kFm.ln1p[4], kFm.ln1p[3]);
-  p = fma(r, p, kFm.ln1p[2]);
-  p = fma(r, p, kFm.ln1p[1]);
-  p = fma(r, p, kFm.ln1p[0]);
+  const double p = log1p_poly(r);
   const double t = fma(r * r, p, f.base - r);          // -ln u
-  // Angle phi = (pi/2)(A + 1/2) 2^-20: the top 7 bits of A pick one of 128 cells whose centre
-  // carries sqrt(2)*(sin, cos) in shared memory; the low 13 bits give the offset inside the cell,
-  // delta = (pi/2) t with |t| <= 2^-8, short enough for two 2-3 term polynomials (11 fp64
-  // operations instead of the 20 of a full-quadrant polynomial pair). The offset bits stay where
-  // they are (bits 10..22 of the low mantissa word): d = 1 + r 2^-42,
-  // t = (r + 1/2) 2^-20 - 2^-8 = d 2^22 - (2^22 + 2^-8 - 2^-21), exact.
-  const double2 sc = sm.sctab[(f.w1 >> 23) & 0x7Fu];
-  const double td = fma(__hiloint2double(0x3FF00000, (int)(f.w1 & 0x007FFC00u)), 4194304.0,
-                        -(4194304.0 + 0x1p-8 - 0x1p-21));
+  // Angle phi = (pi/2)(A + 1/2) 2^-20, A = bits 10..29 of w1: the top B = EBN_SC_TAB_BITS bits of A
+  // pick one of 2^B cells whose centre carries sqrt(2)*(sin, cos) in shared memory; the low 20-B
+  // bits give the offset inside the cell, delta = (pi/2) t with |t| <= 2^-(B+1), short enough for
+  // two 2-3 term polynomials (10-11 fp64 operations instead of the 20 of a full-quadrant pair).
+  // The offset bits stay where they are in the low mantissa word: d = 1 + r 2^-42,
+  // t = (r + 1/2) 2^-20 - 2^-(B+1) = d 2^22 - (2^22 + 2^-(B+1) - 2^-21), exact.
+  constexpr int B = EBN_SC_TAB_BITS;
+  constexpr uint32_t kOffsetMask = ((1u << (20 - B)) - 1u) << 10;
+  constexpr double kHalfCell = 1.0 / (double)(1 << (B + 1));
+  const double2 sc = sm.sctab[(f.w1 >> (30 - B)) & ((1u << B) - 1u)];
+  const double td = fma(__hiloint2double(0x3FF00000, (int)(f.w1 & kOffsetMask)), 4194304.0,
+                        -(4194304.0 + kHalfCell - 0x1p-21));
   const double w = td * td;
-  const double sd = td * fma(w, fma(w, kFm.sind[2], kFm.sind[1]), kFm.sind[0]);  // sin(delta)
+  double sd;
+  if (B < 10) sd = td * fma(w, fma(w, kFm.sind[B < 10 ? 2 : 1], kFm.sind[1]), kFm.sind[0]);  // sin(delta)
+  else sd = td * fma(w, kFm.sind[1], kFm.sind[0]);
   const double cm = w * fma(w, kFm.cosd[1], kFm.cosd[0]);                        // cos(delta) - 1
   const double cps = fma(sc.y, sd, fma(sc.x, cm, sc.x));    // sqrt(2) sin(phi)
   const double cms = fma(-sc.x, sd, fma(sc.y, cm, sc.y));   // sqrt(2) cos(phi)
