@@ -15,7 +15,7 @@ Layout
                   evaluate, reduce, dispatch) so the parity tests read like the reference's
 """
 from . import _lib  # noqa: F401
-from ._lib import (EbnError, Job, INPUT_DTYPE, make_inputs, pf_batch, hist_batch, eval_matrix,  # noqa: F401
+from ._lib import (EbnError, Job, INPUT_DTYPE, make_inputs, pf_batch, pf_batch_resumable, hist_batch, eval_matrix,  # noqa: F401
                    sample_matrix, peak_fp64, last_stats, init, shutdown, device_count)
 from .distributions import (Normal, LogNormal, Uniform, Gumbel, Gamma, Exponential, Truncated, truncated,  # noqa: F401
                             Tabulated, EmpiricalDistribution, distribution_parameters, Parameter,

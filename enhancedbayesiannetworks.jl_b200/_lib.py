@@ -300,6 +300,44 @@ def pf_batch(job: Job):
     return cnt, pf, var
 
 
+def pf_batch_resumable(job: Job, chunk: int, checkpoint: str, max_chunks: Optional[int] = None):
+    """A long ebn_pf_batch run in pieces of `chunk` samples per scenario with a checkpoint after every
+    piece: (seed, next sample offset, int64 counts) — a few KB even for 1e13 samples. A run that is
+    interrupted continues from the file; because every sample is a pure function of (seed, stream,
+    index), the final counts are bit-identical to one uninterrupted call (SURVEY.md §5
+    checkpoint / resume). Returns (fail_count, pf, var, done): done is False when `max_chunks`
+    stopped the run early."""
+    import dataclasses
+    import json
+    S, n, first = job.S, job.n, job.sample_offset
+    state = {"seed": int(job.seed), "limit_state": int(job.limit_state), "S": S, "n": n, "first": first,
+             "next": first, "counts": [0] * S}
+    if os.path.exists(checkpoint):
+        with open(checkpoint) as f:
+            saved = json.load(f)
+        same = all(saved.get(k) == state[k] for k in ("seed", "limit_state", "S", "n", "first"))
+        if not same:
+            raise ValueError(f"{checkpoint} belongs to a different job")
+        state = saved
+    counts = np.asarray(state["counts"], dtype=np.int64)
+    done_chunks = 0
+    while state["next"] < first + n and (max_chunks is None or done_chunks < max_chunks):
+        m = min(chunk, first + n - state["next"])
+        piece = dataclasses.replace(job, n=m, sample_offset=state["next"])
+        counts = counts + pf_batch(piece)[0]
+        state["next"] += m
+        state["counts"] = [int(c) for c in counts]
+        tmp = checkpoint + ".tmp"
+        with open(tmp, "w") as f:
+            json.dump(state, f)
+        os.replace(tmp, checkpoint)
+        done_chunks += 1
+    finished = state["next"] >= first + n
+    seen = state["next"] - first
+    pf = counts / max(seen, 1)
+    return counts, pf, (pf - pf * pf) / max(seen, 1), finished
+
+
 def hist_batch(job: Job, edges):
     """ebn_hist_batch → (counts int64[S, nedges+1], sum f64[S], sumsq f64[S])."""
     ensure_init()

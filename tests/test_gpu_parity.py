@@ -439,6 +439,22 @@ def test_sharding_and_offsets_are_count_invariant(ebn):
     assert len(set(c2.tolist())) == 1 and c2[0] == c0[0]
 
 
+def test_checkpointed_run_equals_one_call(ebn, tmp_path):
+    """SURVEY §5 checkpoint/resume: a run cut into pieces, interrupted and continued from its
+    checkpoint file ends with exactly the counts of one uninterrupted call."""
+    from ebn_b200 import workloads as W
+    job = W.w1_vehicle(n=1_000_003)
+    whole = ebn.pf_batch(job)[0]
+    ck = str(tmp_path / "w1.ckpt.json")
+    cnt, pf, var, done = ebn.pf_batch_resumable(job, 300_000, ck, max_chunks=2)     # "interrupted" after 2 pieces
+    assert not done and np.all(cnt <= whole)
+    cnt, pf, var, done = ebn.pf_batch_resumable(job, 300_000, ck)                   # picks the file up
+    assert done and np.array_equal(cnt, whole) and np.array_equal(pf, whole / job.n)
+    other = W.w1_vehicle(n=1_000_003, seed=5)
+    with pytest.raises(ValueError, match="different job"):
+        ebn.pf_batch_resumable(other, 300_000, ck)
+
+
 def test_tiny_and_ragged_sizes(ebn):
     from ebn_b200 import workloads as W
     for n in (1, 2, 3, 255, 256, 257, 511, 513):
