@@ -744,6 +744,17 @@ int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, i
   g.stats.devices = (int)nd;
   g.stats.specialised = P.plan_class >= PLAN_STATIC0 || !P.jit_spec.kinds.empty();
   g.stats.jit_compiles = P.jit_compiles;
+  if (getenv("EBN_TRACE")) {  // one line per call on stderr: which kernel path ran, how long
+    const LsInfo* li = ls_info(job->limit_state);
+    fprintf(stderr,
+            "[ebncuda] %s %s S=%d d=%d n=%lld plan=%s%s%s strict=%d devices=%zu blocks=%d items/scenario=%lld "
+            "kernel=%.3f ms compiled=%d\n",
+            mode == 0 ? "pf_batch" : "hist_batch", li ? li->name : "?", S, job->n_inputs, (long long)job->n_per_scenario,
+            P.plan_class == PLAN_COPULA ? "copula" : P.plan_class >= PLAN_STATIC0 ? "compile-time" : "runtime-dispatched",
+            P.jit ? (P.jit_spec.kinds.empty() ? " (run-time compiled functor)" : " (run-time compiled)") : "",
+            (job->flags & EBN_JOB_FP32_SAMPLING) ? " fp32-sampling" : "", job->strict ? 1 : 0, nd, blocks[0],
+            (long long)P.items_per_scenario, kms, P.jit_compiles);
+  }
   return EBN_OK;
 }
 
