@@ -99,8 +99,15 @@ def _lower_expression(models: List[Model], performance, input_names: List[str]) 
     return Lowered(L.LS_EXPRESSION, prog.consts, list(input_names), hidden, prog.columns)
 
 
-def lower(models: Sequence[Model], performance, input_names: Sequence[str]) -> Lowered:
-    """Maps a model chain (+ performance) onto a device limit state."""
+# A polynomial chain runs through the interpreted PolynomialProgram functor and the runtime-dispatched
+# sampling plan (7.6e10 samples/s on A + B); the same chain as a formula compiles into a kernel with a
+# compile-time plan (4.2e11, profiles/r01_t_workloads.txt). Compiling costs ~0.4 s once: worth it above:
+JIT_POLY_MIN_SAMPLES = 5e10
+
+
+def lower(models: Sequence[Model], performance, input_names: Sequence[str], prefer_expression: bool = False) -> Lowered:
+    """Maps a model chain (+ performance) onto a device limit state. `prefer_expression`: send a
+    polynomial chain through the run-time compiled path too (large jobs)."""
     models = list(models)
     seen, uniq = set(), []
     for m in models:  # transmission may hand the same model twice (reference quirk, transmission.jl:13)
@@ -112,6 +119,8 @@ def lower(models: Sequence[Model], performance, input_names: Sequence[str]) -> L
     if any(isinstance(m.func, Expression) for m in models) or isinstance(performance, Expression):
         return _lower_expression(models, performance, input_names)
     if all(isinstance(m.func, Poly) for m in models) and (performance is None or isinstance(performance, (Poly, str))):
+        if prefer_expression and models:
+            return _lower_expression(models, performance, input_names)
         stages = [m.func for m in models]
         names = [m.name for m in models]
         if isinstance(performance, Poly):
@@ -285,7 +294,8 @@ def _is_imprecise(i) -> bool:
 
 def pf_scenarios(models, performance, scenario_inputs, sim: CudaMonteCarlo):
     """All scenarios of a node in one ebn_pf_batch call → (pf[S], std[S], [Samples])."""
-    low = lower(models, performance, input_names(scenario_inputs[0]))
+    big = len(scenario_inputs) * float(sim.n) >= JIT_POLY_MIN_SAMPLES and L.jit_available()
+    low = lower(models, performance, input_names(scenario_inputs[0]), prefer_expression=big)
     job = build_job(low, scenario_inputs, sim)
     cnt, pf, var = L.pf_batch(job)
     return pf, np.sqrt(var), [Samples(job, s, low.out_columns) for s in range(job.S)], cnt
@@ -536,7 +546,8 @@ def random_slicing(models, performance, scenario_inputs, sim: CudaRandomSlicing)
 def output_histograms(models, scenario_inputs, sim: CudaMonteCarlo, edges: Optional[np.ndarray] = None):
     """`sample` + `evaluate!` for a ContinuousFunctionalNode: per-scenario histogram and moments of
     the last model's output. Without `edges`, a pilot call finds the output range."""
-    low = lower(models, None, input_names(scenario_inputs[0]))
+    big = len(scenario_inputs) * float(sim.n) >= JIT_POLY_MIN_SAMPLES and L.jit_available()
+    low = lower(models, None, input_names(scenario_inputs[0]), prefer_expression=big)
     job = build_job(low, scenario_inputs, sim)
     if edges is None:
         pilot = L.Job(job.limit_state, job.consts, job.inputs, min(job.n, 1 << 16), job.seed, job.strict,

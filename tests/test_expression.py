@@ -175,6 +175,13 @@ def test_lowering_of_expression_models():
     X = np.random.default_rng(0).normal(0, 1, (1000, 3))
     g = replay.g_expression(X, low2.consts)
     assert np.array_equal(g, np.sqrt(np.abs(X[:, 0] + X[:, 1])) * X[:, 2])
+    # a polynomial chain can be sent down the same road (what pf_scenarios does for large jobs)
+    chain = [Model(Poly([(1, ["A"]), (1, ["B"])]), "C")]
+    lp = lower(chain, Poly([(2, []), (-1, ["C"])]), ["A", "B"])
+    le = lower(chain, Poly([(2, []), (-1, ["C"])]), ["A", "B"], prefer_expression=True)
+    assert lp.limit_state == L.LS_POLYNOMIAL and le.limit_state == L.LS_EXPRESSION and lp.out_columns == le.out_columns
+    Xp = np.random.default_rng(1).normal(0, 1, (1000, 2))
+    assert np.array_equal(replay.g_expression(Xp, le.consts), replay.g_polynomial(Xp, lp.consts))
     with pytest.raises(UnsupportedModel, match="two different values"):
         lower([Model(Expression("df.A * k", k=1.0), "C")], Expression("df.C - k", k=2.0), ["A"])
     with pytest.raises(UnsupportedModel, match="unknown name"):

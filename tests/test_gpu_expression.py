@@ -242,6 +242,22 @@ def test_random_formulas_against_the_oracle(ebn):
         assert bad.mean() < 0.01, (trial, float(bad.mean()), models, perf)
 
 
+def test_large_polynomial_jobs_take_the_compiled_road(ebn):
+    """uq.pf_scenarios sends a polynomial chain through the run-time compiled path once the job is
+    large enough to repay the compilation: same anchor (Phi(-1)), 5x the throughput."""
+    from ebn_b200 import uq
+    E = ebn
+    models = [E.Model(E.Poly([(1, ["A"]), (1, ["B"])]), "C")]
+    perf = E.Poly([(2, []), (-1, ["C"])])
+    inputs = [E.Parameter(1.0, "A"), E.RandomVariable(E.Normal(), "B")]
+    pf, sd, smp = E.probability_of_failure(models, perf, inputs, E.MonteCarlo(int(uq.JIT_POLY_MIN_SAMPLES)))
+    st = ebn.last_stats()
+    assert st["specialised"] == 1 and smp.job.limit_state == ebn._lib.LS_EXPRESSION
+    assert abs(pf - 0.15865525393145707) < 5 * sd
+    pf_small, _, smp_small = E.probability_of_failure(models, perf, inputs, E.MonteCarlo(100_000))
+    assert smp_small.job.limit_state == ebn._lib.LS_POLYNOMIAL and abs(pf_small - 0.158655) < 0.006
+
+
 def test_expression_errors(ebn):
     from ebn_b200 import expr
     L = ebn._lib

@@ -79,3 +79,7 @@ rows = [[(0, a, 0, 0, 0, -np.inf, np.inf), (1, 0.0, 1.0, 0, 0, -np.inf, np.inf)]
 hj = ebn_b200.Job(ebn_b200._lib.LS_POLYNOMIAL, prog, ebn_b200.make_inputs(rows), n=10**8, seed=3)
 run("histogram path A+B, 2048 edges, 20 scenarios", hj, hist_edges=np.linspace(-8, 11, 1025))
 run("count path A+B (polynomial functor, generic plan)", hj)
+ab = expr.compile_program(["A", "B"], [("C", "df.A .+ df.B")], "df.C")
+ej = ebn_b200.Job(ebn_b200._lib.LS_EXPRESSION, ab.consts, hj.inputs, n=10**8, seed=3)
+run("histogram path A+B as a formula (run-time compiled)", ej, hist_edges=np.linspace(-8, 11, 1025))
+run("count path A+B as a formula (run-time compiled)", ej)
