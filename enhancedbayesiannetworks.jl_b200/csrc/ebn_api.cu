@@ -635,10 +635,78 @@ int allreduce(std::vector<void*>& i64, size_t n_i64, std::vector<void*>& f64, si
   return EBN_OK;
 }
 
-int run_batch(const ebn_job_t* job, int mode, const double* edges, int nedges, int64_t* counts_out,
+// The interpreted coefficient-table functors (PolynomialProgram, MinAffine) are the road that needs no
+// NVRTC, not the fast one: the same limit state as an expression program compiles into straight-line
+// code with a compile-time sampling plan (C = A + B: 7.6e10 -> 4.2e11 samples/s). Large batches are
+// therefore rewritten into EBN_LS_EXPRESSION here, instruction for instruction in the functor's own
+// evaluation order, so strict results do not change. Returns false when the job stays as it is.
+constexpr double kJitFunctorMinSamples = 5e10;
+
+bool rewrite_as_expression(const ebn_job_t* job, std::vector<double>& out) {
+  if (job->limit_state != EBN_LS_POLYNOMIAL && job->limit_state != EBN_LS_MIN_AFFINE) return false;
+  if (job->flags & EBN_JOB_NO_JIT_PLAN) return false;
+  if ((double)job->n_per_scenario * job->n_scenarios < kJitFunctorMinSamples && !(job->flags & EBN_JOB_JIT_PLAN)) return false;
+  if (check_limit_state(job->limit_state, job->consts, job->n_consts, job->n_inputs) != EBN_OK) return false;
+  if (!jit_available(nullptr)) return false;
+  const double* k = job->consts;
+  const int d = job->n_inputs;
+  std::vector<double> code;
+  auto emit = [&](int op, double arg) { code.push_back((double)op); code.push_back(arg); };
+  if (job->limit_state == EBN_LS_POLYNOMIAL) {
+    const int T = (int)k[0];
+    if (d + T - 1 > EBN_MAX_INPUTS) return false;
+    int pos = 1;
+    for (int t = 0; t < T; ++t) {
+      const int nt = (int)k[pos++];
+      for (int q = 0; q < nt; ++q) {
+        emit(EBN_OP_CONST, k[pos++]);                       // term = coef
+        const int nf = (int)k[pos++];
+        for (int f = 0; f < nf; ++f) {                      // term = term * x[col]
+          emit(EBN_OP_INPUT, k[pos++]);
+          emit(EBN_OP_MUL, 0.0);
+        }
+        if (q > 0) emit(EBN_OP_ADD, 0.0);                   // acc = acc + term
+      }
+      if (t + 1 < T) emit(EBN_OP_STORE, 0.0);               // a model column; the last stage is g
+    }
+  } else {
+    const int K = (int)k[0];
+    for (int r = 0; r < K; ++r) {
+      const double* row = k + 1 + (size_t)r * (1 + d);
+      emit(EBN_OP_CONST, row[0]);
+      for (int j = 0; j < d; ++j) {
+        if (row[1 + j] == 0.0 && !job->strict) continue;    // 0 * x only matters for the bit pattern
+        emit(EBN_OP_CONST, row[1 + j]);
+        emit(EBN_OP_INPUT, (double)j);
+        emit(EBN_OP_MUL, 0.0);
+        emit(EBN_OP_ADD, 0.0);
+      }
+      if (r > 0) emit(EBN_OP_MIN, 0.0);
+    }
+  }
+  if (code.size() / 2 > EBN_EXPR_MAX_OPS) return false;
+  out.clear();
+  out.push_back(0.0);
+  out.push_back((double)(code.size() / 2));
+  out.insert(out.end(), code.begin(), code.end());
+  return expr_check(out.data(), (int)out.size(), d, nullptr).empty();
+}
+
+int run_batch(const ebn_job_t* job_in, int mode, const double* edges, int nedges, int64_t* counts_out,
               double* sum_out, double* sumsq_out) {
   int rc = require_ready();
   if (rc) return rc;
+  if (!job_in) return fail(EBN_EINVAL, "job is NULL");
+  ebn_job_t rewritten;
+  std::vector<double> program;
+  const ebn_job_t* job = job_in;
+  if (rewrite_as_expression(job_in, program)) {
+    rewritten = *job_in;
+    rewritten.limit_state = EBN_LS_EXPRESSION;
+    rewritten.consts = program.data();
+    rewritten.n_consts = (int32_t)program.size();
+    job = &rewritten;
+  }
   Prepared P;
   if ((rc = prepare(job, mode, P))) return rc;
   const int S = job->n_scenarios;
@@ -1091,6 +1159,16 @@ int64_t ebn_expression_source(const double* consts, int n_consts, int d, char* b
 
 int ebn_jit_compile(const ebn_job_t* job, int role, int64_t* cubin_bytes) {
   if (role < 0 || role > 2) return fail(EBN_EINVAL, "role must be 0 (count), 1 (histogram) or 2 (replay)");
+  if (!job) return fail(EBN_EINVAL, "job is NULL");
+  ebn_job_t rewritten;
+  std::vector<double> program;
+  if (role != 2 && rewrite_as_expression(job, program)) {  // what ebn_pf_batch / ebn_hist_batch would run
+    rewritten = *job;
+    rewritten.limit_state = EBN_LS_EXPRESSION;
+    rewritten.consts = program.data();
+    rewritten.n_consts = (int32_t)program.size();
+    job = &rewritten;
+  }
   Prepared P;
   int rc = prepare(job, role == 1 ? 1 : 0, P, 1);  // host logic only
   if (rc) return rc;

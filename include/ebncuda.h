@@ -169,10 +169,13 @@ typedef struct ebn_input {
 
 /* job->flags */
 #define EBN_JOB_COPULA_SHARED 1u /* corr_chol is one [d*d] block for all scenarios */
-#define EBN_JOB_JIT_PLAN 4u      /* compile the job's sampling plan into the kernel at run time
-                                    even for a small job (default: only when the job is large
-                                    enough to repay ~1 s of compilation)                    */
-#define EBN_JOB_NO_JIT_PLAN 8u   /* never do that: use the runtime-dispatched sampling plan    */
+#define EBN_JOB_JIT_PLAN 4u      /* compile the job's sampling plan into the kernel at run time even for
+                                    a small job, and run the polynomial / min-affine functors as
+                                    compiled expression programs instead of interpreting their
+                                    coefficient tables (default: only when the job is large enough to
+                                    repay ~1 s of compilation: 5e10 samples for the two functors,
+                                    1e11 for a sampling plan alone). Strict results do not change.  */
+#define EBN_JOB_NO_JIT_PLAN 8u   /* never do that: runtime-dispatched plan, interpreted functors     */
 #define EBN_JOB_FP32_SAMPLING 16u /* "FP32 where tolerated": untruncated (Log)Normal inputs are drawn with
                                     the Box-Muller transform evaluated in fp32 (same random words; each
                                     normal agrees with the fp64 draw to ~1e-6 sigma, tail to 6.7 sigma);

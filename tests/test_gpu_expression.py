@@ -242,6 +242,39 @@ def test_random_formulas_against_the_oracle(ebn):
         assert bad.mean() < 0.01, (trial, float(bad.mean()), models, perf)
 
 
+def test_library_rewrites_coefficient_table_functors(ebn):
+    """Inside the library, polynomial and min-affine batches that are large (or ask for it) are rewritten
+    into expression programs instruction for instruction: strict counts and histograms do not change."""
+    from test_gpu_parity import poly_program
+    rng = np.random.default_rng(5)
+    rows = [[(1, float(rng.normal()), 1.0 + float(rng.random()), 0, 0, -INF, INF), (3, -1.0, 2.0, 0, 0, -INF, INF),
+             (0, 0.3 * s, 0, 0, 0, -INF, INF)] for s in range(4)]
+    inputs = ebn.make_inputs(rows)
+    prog = poly_program([[(1.0, [0, 0]), (-0.7, []), (1.0, [1])], [(0.5, [3, 2]), (2.0, [0])], [(1.0, [4]), (-1.25, [])]])
+    n = 300_001
+    a = ebn.Job(ebn._lib.LS_POLYNOMIAL, prog, inputs, n=n, seed=8, strict=True, jit_plan=False)
+    b = ebn.Job(ebn._lib.LS_POLYNOMIAL, prog, inputs, n=n, seed=8, strict=True, jit_plan=True)
+    ca = ebn.pf_batch(a)[0]
+    assert ebn.last_stats()["specialised"] == 0
+    cb = ebn.pf_batch(b)[0]
+    assert ebn.last_stats()["specialised"] == 1
+    assert np.array_equal(ca, cb) and 0 < ca.min() and ca.max() < n
+    edges = np.linspace(-6, 10, 65)
+    ha, hb = ebn.hist_batch(a, edges), ebn.hist_batch(b, edges)
+    assert np.array_equal(ha[0], hb[0]) and np.allclose(ha[1], hb[1], rtol=1e-12)
+    k = np.array([2.0, 0.5, 1.0, 0.0, -2.0, -0.25, 0.0, 1.5, 1.0])
+    c = ebn.Job(ebn._lib.LS_MIN_AFFINE, k, inputs, n=n, seed=8, strict=True, jit_plan=False)
+    d = ebn.Job(ebn._lib.LS_MIN_AFFINE, k, inputs, n=n, seed=8, strict=True, jit_plan=True)
+    assert np.array_equal(ebn.pf_batch(c)[0], ebn.pf_batch(d)[0])
+    assert ebn.last_stats()["specialised"] == 1
+    # and the automatic case: a batch above the threshold
+    big = ebn.Job(ebn._lib.LS_POLYNOMIAL, prog, inputs[:1], n=6 * 10**10, seed=8)
+    cnt, pf, var = ebn.pf_batch(big)
+    st = ebn.last_stats()
+    assert st["specialised"] == 1 and st["kernel_ms"] < 1000.0
+    assert abs(pf[0] - ca[0] / n) < 5 * math.sqrt(ca[0] / n * (1 - ca[0] / n) / n)
+
+
 def test_large_polynomial_jobs_take_the_compiled_road(ebn):
     """uq.pf_scenarios sends a polynomial chain through the run-time compiled path once the job is
     large enough to repay the compilation: same anchor (Phi(-1)), 5x the throughput."""

@@ -39,11 +39,8 @@ w3 = W.w3_straub_copula(n=2 * 10**7)
 w3.jit_plan = False
 run("W3 Straub-style copula, 64 scenarios (looping copula plan)", w3)
 w3.jit_plan = True
-run("W3 copula, plan unrolled at run time", w3)
+run("W3 copula compiled at run time (unrolled plan, coefficient table rewritten as a formula)", w3)
 from ebn_b200 import expr  # noqa: E402
-w3p = expr.compile_program(["r1", "r2", "r3", "r4", "r5", "V", "H"], [], "min(r1 + r2 + r4 + r5 - 5 * H, r2 + 2 * r3 + r4 - 5 * V, r1 + 2 * r3 + 2 * r4 + r5 - 5 * H - 5 * V)")
-run("W3 copula, unrolled plan + frame mechanisms as a formula",
-    ebn_b200.Job(ebn_b200._lib.LS_EXPRESSION, w3p.consts, w3.inputs, n=w3.n, seed=w3.seed, corr_chol=w3.corr_chol, tables=w3.tables))
 run("W5 vehicle grid, 1024 scenarios", W.w5_vehicle_grid(n=4 * 10**6))
 run("W4 vehicle, V fixed: 4 states x 25 outer-loop values", W.w4_vehicle_fixed_v(np.linspace(7, 12, 25), n=2 * 10**7))
 j = W.w1_vehicle(n=10**8)
@@ -76,10 +73,9 @@ run("W2 Straub, closures as text (run-time compiled, fast)",
     ebn_b200.Job(ebn_b200._lib.LS_EXPRESSION, sp.consts, w2.inputs, n=10**9, seed=w2.seed))
 prog = np.array([1, 2, 1.0, 1, 0, 1.0, 1, 1])
 rows = [[(0, a, 0, 0, 0, -np.inf, np.inf), (1, 0.0, 1.0, 0, 0, -np.inf, np.inf)] for a in np.linspace(0, 3, 20)]
-hj = ebn_b200.Job(ebn_b200._lib.LS_POLYNOMIAL, prog, ebn_b200.make_inputs(rows), n=10**8, seed=3)
+hj = ebn_b200.Job(ebn_b200._lib.LS_POLYNOMIAL, prog, ebn_b200.make_inputs(rows), n=10**8, seed=3, jit_plan=False)
 run("histogram path A+B, 2048 edges, 20 scenarios", hj, hist_edges=np.linspace(-8, 11, 1025))
 run("count path A+B (polynomial functor, generic plan)", hj)
-ab = expr.compile_program(["A", "B"], [("C", "df.A .+ df.B")], "df.C")
-ej = ebn_b200.Job(ebn_b200._lib.LS_EXPRESSION, ab.consts, hj.inputs, n=10**8, seed=3)
-run("histogram path A+B as a formula (run-time compiled)", ej, hist_edges=np.linspace(-8, 11, 1025))
-run("count path A+B as a formula (run-time compiled)", ej)
+hj.jit_plan = True   # what the library does on its own above 5e10 samples: the program rewritten as a formula
+run("histogram path A+B, polynomial program compiled at run time", hj, hist_edges=np.linspace(-8, 11, 1025))
+run("count path A+B, polynomial program compiled at run time", hj)
