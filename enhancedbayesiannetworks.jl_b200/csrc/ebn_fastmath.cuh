@@ -56,7 +56,9 @@ __device__ __forceinline__ void fastmath_init(FastMathSmem& sm, int tid, int nth
 __device__ __forceinline__ int log_cell(int hi) { return (hi >> (20 - EBN_LOG_TAB_BITS)) & ((1 << EBN_LOG_TAB_BITS) - 1); }
 __device__ __forceinline__ double log1p_poly(double r) {
   if (EBN_LOG_TAB_BITS >= 10) {      // |r| <= 2^-11: the r^5/5 term is below 6e-18
-    return fma(r, fma(r, kFm.ln1p[2], kFm.ln1p[1]), kFm.ln1p[0]);
+    // 1/4 and 1/2 as literals: their low 32 bits are zero, so they are instruction immediates and
+    // only -1/3 comes from the constant bank (two bank operands in one DFMA would cost an LDC)
+    return fma(r, fma(r, 0.25, kFm.ln1p[1]), 0.5);
   } else {
     double p = fma(r, kFm.ln1p[4], kFm.ln1p[3]);
     p = fma(r, p, kFm.ln1p[2]);
