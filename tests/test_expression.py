@@ -163,6 +163,25 @@ def test_run_time_compilation_without_a_device():
     assert L.jit_compile(mixed, 0) == 0
 
 
+def test_coefficient_table_functors_compile_as_formulas_when_asked():
+    """The library rewrites polynomial / min-affine batches into expression programs (large batches, or
+    EBN_JOB_JIT_PLAN): visible without a GPU through ebn_jit_compile."""
+    if not L.jit_available():
+        pytest.skip("libnvrtc not loadable here")
+    rows = [[(1, 0.0, 1.0, 0, 0, -INF, INF), (3, -1.0, 2.0, 0, 0, -INF, INF)]]
+    prog = np.array([2, 3, 1.0, 2, 0, 0, -0.7, 0, 1.0, 1, 1, 2, 2.0, 0, -1.0, 1, 2], dtype=float)  # x0^2 - 0.7 + x1 ; 2 - col2
+    small = L.Job(L.LS_POLYNOMIAL, prog, L.make_inputs(rows), n=1000)
+    assert L.jit_compile(small, 0) == 0                         # interpreted functor, runtime-dispatched plan
+    asked = L.Job(L.LS_POLYNOMIAL, prog, L.make_inputs(rows), n=1000, jit_plan=True)
+    assert L.jit_compile(asked, 0) > 10_000 and L.jit_compile(asked, 1) > 10_000
+    large = L.Job(L.LS_POLYNOMIAL, prog, L.make_inputs(rows), n=6 * 10**10)
+    assert L.jit_compile(large, 0) > 10_000
+    large.jit_plan = False
+    assert L.jit_compile(large, 0) == 0
+    k = np.array([2.0, 0.5, 1.0, 0.0, -2.0, -0.25, 1.5])
+    assert L.jit_compile(L.Job(L.LS_MIN_AFFINE, k, L.make_inputs(rows), n=1000, jit_plan=True), 0) > 10_000
+
+
 def test_lowering_of_expression_models():
     from ebn_b200 import Expression, Model, Poly
     from ebn_b200.uq import UnsupportedModel, lower
