@@ -179,8 +179,20 @@ std::string expr_codegen(const double* consts, int n_consts, int d) {
       case EBN_OP_NEG: apply({a}, [](const std::vector<std::string>& n) { return "-(" + n[0] + ")"; }); break;
       case EBN_OP_ABS: apply({a}, call1("fabs")); break;
       case EBN_OP_SQRT: apply({a}, call1("Ops::sqrt")); break;
-      case EBN_OP_EXP: apply({a}, call1("exp")); break;
-      case EBN_OP_LOG: apply({a}, call1("log")); break;
+      // per-sample exp / log take the lean table-driven versions outside strict mode; a constant
+      // operand is evaluated in setup(), before the shared-memory tables exist: plain library call
+      case EBN_OP_EXP:
+        if (a.inv) apply({a}, call1("exp"));
+        else apply({a}, [](const std::vector<std::string>& n) {
+          return "(Ops::strict ? exp(" + n[0] + ") : exp_guarded(" + n[0] + ", *c.sm))";
+        });
+        break;
+      case EBN_OP_LOG:
+        if (a.inv) apply({a}, call1("log"));
+        else apply({a}, [](const std::vector<std::string>& n) {
+          return "(Ops::strict ? log(" + n[0] + ") : log_guarded(" + n[0] + ", *c.sm))";
+        });
+        break;
       case EBN_OP_SIN: apply({a}, call1("sin")); break;
       case EBN_OP_COS: apply({a}, call1("cos")); break;
       case EBN_OP_MIN: apply({a, b}, call2("Ops::min")); break;
@@ -220,8 +232,10 @@ std::string expr_codegen(const double* consts, int n_consts, int d) {
   s += fmt("  static constexpr int D = %d;\n", d);
   s += fmt("  static constexpr int XCAP = %d;\n", d + I.n_store);
   s += "  static constexpr int NC = -1;\n";
-  s += fmt("  struct Ctx { double k[%d]; double h[%d]; };\n", I.n_params > 0 ? I.n_params : 1, nh > 0 ? nh : 1);
-  s += "  __device__ static void setup(Ctx& c, const double* k, int, int, const FastMathSmem*) {\n";
+  s += fmt("  struct Ctx { double k[%d]; double h[%d]; const FastMathSmem* sm; };\n", I.n_params > 0 ? I.n_params : 1,
+           nh > 0 ? nh : 1);
+  s += "  __device__ static void setup(Ctx& c, const double* k, int, int, const FastMathSmem* sm) {\n";
+  s += "    c.sm = sm;\n";
   s += fmt("#pragma unroll\n    for (int i = 0; i < %d; ++i) c.k[i] = k[2 + i];\n", I.n_params);
   s += setup;
   s += "  }\n";

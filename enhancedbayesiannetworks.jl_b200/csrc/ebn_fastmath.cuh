@@ -128,6 +128,15 @@ __device__ __forceinline__ double exp_fast(double x, const FastMathSmem& sm) {
   return __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
 }
 
+// exp / log for callers that cannot promise the lean versions' domain (generated functors in fast
+// mode): the lean path inside it, the CUDA library outside (rare, warp-divergent only there).
+__device__ __forceinline__ double exp_guarded(double x, const FastMathSmem& sm) {
+  return fabs(x) < 700.0 ? exp_fast(x, sm) : exp(x);
+}
+__device__ __forceinline__ double log_guarded(double x, const FastMathSmem& sm) {
+  return (x > 0x1p-1000 && x < 0x1p1000) ? -neg_log_pos(x, sm) : log(x);
+}
+
 // sqrt(t) for t in [2^-60, 2^60]: MUFU.RSQ64H seed y ~ t^-1/2 (relative error e0 ~ 2^-20),
 // then one third-order correction: with a = t*y and e = 1 - a*y,
 //   sqrt(t) = a / sqrt(1 - e) = a * (1 + e/2 + 3 e^2/8 + O(e^3)),   truncation 5 e^3/16 < 2^-58.

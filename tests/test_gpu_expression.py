@@ -92,9 +92,21 @@ def test_expression_all_opcodes_against_oracle(ebn):
                                   "w - abs(a)^1.5 - b^5 / 100 + c^-2", params={})
     X2 = rng.normal(0, 2, (50_000, 3))
     _, want = ocpu.eval_matrix(ocpu.LS_EXPRESSION, transc.consts, X2, want_g=True)
+    want_t = want
     _, got = ebn.eval_matrix(ebn._lib.LS_EXPRESSION, transc.consts, X2, strict=True, want_g=True)
     err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
     assert np.max(err) < 1e-12, np.max(err)
+    # fast mode: per-sample exp / log go through the lean table-driven versions (guarded outside their
+    # domain), a constant operand through the library call in setup()
+    wide = expr.compile_program(["a", "b", "c"], [("w", "exp(a * 200) + log(abs(b) * 1e-200 + 1e-320) + exp(k) * log(k + 2)")],
+                                "w / (1 + abs(w)) - c / 8", params={"k": 0.75})
+    _, want = ocpu.eval_matrix(ocpu.LS_EXPRESSION, wide.consts, X2, want_g=True)
+    _, got = ebn.eval_matrix(ebn._lib.LS_EXPRESSION, wide.consts, X2, strict=False, want_g=True)
+    ok = np.isfinite(want)
+    assert ok.mean() > 0.9 and np.array_equal(np.isfinite(got), ok)
+    assert np.max(np.abs(got[ok] - want[ok])) < 1e-12
+    _, got_fast = ebn.eval_matrix(ebn._lib.LS_EXPRESSION, transc.consts, X2, strict=False, want_g=True)
+    assert np.max(np.abs(got_fast - want_t) / np.maximum(1.0, np.abs(want_t))) < 1e-11
 
 
 def test_expression_reference_toy_models(ebn):
