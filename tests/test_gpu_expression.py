@@ -254,6 +254,40 @@ def test_random_formulas_against_the_oracle(ebn):
         assert bad.mean() < 0.01, (trial, float(bad.mean()), models, perf)
 
 
+def test_random_jobs_end_to_end(ebn):
+    """Everything at once, randomised: random marginal rows (same kinds in every scenario or not), a
+    random formula chain over them, odd sample counts, a resume offset. The fused count of every
+    scenario equals the oracle's count on the replayed matrix, the shards of a 3-rank job add up to the
+    whole, and the histogram of g over the whole real line holds every sample."""
+    import dataclasses
+    from ebn_b200 import expr
+    from test_gpu_parity import _random_marginal
+    rng = np.random.default_rng(9001)
+    for trial in range(8):
+        d = int(rng.integers(2, 6))
+        base = [_random_marginal(rng) for _ in range(d)]
+        rows = [base, base, [_random_marginal(rng) for _ in range(d)] if trial % 2 else base]
+        names = [f"x{j}" for j in range(d)]
+        consts = {"k0": float(rng.normal(0, 2))}
+        models = [("m0", _random_formula(rng, names, list(consts), 3))]
+        perf = _random_formula(rng, names + ["m0"], list(consts), 3)
+        prog = expr.compile_program(names, models, perf, consts)
+        n = int(rng.integers(20_000, 60_000)) | 1
+        job = ebn.Job(ebn._lib.LS_EXPRESSION, prog.consts, ebn.make_inputs(rows), n=n, seed=int(rng.integers(1, 2**60)),
+                      strict=True, sample_offset=int(rng.choice([0, 7, 2**34 + 3])))
+        cnt = ebn.pf_batch(job)[0]
+        assert ebn.last_stats()["specialised"] == (0 if trial % 2 else 1)
+        for s in range(3):
+            X = ebn.sample_matrix(job, s, job.sample_offset, n)
+            assert int(cnt[s]) == ocpu.eval_matrix(ocpu.LS_EXPRESSION, prog.consts, X), (trial, s, models, perf)
+        parts = sum(ebn.pf_batch(dataclasses.replace(job, shard_rank=r, shard_world=3, partial=True))[0] for r in range(3))
+        assert np.array_equal(parts, cnt)
+        h = ebn.hist_batch(job, np.array([0.0]))[0]
+        assert np.all(h.sum(axis=1) == n) and np.all(h[:, 0] <= n)
+        # bin 0 = g < 0 (NaN lands in the last bin): the histogram and the count path agree
+        assert np.array_equal(h[:, 0], cnt)
+
+
 def test_library_rewrites_coefficient_table_functors(ebn):
     """Inside the library, polynomial and min-affine batches that are large (or ask for it) are rewritten
     into expression programs instruction for instruction: strict counts and histograms do not change."""
