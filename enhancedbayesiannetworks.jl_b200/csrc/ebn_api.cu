@@ -645,7 +645,10 @@ constexpr double kJitFunctorMinSamples = 5e10;
 bool rewrite_as_expression(const ebn_job_t* job, std::vector<double>& out) {
   if (job->limit_state != EBN_LS_POLYNOMIAL && job->limit_state != EBN_LS_MIN_AFFINE) return false;
   if (job->flags & EBN_JOB_NO_JIT_PLAN) return false;
-  if ((double)job->n_per_scenario * job->n_scenarios < kJitFunctorMinSamples && !(job->flags & EBN_JOB_JIT_PLAN)) return false;
+  const char* env = getenv("EBN_JIT_PLAN");  // "0": never, "1": always (experiments), as for sampling plans
+  if (env && env[0] == '0') return false;
+  const bool asked = (job->flags & EBN_JOB_JIT_PLAN) || (env && env[0] == '1');
+  if ((double)job->n_per_scenario * job->n_scenarios < kJitFunctorMinSamples && !asked) return false;
   if (check_limit_state(job->limit_state, job->consts, job->n_consts, job->n_inputs) != EBN_OK) return false;
   if (!jit_available(nullptr)) return false;
   const double* k = job->consts;
