@@ -111,7 +111,8 @@ enum {
  * Strict mode executes one IEEE operation per instruction in program order, which is Julia's
  * evaluation order when the wrapper emits the expression tree in post-order; sqrt/log of a
  * negative number gives NaN (a safe sample) where Julia would throw a DomainError.
- * exp, log, sin, cos and pow are within 1-2 ulp of Julia's, not bit-identical.
+ * exp, log, sin, cos and pow are within 1-2 ulp of Julia's, not bit-identical. min / max of two
+ * zeros of opposite sign return the first operand (Julia orders -0.0 below 0.0); `g < 0` cannot tell.
  */
 enum {
   EBN_OP_INPUT = 0,   /* push column `operand` (an input or an already stored column)        */
