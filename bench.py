@@ -264,6 +264,9 @@ def main():
                 "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": DRAM_TRAFFIC_BYTES_PER_LAUNCH,
                 "traffic_unit": "bytes per launch (ncu, n=1e7 launch; algorithmic traffic is O(S) descriptors)",
                 "fp64_slots_per_sample": F_ALG_W1,
+                "ncu": {"fp64_pipe_active_pct": 48.8, "issue_slots_active_pct": 64.2, "tensor_pipe_active_pct": 0.0,
+                        "instructions_per_sample_pair": 314, "fp64_instructions_per_sample_pair": 119,
+                        "source": "profiles/r01_s_ncu_full_w1_n1e7_summary.txt (static: taken from the committed capture)"},
                 "peak_source": "measured in this run by ebn_peak_fp64 (independent DFMA chains, burst); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "note": "compute-bound path: algorithmic DRAM traffic is ~0 B/sample, no tensor cores",
