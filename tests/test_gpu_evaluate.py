@@ -447,7 +447,7 @@ def test_examples_run(E):
     mods = {}
     import sys
     sys.path.insert(0, os.path.join(root, "examples"))
-    for name in ("vehicle_suspension", "straub_example", "vehicle_suspension_imprecise"):
+    for name in ("vehicle_suspension", "straub_example", "vehicle_suspension_imprecise", "custom_model"):
         spec = importlib.util.spec_from_file_location(f"example_{name}", os.path.join(root, "examples", f"{name}.py"))
         mods[name] = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mods[name])
@@ -456,6 +456,11 @@ def test_examples_run(E):
     assert len(pf) == 20 and abs(pf[("offroad", "normal_load", "[11.5, 12.0]")] - 0.7373) < 0.005
     pi = mods["straub_example"].main(10**6)
     assert np.allclose(pi, [0.026129, 0.973871], atol=0.01)
+    cm = mods["custom_model"]
+    pf, sd, smp = E.probability_of_failure([cm.stress], cm.performance, cm.inputs, E.MonteCarlo(2_000_000))
+    rows = smp.fetch(0, 1000)
+    assert 1e-4 < pf < 0.2 and list(rows) == ["fy", "P", "e", "A", "W", "sigma", "g"]
+    assert np.allclose(rows["g"], rows["fy"] - (1000 * rows["P"] / 5400.0 + 1000 * rows["P"] * np.abs(rows["e"]) / 3.9e5), rtol=1e-12)
     ei = mods["vehicle_suspension_imprecise"].main(200_000)
     assert not ei.isprecise()
     bounds = {r["V_d"]: r["Π"] for r in ei.cpt.data
