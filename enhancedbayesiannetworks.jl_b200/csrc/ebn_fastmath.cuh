@@ -25,6 +25,9 @@ struct FastMathConst {
   double inv_ln2_64, ln2_64_hi, ln2_64_lo;
   double sind[EBN_SC_TAB_BITS < 10 ? 3 : 2];   // sin(delta) = t*(d0 + d1 t^2 [+ d2 t^4]), delta = (pi/2) t inside a table cell
   double cosd[2];   // cos(delta) - 1 = t^2*(e0 + e1 t^2)
+  uint32_t mant20, one_hi;   // 0x000fffff, 0x3ff00000: LOP3 operands the compiler must not fold (see hi_of_one_two)
+  double td_off;             // -(2^22 + half cell - 2^-21): addend of the in-cell offset (bm_trig)
+  double c375;               // 3/8 of the square-root correction
 };
 __constant__ FastMathConst kFm = {
     {0.5, -0.33333333333333331483, 0.25, -0.2000000000000000111, 0.16666666666666665741},
@@ -35,6 +38,9 @@ __constant__ FastMathConst kFm = {
     0x1.473de6af278edp-40,          // ln2/64 - high part
     {EBN_SIND_COEFS},
     {EBN_COSD_COEFS},
+    0x000FFFFFu, 0x3FF00000u,
+    -(4194304.0 + 1.0 / (double)(1 << (EBN_SC_TAB_BITS + 1)) - 0x1p-21),
+    0.375,
 };
 
 // Shared-memory copy of the log table (per-lane random index: shared memory,
@@ -49,6 +55,41 @@ __device__ __forceinline__ void fastmath_init(FastMathSmem& sm, int tid, int nth
   for (int i = tid; i < (1 << EBN_LOG_TAB_BITS); i += nthreads) sm.logtab[i] = kLogTab[i];
   for (int i = tid; i < (1 << EBN_SC_TAB_BITS); i += nthreads) sm.sctab[i] = kSinCosTab[i];
   for (int i = tid; i < 64; i += nthreads) sm.exptab[i] = kExpTab[i];
+}
+
+// Tuning switches of the Box-Muller transform (bit mask; profiles/r02_*):
+//   1  -ln u through one Horner chain (two operations fewer than r^2 p + (base - r))
+//   2  x = mu + (sigma R) * trig: the scale is folded into the radius (one multiplication fewer per pair)
+//   4  bit placement with single LOP3s: (w & 0xfffff) | 0x3ff00000 with both masks as register operands,
+//      and the low mantissa word as one bit-select
+//   8  exponent -> double through I2F (XU pipe, idle) instead of the 2^52 magic (MOV + DADD)
+//  32  polynomial top coefficients as immediates, the remaining literals from the constant bank
+//  16  r = u * (rc 2^e) - 1 with the exponent added to the table entry's high word (one IMAD) instead of
+//      rebuilding the mantissa m = u 2^e as a new register pair (LOP3 + MOV); the same value bit for bit
+#ifndef EBN_BM_OPT
+#define EBN_BM_OPT 47   // measured best on B200 (profiles/r02_tune_w1.txt); 16 costs 1 %
+#endif
+
+// High word of the double in [1,2) whose top 20 mantissa bits are the low 20 bits of w:
+// (w & 0x000fffff) | 0x3ff00000. Written as ONE three-input LOP3 whose two masks are operands
+// (constant bank / registers): with two literals ptxas needs two instructions.
+__device__ __forceinline__ uint32_t hi_of_one_two(uint32_t w) {
+  if (EBN_BM_OPT & 4) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(w), "r"(kFm.mant20), "r"(kFm.one_hi));
+    return d;
+  }
+  return (w & 0x000FFFFFu) | 0x3FF00000u;
+}
+// (a & mask) | (b & ~mask) in one LOP3.
+template <uint32_t MASK>
+__device__ __forceinline__ uint32_t bit_select(uint32_t a, uint32_t b) {
+  if (EBN_BM_OPT & 4) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "n"(MASK));
+    return d;
+  }
+  return (a & MASK) | (b & ~MASK);
 }
 
 // Index of the log-table cell from the high word of a double, and the polynomial
@@ -146,7 +187,9 @@ __device__ __forceinline__ double sqrt_pos(double t) {
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
   const double a = t * y;
   const double e = fma(-a, y, 1.0);
-  const double c = fma(e, 0.375, 0.5);
+  // 32: literals that are not instruction immediates come from the constant bank (one c[] operand per
+  // instruction is free; a literal costs two MOVs per use inside the loop)
+  const double c = (EBN_BM_OPT & 32) ? fma(e, kFm.c375, 0.5) : fma(e, 0.375, 0.5);
   return fma(a * e, c, a);
 }
 
@@ -168,51 +211,95 @@ struct BmFront {
 };
 
 __device__ __forceinline__ BmFront box_muller_front(uint32_t w0, uint32_t w1, const FastMathSmem& sm) {
-  // Bit placement with two LOP3 and one shift (the integer ALU is the scarce pipe next to the
-  // fp64 pipe): the low 20 bits of w0 become the high mantissa bits, its top 12 bits stay in
-  // place in the low word, bits 0..9 of w1 land right below them; the low 10 mantissa bits are 0.
-  const double u = __hiloint2double((int)((w0 & 0x000FFFFFu) | 0x3FF00000u),
-                                    (int)((w0 & 0xFFF00000u) | ((w1 << 10) & 0x000FFFFFu))) -
+  // Bit placement (the integer ALU is the scarce pipe next to the fp64 pipe): the low 20 bits of w0
+  // become the high mantissa bits, its top 12 bits stay in place in the low word, bits 0..9 of w1
+  // land right below them; the low 10 mantissa bits are 0.
+  const double u = __hiloint2double((int)hi_of_one_two(w0), (int)bit_select<0xFFF00000u>(w0, w1 << 10)) -
                    (1.0 - 0x1p-43);
   const int hi = __double2hiint(u);
   const int ne = 1023 - (hi >> 20);
-  const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(u));
   const double2 t = sm.logtab[log_cell(hi)];
   BmFront f;
-  f.r = fma(m, t.x, -1.0);
-  f.base = fma(__hiloint2double(0x43380000, ne) - 6755399441055744.0, kFm.ln2, t.y);
+  if (EBN_BM_OPT & 16) {
+    f.r = fma(u, __hiloint2double(__double2hiint(t.x) + (ne << 20), __double2loint(t.x)), -1.0);
+  } else {
+    const double m = __hiloint2double((int)hi_of_one_two((uint32_t)hi), __double2loint(u));
+    f.r = fma(m, t.x, -1.0);
+  }
+  const double ned = (EBN_BM_OPT & 8) ? __int2double_rn(ne) : __hiloint2double(0x43380000, ne) - 6755399441055744.0;
+  f.base = fma(ned, kFm.ln2, t.y);
   f.w1 = w1;
   return f;
 }
 
-__device__ __forceinline__ void box_muller_back(const BmFront& f, const FastMathSmem& sm, double& z0, double& z1) {
+// -ln u from the front end's reduction.
+__device__ __forceinline__ double bm_neg_log(const BmFront& f) {
   const double r = f.r;
   const double p = log1p_poly(r);
-  const double t = fma(r * r, p, f.base - r);          // -ln u
-  // Angle phi = (pi/2)(A + 1/2) 2^-20, A = bits 10..29 of w1: the top B = EBN_SC_TAB_BITS bits of A
-  // pick one of 2^B cells whose centre carries sqrt(2)*(sin, cos) in shared memory; the low 20-B
-  // bits give the offset inside the cell, delta = (pi/2) t with |t| <= 2^-(B+1), short enough for
-  // two 2-3 term polynomials (10-11 fp64 operations instead of the 20 of a full-quadrant pair).
-  // The offset bits stay where they are in the low mantissa word: d = 1 + r 2^-42,
-  // t = (r + 1/2) 2^-20 - 2^-(B+1) = d 2^22 - (2^22 + 2^-(B+1) - 2^-21), exact.
+  if (EBN_BM_OPT & 1) return fma(r, fma(r, p, -1.0), f.base);   // base - r + r^2 p as one Horner chain
+  return fma(r * r, p, f.base - r);
+}
+
+// sqrt(2)*(sin, cos) of the pair's first-quadrant angle.
+// Angle phi = (pi/2)(A + 1/2) 2^-20, A = bits 10..29 of w1: the top B = EBN_SC_TAB_BITS bits of A
+// pick one of 2^B cells whose centre carries sqrt(2)*(sin, cos) in shared memory; the low 20-B
+// bits give the offset inside the cell, delta = (pi/2) t with |t| <= 2^-(B+1), short enough for
+// two 2-3 term polynomials (10-11 fp64 operations instead of the 20 of a full-quadrant pair).
+// The offset bits stay where they are in the low mantissa word: d = 1 + r 2^-42,
+// t = (r + 1/2) 2^-20 - 2^-(B+1) = d 2^22 - (2^22 + 2^-(B+1) - 2^-21), exact.
+__device__ __forceinline__ void bm_trig(uint32_t w1, const FastMathSmem& sm, double& cps, double& cms) {
   constexpr int B = EBN_SC_TAB_BITS;
   constexpr uint32_t kOffsetMask = ((1u << (20 - B)) - 1u) << 10;
   constexpr double kHalfCell = 1.0 / (double)(1 << (B + 1));
-  const double2 sc = sm.sctab[(f.w1 >> (30 - B)) & ((1u << B) - 1u)];
-  const double td = fma(__hiloint2double(0x3FF00000, (int)(f.w1 & kOffsetMask)), 4194304.0,
-                        -(4194304.0 + kHalfCell - 0x1p-21));
-  const double w = td * td;
-  double sd;
-  if (B < 10) sd = td * fma(w, fma(w, kFm.sind[B < 10 ? 2 : 1], kFm.sind[1]), kFm.sind[0]);  // sin(delta)
-  else sd = td * fma(w, kFm.sind[1], kFm.sind[0]);
-  const double cm = w * fma(w, kFm.cosd[1], kFm.cosd[0]);                        // cos(delta) - 1
-  const double cps = fma(sc.y, sd, fma(sc.x, cm, sc.x));    // sqrt(2) sin(phi)
-  const double cms = fma(-sc.x, sd, fma(sc.y, cm, sc.y));   // sqrt(2) cos(phi)
-  const double rr = sqrt_pos(t);                        // sqrt(-ln u) = R / sqrt(2)
-  const double a = rr * cps;  // R*sin(phi)
-  const double b = rr * cms;  // R*cos(phi)
-  z0 = __hiloint2double(__double2hiint(a) ^ (int)(f.w1 & 0x80000000u), __double2loint(a));
-  z1 = __hiloint2double(__double2hiint(b) ^ (int)((f.w1 << 1) & 0x80000000u), __double2loint(b));
+  const double2 sc = sm.sctab[(w1 >> (30 - B)) & ((1u << B) - 1u)];
+  double td, sd, cm;
+  if (EBN_BM_OPT & 32) {
+    // the top coefficients are immediates (low word zero, tools/gen_fastmath_tables.py), every other
+    // constant is a constant-bank operand: no coefficient lives in a register
+    td = fma(__hiloint2double(0x3FF00000, (int)(w1 & kOffsetMask)), 4194304.0, kFm.td_off);
+    const double w = td * td;
+    if (B < 10) sd = td * fma(w, fma(w, EBN_SIND_TOP, kFm.sind[1]), kFm.sind[0]);
+    else sd = td * fma(w, EBN_SIND_TOP, kFm.sind[0]);
+    cm = w * fma(w, EBN_COSD_TOP, kFm.cosd[0]);
+  } else {
+    td = fma(__hiloint2double(0x3FF00000, (int)(w1 & kOffsetMask)), 4194304.0,
+             -(4194304.0 + kHalfCell - 0x1p-21));
+    const double w = td * td;
+    if (B < 10) sd = td * fma(w, fma(w, kFm.sind[B < 10 ? 2 : 1], kFm.sind[1]), kFm.sind[0]);  // sin(delta)
+    else sd = td * fma(w, kFm.sind[1], kFm.sind[0]);
+    cm = w * fma(w, kFm.cosd[1], kFm.cosd[0]);                        // cos(delta) - 1
+  }
+  cps = fma(sc.y, sd, fma(sc.x, cm, sc.x));    // sqrt(2) sin(phi)
+  cms = fma(-sc.x, sd, fma(sc.y, cm, sc.y));   // sqrt(2) cos(phi)
+}
+
+__device__ __forceinline__ double flip_sign(double a, uint32_t sign_bit) {
+  return __hiloint2double(__double2hiint(a) ^ (int)(sign_bit & 0x80000000u), __double2loint(a));
+}
+
+__device__ __forceinline__ void box_muller_back(const BmFront& f, const FastMathSmem& sm, double& z0, double& z1) {
+  double cps, cms;
+  bm_trig(f.w1, sm, cps, cms);
+  const double rr = sqrt_pos(bm_neg_log(f));           // sqrt(-ln u) = R / sqrt(2)
+  z0 = flip_sign(rr * cps, f.w1);        // s0 R sin(phi)
+  z1 = flip_sign(rr * cms, f.w1 << 1);   // s1 R cos(phi)
+}
+
+// x = mu + sigma z for both samples of the pair.
+__device__ __forceinline__ void box_muller_back_affine(const BmFront& f, const FastMathSmem& sm, double mu,
+                                                       double sigma, double& x0, double& x1) {
+  if (EBN_BM_OPT & 2) {
+    double cps, cms;
+    bm_trig(f.w1, sm, cps, cms);
+    const double rs = sqrt_pos(bm_neg_log(f)) * sigma;   // sigma R / sqrt(2)
+    x0 = fma(flip_sign(rs, f.w1), cps, mu);
+    x1 = fma(flip_sign(rs, f.w1 << 1), cms, mu);
+  } else {
+    double z0, z1;
+    box_muller_back(f, sm, z0, z1);
+    x0 = fma(z0, sigma, mu);
+    x1 = fma(z1, sigma, mu);
+  }
 }
 
 // The same transform in fp32 ("FP32 where tolerated"): the radius uniform keeps the 32 bits of w0

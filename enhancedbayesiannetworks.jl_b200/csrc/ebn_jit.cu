@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 
 #include "../../include/ebncuda.h"
+#include "ebn_device.cuh"
 #include "ebn_expr.h"
 #include "ebn_jit_sources.inc"
 
@@ -237,6 +238,40 @@ void disk_write(const std::string& dir, const std::string& path, const JitKernel
   else unlink(tmp.c_str());
 }
 
+// The tuning macros this library was built with (Makefile EXTRA=...): a kernel compiled at run time must
+// see the same values, or it would be launched with a block shape it was not compiled for. Macros that
+// were not given on the command line keep the defaults of the embedded headers, which are this build's.
+#define EBN_STR2(x) #x
+#define EBN_STR(x) EBN_STR2(x)
+const char* const kBuildDefines[] = {
+    "-DEBN_THREADS=" EBN_STR(EBN_THREADS),
+#ifdef EBN_UNROLL
+    "-DEBN_UNROLL=" EBN_STR(EBN_UNROLL),
+#endif
+#ifdef EBN_PINGPONG
+    "-DEBN_PINGPONG=" EBN_STR(EBN_PINGPONG),
+#endif
+#ifdef EBN_VEHICLE_BLOCKS
+    "-DEBN_VEHICLE_BLOCKS=" EBN_STR(EBN_VEHICLE_BLOCKS),
+#endif
+#ifdef EBN_STRAUB_BLOCKS
+    "-DEBN_STRAUB_BLOCKS=" EBN_STR(EBN_STRAUB_BLOCKS),
+#endif
+#ifdef EBN_BM_OPT
+    "-DEBN_BM_OPT=" EBN_STR(EBN_BM_OPT),
+#endif
+#ifdef EBN_PHILOX_ROUNDS
+    "-DEBN_PHILOX_ROUNDS=" EBN_STR(EBN_PHILOX_ROUNDS),
+#endif
+};
+constexpr int kNumBuildDefines = sizeof(kBuildDefines) / sizeof(kBuildDefines[0]);
+
+std::string build_defines_key() {
+  std::string s;
+  for (const char* d : kBuildDefines) s += std::string(d) + " ";
+  return s;
+}
+
 bool compile(const Unit& u, JitKernel* k, std::string* err) {
   constexpr int NH = sizeof(kJitSources) / sizeof(kJitSources[0]);
   const char* names[NH];
@@ -254,8 +289,9 @@ bool compile(const Unit& u, JitKernel* k, std::string* err) {
   bool ok = false;
   do {
     if ((r = g_rtc.AddNameExpression(prog, u.name_expr.c_str()))) break;
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
-    r = g_rtc.CompileProgram(prog, 3, opts);
+    const char* opts[3 + kNumBuildDefines] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+    for (int i = 0; i < kNumBuildDefines; ++i) opts[3 + i] = kBuildDefines[i];
+    r = g_rtc.CompileProgram(prog, 3 + kNumBuildDefines, opts);
     if (r) {
       size_t n = 0;
       g_rtc.GetProgramLogSize(prog, &n);
@@ -282,9 +318,38 @@ bool compile(const Unit& u, JitKernel* k, std::string* err) {
 
 }  // namespace
 
+// One-off probe: can this NVRTC generate sm_100a code at all? (A libnvrtc older than 12.8 loads fine and
+// then rejects the architecture; torch bundles its own copy, so the first libnvrtc.so.12 on the search
+// path is not necessarily the toolkit's.) Without the probe the OPTIONAL uses of run-time compilation
+// (sampling plans of large jobs, rewritten coefficient-table functors) would fail where the compiled-in
+// kernels could have run the job.
+bool nvrtc_probe() {
+  static int state = 0;  // 0 unknown, 1 ok, -1 failed
+  if (state) return state > 0;
+  nvrtcProgram prog = nullptr;
+  const char* src = "extern \"C\" __global__ void ebn_probe(double* p) { p[0] = 1.0; }\n";
+  int r = g_rtc.CreateProgram(&prog, src, "ebn_probe.cu", 0, nullptr, nullptr);
+  if (!r) {
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17"};
+    r = g_rtc.CompileProgram(prog, 2, opts);
+    size_t n = 0;
+    if (!r) r = g_rtc.GetCUBINSize(prog, &n);
+    if (!r && n == 0) r = -1;
+    g_rtc.DestroyProgram(&prog);
+  }
+  if (r) {
+    g_rtc.why = fmt("libnvrtc %d.%d cannot compile for sm_100a (%s); point EBN_NVRTC_LIB at a CUDA >= 12.8 copy",
+                    g_rtc.major, g_rtc.minor, r > 0 ? g_rtc.GetErrorString(r) : "empty cubin");
+    state = -1;
+    return false;
+  }
+  state = 1;
+  return true;
+}
+
 bool jit_available(std::string* why) {
   std::lock_guard<std::mutex> lk(g_mu);
-  const bool ok = nvrtc_load();
+  const bool ok = nvrtc_load() && nvrtc_probe();
   if (!ok && why) *why = g_rtc.why;
   return ok;
 }
@@ -294,13 +359,13 @@ bool jit_get(const JitSpec& spec, JitRole role, JitKernel** out, bool* compiled,
   if (compiled) *compiled = false;
   Unit u;
   if (!make_unit(spec, role, &u, err)) return false;
-  const std::string key = u.name_expr + "\n" + u.source;
+  const std::string key = build_defines_key() + "\n" + u.name_expr + "\n" + u.source;
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
     *out = it->second.get();
     return true;
   }
-  if (!nvrtc_load()) {
+  if (!nvrtc_load() || !nvrtc_probe()) {
     *err = g_rtc.why + " — expression limit states and run-time sampling plans need it (there is no CPU fallback)";
     return false;
   }

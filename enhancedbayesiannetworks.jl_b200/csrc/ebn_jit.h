@@ -27,7 +27,7 @@ struct JitSpec {
 
 struct JitKernel;  // cubin + entry name + the functions loaded per device
 
-// Is libnvrtc loadable? No GPU needed.
+// Is libnvrtc loadable AND able to generate sm_100a code (one-off probe compile)? No GPU needed.
 bool jit_available(std::string* why);
 
 // Compiles the kernel, or finds it in the in-memory cache or (EBN_JIT_CACHE=dir) on disk. No GPU needed.

@@ -60,9 +60,13 @@ struct VehicleSuspension {
   static constexpr int NC = 5;
   static constexpr bool HAS_FAILS = !Ops::strict;  // sign-only test in fast mode
 #ifndef EBN_VEHICLE_BLOCKS
-#define EBN_VEHICLE_BLOCKS EBN_BLOCKS_FOR_WARPS(16)
+#define EBN_VEHICLE_BLOCKS EBN_BLOCKS_FOR_WARPS(8)
 #endif
-  static constexpr int MIN_BLOCKS = EBN_VEHICLE_BLOCKS;  // 16 warps per SM: 128 registers, no spills; throughput is issue-bound, not occupancy-bound
+  // 8 warps per SM (two per sub-partition): the kernel is bound by issue slots / register-file traffic, not by
+  // latency, and fewer resident warps contend less (measured: 16 warps 1.625e11, 12 warps 1.672e11,
+  // 8 warps 1.692e11 samples/s, profiles/r02_tune_w1.txt)
+  // strict mode (IEEE divisions and a square root per sample) is latency-bound instead: 16 warps per SM
+  static constexpr int MIN_BLOCKS = Ops::strict ? EBN_BLOCKS_FOR_WARPS(16) : EBN_VEHICLE_BLOCKS;
   struct Ctx {
     double M, m, gg, pow_a, pow_b;     // strict
     double pim, mM, iM, imM, immM, mpM, Mg;

@@ -25,6 +25,9 @@ constexpr int kWarps = kThreads / 32;
 #define EBN_UNROLL 1
 #endif
 constexpr int kPairUnroll = EBN_UNROLL;  // pairs per trip of the static count loop
+#ifndef EBN_PINGPONG
+#define EBN_PINGPONG 0
+#endif
 
 // Compile-time sampling plans ------------------------------------------------
 template <int... K>
@@ -230,12 +233,38 @@ struct BackAll {
 // all-fp64 phase (profiles/r01_b_*, tools/microbench), and the shared-memory latency of the
 // log table is exposed.
 // CHECK = the item touches the [first, last) boundary and samples must be masked.
+// One pair of the pipelined count loop: generate and pre-process pair `qn` into `nxt` while pair `q`
+// (already in `cur`) goes through the back end and the limit state.
+template <class LS, class Plan, bool CHECK>
+__device__ __forceinline__ unsigned static_count_step(const typename LS::Ctx& ctx, const DevInput* r_plan,
+                                                      PairCtr& pc, int64_t q, int64_t qn,
+                                                      const InState* cur, InState* nxt,
+                                                      const McParams& p, const FastMathSmem& sm) {
+  constexpr int XCAP = LS::XCAP;
+  constexpr int NC = static_calls<Plan>() > 0 ? static_calls<Plan>() : 1;
+  {  // prefetch (one surplus generation per item and thread)
+    Philox4 ph[NC];
+    static_gen<Plan>(ph, (uint32_t)qn, (uint32_t)((uint64_t)qn >> 32), pc);
+    FrontAll<Plan, 0>::run(ph, sm, nxt);
+  }
+  pc.qlo = (uint32_t)q;
+  pc.qhi = (uint32_t)((uint64_t)q >> 32);
+  double x0[XCAP], x1[XCAP];
+  BackAll<Plan, 0>::run(r_plan, cur, pc, p.tables, sm, x0, x1);
+  const unsigned f0 = sample_fails<LS>(ctx, x0) ? 1u : 0u;
+  const unsigned f1 = sample_fails<LS>(ctx, x1) ? 1u : 0u;
+  if (CHECK) {
+    const int64_t i0 = q << 1;
+    return ((i0 >= p.first) ? f0 : 0u) + (((i0 + 1) < p.last) ? f1 : 0u);
+  }
+  return f0 + f1;
+}
+
 template <class LS, class Plan, bool CHECK>
 __device__ __forceinline__ unsigned static_count_loop(const typename LS::Ctx& ctx,
                                                       const DevInput* r_plan, PairCtr pc,
                                                       int64_t q_begin, int64_t q_end, int tid,
                                                       const McParams& p, const FastMathSmem& sm) {
-  constexpr int XCAP = LS::XCAP;
   constexpr int NC = static_calls<Plan>() > 0 ? static_calls<Plan>() : 1;
   unsigned cnt = 0;
   int64_t q = q_begin + tid;
@@ -245,30 +274,24 @@ __device__ __forceinline__ unsigned static_count_loop(const typename LS::Ctx& ct
     static_gen<Plan>(ph, (uint32_t)q, (uint32_t)((uint64_t)q >> 32), pc);
     FrontAll<Plan, 0>::run(ph, sm, nxt);
   }
+#if EBN_PINGPONG
+  // Two pairs per trip, the two pipeline stages swapping buffers: no register copies between trips.
+  InState alt[Plan::n];
+#pragma unroll 1
+  for (; q + kThreads < q_end; q += 2 * kThreads) {
+    cnt += static_count_step<LS, Plan, CHECK>(ctx, r_plan, pc, q, q + kThreads, nxt, alt, p, sm);
+    cnt += static_count_step<LS, Plan, CHECK>(ctx, r_plan, pc, q + kThreads, q + 2 * kThreads, alt, nxt, p, sm);
+  }
+  if (q < q_end) cnt += static_count_step<LS, Plan, CHECK>(ctx, r_plan, pc, q, q + kThreads, nxt, alt, p, sm);
+#else
 #pragma unroll kPairUnroll
   for (; q < q_end; q += kThreads) {
     InState cur[Plan::n];
 #pragma unroll
     for (int j = 0; j < Plan::n; ++j) cur[j] = nxt[j];
-    {  // prefetch (one surplus generation per item and thread)
-      const int64_t qn = q + kThreads;
-      Philox4 ph[NC];
-      static_gen<Plan>(ph, (uint32_t)qn, (uint32_t)((uint64_t)qn >> 32), pc);
-      FrontAll<Plan, 0>::run(ph, sm, nxt);
-    }
-    pc.qlo = (uint32_t)q;
-    pc.qhi = (uint32_t)((uint64_t)q >> 32);
-    double x0[XCAP], x1[XCAP];
-    BackAll<Plan, 0>::run(r_plan, cur, pc, p.tables, sm, x0, x1);
-    const unsigned f0 = sample_fails<LS>(ctx, x0) ? 1u : 0u;
-    const unsigned f1 = sample_fails<LS>(ctx, x1) ? 1u : 0u;
-    if (CHECK) {
-      const int64_t i0 = q << 1;
-      cnt += ((i0 >= p.first) ? f0 : 0u) + (((i0 + 1) < p.last) ? f1 : 0u);
-    } else {
-      cnt += f0 + f1;
-    }
+    cnt += static_count_step<LS, Plan, CHECK>(ctx, r_plan, pc, q, q + kThreads, cur, nxt, p, sm);
   }
+#endif
   return cnt;
 }
 
@@ -308,6 +331,8 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
   extern __shared__ unsigned char s_dyn[];  // MODE 1: edges (double) then bins (u32)
   double* s_edges = reinterpret_cast<double*>(s_dyn);
   unsigned int* s_bins = reinterpret_cast<unsigned int*>(s_dyn + sizeof(double) * (MODE == 1 ? p.nedges : 0));
+
+  if (blockDim.x != kThreads) __trap();  // launched with a block shape the kernel was not compiled for
 
   typename LS::Ctx ctx;
   LS::setup(ctx, p.consts, p.n_consts, p.d, &s_fm);
@@ -439,6 +464,7 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
   __shared__ FastMathSmem s_fm;
   __shared__ DevInput s_plan[EBN_MAX_INPUTS];
   __shared__ double s_chol[Plan::is_copula ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
+  if (blockDim.x != kThreads) __trap();
   typename LS::Ctx ctx;
   LS::setup(ctx, p.consts, p.n_consts, p.d, &s_fm);
   fastmath_init(s_fm, threadIdx.x, kThreads);
@@ -492,6 +518,7 @@ __global__ void __launch_bounds__(kThreads) matrix_kernel(const double* consts, 
   constexpr int XCAP = LS::XCAP;
   __shared__ unsigned int s_red[kWarps];
   __shared__ FastMathSmem s_fm;
+  if (blockDim.x != kThreads) __trap();
   typename LS::Ctx ctx;
   LS::setup(ctx, consts, n_consts, d, &s_fm);
   fastmath_init(s_fm, threadIdx.x, kThreads);

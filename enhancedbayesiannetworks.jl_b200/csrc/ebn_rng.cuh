@@ -20,8 +20,11 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
                                                  uint32_t c3, uint32_t k0, uint32_t k1) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
   constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#ifndef EBN_PHILOX_ROUNDS
+#define EBN_PHILOX_ROUNDS 10   // measurement-only switch (profiles/r02_*): the shipped stream is Philox4x32-10
+#endif
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < EBN_PHILOX_ROUNDS; ++r) {
     const uint64_t p0 = (uint64_t)M0 * c0;
     const uint64_t p1 = (uint64_t)M1 * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;

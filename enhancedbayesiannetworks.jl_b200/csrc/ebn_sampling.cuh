@@ -42,7 +42,7 @@ __device__ __forceinline__ double u32w(uint32_t w) {
 
 // the [1,2) double behind U32(w), before the offset is removed
 __device__ __forceinline__ double u32w_raw(uint32_t w) {
-  return __hiloint2double((int)((w & 0x000FFFFFu) | 0x3FF00000u), (int)(w & 0xFFF00000u));
+  return __hiloint2double((int)hi_of_one_two(w), (int)(w & 0xFFF00000u));
 }
 
 // Word sources -----------------------------------------------------------------
@@ -198,10 +198,7 @@ __device__ __forceinline__ void draw_back(const DevInput& in, const InState& st,
     x0 = fma(u32w_raw(st.w0), in.b, in.c);
     x1 = fma(u32w_raw(st.w1), in.b, in.c);
   } else if (KIND == DK_NORMAL_BM || KIND == DK_LOGNORMAL_BM) {
-    double z0, z1;
-    box_muller_back(st.bm, sm, z0, z1);
-    x0 = fma(z0, in.b, in.a);
-    x1 = fma(z1, in.b, in.a);
+    box_muller_back_affine(st.bm, sm, in.a, in.b, x0, x1);
     if (KIND == DK_LOGNORMAL_BM) {
       x0 = exp_fast(x0, sm);
       x1 = exp_fast(x1, sm);

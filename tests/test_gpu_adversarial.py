@@ -46,7 +46,7 @@ def _adversarial_rows(L, fixed_v=False):
     return rows
 
 
-def _explain_by_ties(ebn, job, oracle_ls, oracle_consts, window=1 << 17):
+def _explain_by_ties(ebn, job, oracle_ls, oracle_consts, window=1 << 17, both_signs=False):
     """Localises every sample on which the fused kernel's failure indicator differs from the oracle's
     on the replayed matrix. Returns (rows examined, NaN-g fraction, list of (scenario, row, g))."""
     n, S = job.n, job.S
@@ -57,7 +57,7 @@ def _explain_by_ties(ebn, job, oracle_ls, oracle_consts, window=1 << 17):
         want.append(np.concatenate([[0], np.cumsum(g < 0)]))   # NaN < 0 is False: safe, like the reference
         gs.append(g)
         nan_rows += int(np.isnan(g).sum())
-        if oracle_ls == ocpu.LS_VEHICLE:
+        if both_signs:
             assert (X[:, 3] < 0).any() and (X[:, 3] > 0).any() and (X[:, 5] < 0).any() and (X[:, 5] > 0).any()
 
     def counts(first, m):
@@ -98,7 +98,7 @@ def test_sign_only_predicate_on_adversarial_marginals(ebn, fp32, fixed_v):
                 seed=0xADBE_0001 + 2 * fp32 + fixed_v, strict=False, fp32_sampling=fp32)
     ebn.pf_batch(dataclasses.replace(job, n=1000))
     assert ebn.last_stats()["specialised"] == 1, "the compile-time sampling plan must be the one under test"
-    rows, nan_frac, bad = _explain_by_ties(ebn, job, ocpu.LS_VEHICLE, job.consts)
+    rows, nan_frac, bad = _explain_by_ties(ebn, job, ocpu.LS_VEHICLE, job.consts, both_signs=True)
     assert nan_frac > 0.10, nan_frac
     not_ties = [(s, r, g) for (s, r, g) in bad if not abs(g) < TIE]
     assert not not_ties, f"sign-only predicate disagrees off a tie: {not_ties[:5]}"
@@ -151,7 +151,7 @@ def test_compiled_formula_fast_mode_on_adversarial_marginals(ebn):
         "min(g1, g2, g3, g4)", params={"M": k[0], "m": k[1], "g": k[2], "Mg15": k[3], "gMm": k[4]})
     n = 1_000_001
     job = L.Job(L.LS_EXPRESSION, prog.consts, L.make_inputs(_adversarial_rows(L)), n, seed=0xADBE_0009, strict=False)
-    rows, nan_frac, bad = _explain_by_ties(ebn, job, ocpu.LS_EXPRESSION, prog.consts)
+    rows, nan_frac, bad = _explain_by_ties(ebn, job, ocpu.LS_EXPRESSION, prog.consts, both_signs=True)
     assert nan_frac > 0.10
     # fast mode re-associates: every mechanism is `1 - ratio` or `x - threshold`, so a flip needs |g| ~ 1e-15
     not_ties = [(s, r, g) for (s, r, g) in bad if not abs(g) < TIE]
