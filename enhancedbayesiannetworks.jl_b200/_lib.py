@@ -81,7 +81,7 @@ class EbnStats(C.Structure):
 assert C.sizeof(EbnJob) == 104 and C.sizeof(EbnStats) == 48
 
 EXPORTS = [
-    "ebn_abi_version", "ebn_device_count", "ebn_init", "ebn_shutdown", "ebn_set_stream",
+    "ebn_abi_version", "ebn_build_id", "ebn_device_count", "ebn_init", "ebn_shutdown", "ebn_set_stream",
     "ebn_nccl_unique_id", "ebn_comm_init_rank", "ebn_comm_destroy", "ebn_pf_batch",
     "ebn_hist_batch", "ebn_eval_matrix", "ebn_sample_matrix", "ebn_sample_matrix_ex", "ebn_peak_fp64", "ebn_last_stats",
     "ebn_partition", "ebn_last_error", "ebn_limit_state_id", "ebn_limit_state_name", "ebn_limit_state_arity",
@@ -111,6 +111,7 @@ def load():
     L = C.CDLL(LIB_PATH)
     vp, i64p, dp = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)
     L.ebn_abi_version.restype = C.c_int
+    L.ebn_build_id.restype = C.c_char_p
     L.ebn_device_count.restype = C.c_int
     L.ebn_init.argtypes = [C.POINTER(C.c_int), C.c_int]
     L.ebn_set_stream.argtypes = [vp]
@@ -154,6 +155,11 @@ def _i64p(a):
 
 
 _initialised = False
+
+
+def build_id() -> str:
+    """ebn_build_id: hash of the kernel sources and tuning flags the library was built from."""
+    return load().ebn_build_id().decode()
 
 
 def device_count() -> int:

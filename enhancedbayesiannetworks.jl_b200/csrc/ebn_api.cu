@@ -21,6 +21,7 @@
 #include "ebn_expr.h"
 #include "ebn_jit.h"
 #include "ebn_kernels.h"
+#include "ebn_build_id.inc"
 
 static_assert(sizeof(ebn_input_t) == 56, "ebn_input_t must be 56 bytes");
 static_assert(sizeof(ebn_stats_t) == 48, "ebn_stats_t must be 48 bytes");
@@ -837,6 +838,7 @@ int run_batch(const ebn_job_t* job_in, int mode, const double* edges, int nedges
 extern "C" {
 
 int ebn_abi_version(void) { return EBN_ABI_VERSION; }
+const char* ebn_build_id(void) { return EBN_BUILD_ID; }
 
 const char* ebn_last_error(void) { return g_err.c_str(); }
 

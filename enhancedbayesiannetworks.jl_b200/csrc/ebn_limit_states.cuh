@@ -62,9 +62,11 @@ struct VehicleSuspension {
 #ifndef EBN_VEHICLE_BLOCKS
 #define EBN_VEHICLE_BLOCKS EBN_BLOCKS_FOR_WARPS(8)
 #endif
-  // 8 warps per SM (two per sub-partition): the kernel is bound by issue slots / register-file traffic, not by
-  // latency, and fewer resident warps contend less (measured: 16 warps 1.625e11, 12 warps 1.672e11,
-  // 8 warps 1.692e11 samples/s, profiles/r02_tune_w1.txt)
+  // A launch bound of 2 blocks per SM caps the kernel at 255 registers per thread; ptxas then uses ~124 and
+  // four blocks are resident anyway (the host sizes the grid from the occupancy query). The cap matters for
+  // the schedule ptxas picks, not for occupancy: bound 4 (128 registers) 1.565e11, bound 3 1.674e11,
+  // bound 2 1.692e11 samples/s; one resident warp per sub-partition already gives 88 % of that
+  // (profiles/r02_tune_w1.txt, r02_occupancy_sweep.txt).
   // strict mode (IEEE divisions and a square root per sample) is latency-bound instead: 16 warps per SM
   static constexpr int MIN_BLOCKS = Ops::strict ? EBN_BLOCKS_FOR_WARPS(16) : EBN_VEHICLE_BLOCKS;
   struct Ctx {

@@ -232,6 +232,9 @@ typedef struct ebn_stats {
 #ifndef __CUDACC_RTC__ /* host entry points */
 /* ---- lifecycle ---------------------------------------------------------- */
 int ebn_abi_version(void);
+/* Identity of the device code in this library: a hash of the kernel sources and tuning flags it was
+ * built from. Measurements frozen under profiles/ name the build they belong to. No GPU needed.   */
+const char* ebn_build_id(void);
 int ebn_device_count(void);
 /* devices == NULL, ndev == 0: device 0 only. ndev > 1: single process driving
  * several GPUs; counts are combined with ncclAllReduce (ncclCommInitAll).    */

@@ -93,3 +93,13 @@ def test_partition_validates_jobs_without_a_gpu():
     job.inputs[0, 1]["lo"] = 10.0  # truncated Gamma must come tabulated
     with pytest.raises(L.EbnError, match="EBN_EMARGINAL.*TABULATED"):
         L.partition(job)
+
+
+def test_frozen_profile_belongs_to_this_build():
+    """bench.py quotes instruction counts from profiles/w1_kernel_profile.json and refuses to run when the file
+    was frozen for another build of the kernels: keep the two in step (python tools/freeze_profile.py)."""
+    import json
+    prof = json.load(open(os.path.join(ROOT, "profiles", "w1_kernel_profile.json")))
+    assert prof["build_id"] == L.build_id(), "kernel sources changed: run `python tools/freeze_profile.py`"
+    assert 40 < prof["sass"]["fp64_instructions_per_sample"] < 80
+    assert len(L.build_id()) == 16

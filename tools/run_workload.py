@@ -1,4 +1,4 @@
-"""Runs one secondary workload a few times (for ncu): python tools/run_workload.py w2|w3|hist [n]"""
+"""Runs one secondary workload a few times (for ncu): python tools/run_workload.py w1|w2|w3|hist [total samples]"""
 import os
 import sys
 
@@ -11,7 +11,9 @@ from ebn_b200 import workloads as W  # noqa: E402
 ebn_b200.init()
 wl = sys.argv[1]
 n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 10**8
-if wl == "w2":
+if wl == "w1":
+    job = W.w1_vehicle(n=n // 20)
+elif wl == "w2":
     job = W.w2_straub(n=n)
 elif wl == "w3":
     job = W.w3_straub_copula(n=n // 64)
