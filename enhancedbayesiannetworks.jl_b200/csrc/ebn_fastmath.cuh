@@ -178,6 +178,36 @@ __device__ __forceinline__ double log_guarded(double x, const FastMathSmem& sm) 
   return (x > 0x1p-1000 && x < 0x1p1000) ? -neg_log_pos(x, sm) : log(x);
 }
 
+// Phi^-1(p) for p in (0, 1) without logarithm or square root: q = min(p, 1 - p) = 2^-e m picks one of
+// 16 cells per octave from its exponent and top four mantissa bits (one shift of the high word), and the
+// cell carries a degree-7 polynomial in (m - centre): 3e-16 relative to max(1, |z|)
+// (tools/gen_fastmath_tables.py). 11 fp64 operations against ~60 plus two branches of CUDA's
+// normcdfinv. The table (21 KB) stays in global memory behind L1: it is only touched by the
+// truncated-normal kinds. q < 2^-21 (2e-6 of the draws at most) takes the library routine.
+static __device__ __noinline__ double normcdfinv_rare(double p) { return normcdfinv(p); }
+
+__device__ __forceinline__ double normcdfinv_fast(double p) {
+  const bool lower = p < 0.5;
+  const double q = lower ? p : 1.0 - p;
+  const int hi = __double2hiint(q);
+  const unsigned row = (unsigned)((1022 * 16 + 15) - (hi >> 16));   // rows run with decreasing q
+  if (row >= (unsigned)((EBN_ICDF_OCTAVES + 1) << EBN_ICDF_SUB_BITS)) return normcdfinv_rare(p);
+  const int mhi = (int)hi_of_one_two((uint32_t)hi);
+  const double m = __hiloint2double(mhi, __double2loint(q));
+  const double c = __hiloint2double((mhi & (int)0xFFFF0000) | 0x00008000, 0);   // centre of the cell
+  const double dm = m - c;
+  const double2* co = reinterpret_cast<const double2*>(kIcdfTab[row]);
+  const double2 c01 = __ldg(co), c23 = __ldg(co + 1), c45 = __ldg(co + 2), c67 = __ldg(co + 3);
+  double z = fma(dm, c67.y, c67.x);
+  z = fma(dm, z, c45.y);
+  z = fma(dm, z, c45.x);
+  z = fma(dm, z, c23.y);
+  z = fma(dm, z, c23.x);
+  z = fma(dm, z, c01.y);
+  z = fma(dm, z, c01.x);
+  return lower ? z : -z;
+}
+
 // sqrt(t) for t in [2^-60, 2^60]: MUFU.RSQ64H seed y ~ t^-1/2 (relative error e0 ~ 2^-20),
 // then one third-order correction: with a = t*y and e = 1 - a*y,
 //   sqrt(t) = a / sqrt(1 - e) = a * (1 + e/2 + 3 e^2/8 + O(e^3)),   truncation 5 e^3/16 < 2^-58.

@@ -9,7 +9,7 @@ namespace ebn {
 // PLAN_STATIC0 + i: the i-th compile-time plan of the limit state (or, for a run-time compiled kernel,
 // the job's own kinds)
 enum PlanClass { PLAN_DYNAMIC = 0, PLAN_COPULA = 1, PLAN_STATIC0 = 2 };
-constexpr int kMaxStaticPlans = 4;
+constexpr int kMaxStaticPlans = 8;
 
 #ifndef __CUDACC_RTC__
 int threads_per_block();

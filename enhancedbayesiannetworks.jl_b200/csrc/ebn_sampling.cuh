@@ -151,10 +151,13 @@ template <int KIND>
 __device__ __forceinline__ double icdf(const DevInput& in, const double* tables,
                                        const FastMathSmem& sm, double u) {
   const double up = fma(u, in.d, in.c);
-  if (KIND == DK_NORMAL_ICDF) return fma(normcdfinv(up), in.b, in.a);
-  if (KIND == DK_LOGNORMAL_ICDF) return exp_fast(fma(normcdfinv(up), in.b, in.a), sm);
+  if (KIND == DK_NORMAL_ICDF) return fma(normcdfinv_fast(up), in.b, in.a);
+  if (KIND == DK_LOGNORMAL_ICDF) return exp_fast(fma(normcdfinv_fast(up), in.b, in.a), sm);
   if (KIND == DK_GUMBEL) return fma(in.b, neg_log_pos(neg_log01(up, sm), sm), in.a);  // a - b ln(-ln u)
-  if (KIND == DK_EXP_AFFINE) return in.a - in.b * log1p(-up);
+  if (KIND == DK_EXP_AFFINE) {   // a - b ln(1 - u'): the lean logarithm unless 1 - u' rounds to zero
+    const double t = 1.0 - up;
+    return t > 0x1p-1000 ? fma(in.b, neg_log_pos(t, sm), in.a) : in.a - in.b * log1p(-up);
+  }
   return table_quantile(in, tables, up);
 }
 

@@ -44,11 +44,17 @@ from ebn_b200 import expr  # noqa: E402
 run("W5 vehicle grid, 1024 scenarios", W.w5_vehicle_grid(n=4 * 10**6))
 run("W4 vehicle, V fixed: 4 states x 25 outer-loop values", W.w4_vehicle_fixed_v(np.linspace(7, 12, 25), n=2 * 10**7))
 j = W.w1_vehicle(n=10**8)
-j.inputs[:, 3]["lo"] = 400.0   # truncated normals: inverse-CDF path through the generic plan
+j.inputs[:, 3]["lo"] = 400.0   # truncated normal: inverse CDF on the truncation window
+run("W1 with C truncated at 400 (compiled-in plan P,P,U,I,N,N)", j)
+j.inputs[:, 4]["hi"] = 1500.0  # two truncated normals: no compiled-in plan
 j.jit_plan = False
-run("W1 with C truncated at 400 (runtime-dispatched plan)", j)
+run("W1 with C and Ck truncated (runtime-dispatched plan)", j)
 j.jit_plan = True
-run("W1 with C truncated at 400 (plan compiled at run time)", j)
+run("W1 with C and Ck truncated (plan compiled at run time)", j)
+j = W.w1_vehicle(n=10**8)
+for col, (lo, hi) in ((3, (400.0, 460.0)), (4, (1440.0, 1500.0)), (5, (30.0, 80.0))):
+    j.inputs[:, col]["lo"], j.inputs[:, col]["hi"] = lo, hi
+run("W1 with C, Ck and K truncated (compiled-in plan P,P,U,I,I,I)", j)
 k = W.vehicle_consts()
 VEHICLE_TEXT = [
     ("g1", "1 .- (pi .* m .* df.V .* df.A) ./ (df.b0 .* df.K .* g .^ 2) .* ((df.Ck ./ (m .+ M) .- (df.C ./ M)) .^ 2"

@@ -1,5 +1,6 @@
-"""Generates csrc/ebn_fastmath_tables.inc: the -ln(m) reduction table, the 2^(j/64) table and the
-first-quadrant sin/cos cell table with its in-cell polynomials used by ebn_fastmath.cuh. Deterministic; rerun to regenerate.
+"""Generates csrc/ebn_fastmath_tables.inc: the -ln(m) reduction table, the 2^(j/64) table, the
+first-quadrant sin/cos cell table with its in-cell polynomials and the cell table of the inverse normal
+CDF used by ebn_fastmath.cuh. Deterministic; rerun to regenerate.
 
     python tools/gen_fastmath_tables.py [log table bits, default 10] [sin/cos table bits, default 10]
 """
@@ -50,6 +51,22 @@ def _cheb_fit(f, a, b, deg):
     return [float(c[i]) for i in range(n)]
 
 
+def _cheb_fit_centred(f, a, b, deg):
+    """As _cheb_fit, in powers of (x - (a + b)/2)."""
+    mp = mpmath
+    n = deg + 1
+    c = (a + b) / 2
+    xs = [c + (b - a) / 2 * mp.cos(mp.pi * (2 * k + 1) / (2 * n)) for k in range(n)]
+    A = mp.matrix(n, n)
+    y = mp.matrix(n, 1)
+    for i, x in enumerate(xs):
+        for k in range(n):
+            A[i, k] = (x - c) ** k
+        y[i] = f(x)
+    co = mp.lu_solve(A, y)
+    return [float(co[i]) for i in range(n)]
+
+
 def sincos_table(bits):
     """2^bits cells over the first quadrant: sqrt(2)*(sin, cos) of phi_j = (pi/2)(j + 1/2)/2^bits,
     correctly rounded, and the two short polynomials for the offset inside a cell,
@@ -81,6 +98,32 @@ def _hi_word_top(coefs):
     return coefs[:-1] + [struct.unpack("<d", struct.pack("<Q", bits))[0]]
 
 
+ICDF_OCTAVES = 20      # q = min(p, 1-p) in [2^-(ICDF_OCTAVES+1), 1/2]; smaller q takes the library routine
+ICDF_SUB_BITS = 4      # 16 cells per octave of q
+ICDF_DEG = 7
+
+
+def icdf_table():
+    """Phi^-1 for q = min(p, 1 - p) = 2^-e m, m in [1, 2): one degree-7 polynomial in (m - centre) per cell
+    (octave e = 1..ICDF_OCTAVES+1, 16 cells per octave), near-minimax (Chebyshev nodes), max error
+    3e-16 relative to max(1, |z|). Row = 8 coefficients c0..c7 of z(q) <= 0. Rows run with DEcreasing q,
+    so that the row number is a constant minus the top 16 bits of q's high word: cell (e, j) is row
+    (e - 1) * 16 + (15 - j). The first octave (e = 1) only ever sees q = 1/2 exactly (m = 1)."""
+    mp = mpmath
+    sub = 1 << ICDF_SUB_BITS
+    rows = []
+    for e in range(1, ICDF_OCTAVES + 2):
+        for j in reversed(range(sub)):
+            a = 1 + mp.mpf(j) / sub
+            b = 1 + mp.mpf(j + 1) / sub
+
+            def f(m, e=e):
+                q = m * mp.mpf(2) ** (-e)
+                return -mp.sqrt(2) * mp.erfinv(1 - 2 * q) if q < mp.mpf(1) / 2 else mp.sqrt(2) * mp.erfinv(2 * q - 1)
+            rows.append(_cheb_fit_centred(f, a, b, ICDF_DEG))
+    return rows
+
+
 def main():
     log_bits = int(sys.argv[1]) if len(sys.argv) > 1 else 10
     sc_bits = int(sys.argv[2]) if len(sys.argv) > 2 else 10
@@ -110,6 +153,12 @@ def main():
         f.write("#define EBN_COSD_COEFS " + ", ".join(float(c).hex() for c in cd) + "\n")
         f.write("// the highest-order coefficients again, as literals (immediates: their low words are zero)\n")
         f.write(f"#define EBN_SIND_TOP {float(sd[-1]).hex()}\n#define EBN_COSD_TOP {float(cd[-1]).hex()}\n")
+        f.write("// kIcdfTab[(e-1)*16 + 15 - j][k]: z = Phi^-1(q) = sum_k c_k (m - centre)^k for q = 2^-e m in cell j of octave e\n")
+        f.write(f"#define EBN_ICDF_OCTAVES {ICDF_OCTAVES}\n#define EBN_ICDF_SUB_BITS {ICDF_SUB_BITS}\n")
+        f.write(f"static __device__ const __align__(16) double kIcdfTab[{(ICDF_OCTAVES + 1) << ICDF_SUB_BITS}][8] = {{\n")
+        for co in icdf_table():
+            f.write("  {" + ", ".join(float(c).hex() for c in co) + "},\n")
+        f.write("};\n")
     print("wrote", OUT, "mpmath" if mpmath is not None else "longdouble")
 
 
