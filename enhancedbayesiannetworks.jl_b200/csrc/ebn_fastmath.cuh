@@ -182,22 +182,50 @@ __device__ __forceinline__ double log_guarded(double x, const FastMathSmem& sm) 
 // 16 cells per octave from its exponent and top four mantissa bits (one shift of the high word), and the
 // cell carries a degree-7 polynomial in (m - centre): 3e-16 relative to max(1, |z|)
 // (tools/gen_fastmath_tables.py). 11 fp64 operations against ~60 plus two branches of CUDA's
-// normcdfinv. The table (21 KB) stays in global memory behind L1: it is only touched by the
-// truncated-normal kinds. q < 2^-21 (2e-6 of the draws at most) takes the library routine.
+// normcdfinv. The table (16 octaves, 16 KB) lives in shared memory: each lane reads its own row, which
+// the banks serve in parallel (behind L1 the same loads cost ~25 cycles each, measured). It is a
+// function-scope __shared__ array, so only kernels whose sampling plan can draw a truncated normal
+// allocate it; they fill it with icdf_init(). The lookup is branch-free (the row is clamped) so that the
+// loads schedule early; `rare` reports q < 2^-17 (3e-5 of the unit interval) or q = 0, for which the
+// caller substitutes the library routine afterwards.
 static __device__ __noinline__ double normcdfinv_rare(double p) { return normcdfinv(p); }
 
-__device__ __forceinline__ double normcdfinv_fast(double p) {
+// A row is 64 bytes; with that stride every lane's first 16-byte load would fall on one of two bank
+// groups. Rows are spaced 80 bytes apart instead, which spreads random rows over all eight groups.
+constexpr int kIcdfStride = 5;   // double2 per row in shared memory (4 used)
+__device__ __forceinline__ double2* icdf_smem() {
+  __shared__ double2 s_icdf[EBN_ICDF_ROWS * kIcdfStride];
+  return s_icdf;
+}
+__device__ __forceinline__ void icdf_init(int tid, int nthreads) {
+  double2* t = icdf_smem();
+  const double2* g = reinterpret_cast<const double2*>(kIcdfTab);
+  for (int i = tid; i < EBN_ICDF_ROWS * 4; i += nthreads) t[(i >> 2) * kIcdfStride + (i & 3)] = g[i];
+}
+
+// SMEM: read the cell from the shared-memory copy (compile-time sampling plans), else from the global
+// table behind L1 (run-time dispatched plans: no shared memory is spent on a table most jobs never touch;
+// the arithmetic is the same, so both give the same bits).
+template <bool SMEM>
+__device__ __forceinline__ double normcdfinv_cells(double p, bool& rare) {
   const bool lower = p < 0.5;
   const double q = lower ? p : 1.0 - p;
   const int hi = __double2hiint(q);
-  const unsigned row = (unsigned)((1022 * 16 + 15) - (hi >> 16));   // rows run with decreasing q
-  if (row >= (unsigned)((EBN_ICDF_OCTAVES + 1) << EBN_ICDF_SUB_BITS)) return normcdfinv_rare(p);
+  unsigned row = (unsigned)((1022 * 16) - (hi >> 16));   // rows run with decreasing q; q = 1/2 is row 0
+  rare = row >= (unsigned)EBN_ICDF_ROWS;
+  row = rare ? EBN_ICDF_ROWS - 1 : row;
   const int mhi = (int)hi_of_one_two((uint32_t)hi);
   const double m = __hiloint2double(mhi, __double2loint(q));
   const double c = __hiloint2double((mhi & (int)0xFFFF0000) | 0x00008000, 0);   // centre of the cell
   const double dm = m - c;
-  const double2* co = reinterpret_cast<const double2*>(kIcdfTab[row]);
-  const double2 c01 = __ldg(co), c23 = __ldg(co + 1), c45 = __ldg(co + 2), c67 = __ldg(co + 3);
+  double2 c01, c23, c45, c67;
+  if constexpr (SMEM) {
+    const double2* co = icdf_smem() + kIcdfStride * row;
+    c01 = co[0], c23 = co[1], c45 = co[2], c67 = co[3];
+  } else {
+    const double2* co = reinterpret_cast<const double2*>(kIcdfTab[row]);
+    c01 = __ldg(co), c23 = __ldg(co + 1), c45 = __ldg(co + 2), c67 = __ldg(co + 3);
+  }
   double z = fma(dm, c67.y, c67.x);
   z = fma(dm, z, c45.y);
   z = fma(dm, z, c45.x);
@@ -206,6 +234,25 @@ __device__ __forceinline__ double normcdfinv_fast(double p) {
   z = fma(dm, z, c01.y);
   z = fma(dm, z, c01.x);
   return lower ? z : -z;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ double normcdfinv_fast(double p) {
+  bool rare;
+  const double z = normcdfinv_cells<SMEM>(p, rare);
+  return rare ? normcdfinv_rare(p) : z;
+}
+
+// Both samples of a pair: the two lookups interleave, one (never taken) branch for the pair.
+template <bool SMEM>
+__device__ __forceinline__ void normcdfinv_fast2(double p0, double p1, double& z0, double& z1) {
+  bool r0, r1;
+  z0 = normcdfinv_cells<SMEM>(p0, r0);
+  z1 = normcdfinv_cells<SMEM>(p1, r1);
+  if (r0 | r1) {
+    if (r0) z0 = normcdfinv_rare(p0);
+    if (r1) z1 = normcdfinv_rare(p1);
+  }
 }
 
 // sqrt(t) for t in [2^-60, 2^60]: MUFU.RSQ64H seed y ~ t^-1/2 (relative error e0 ~ 2^-20),

@@ -111,6 +111,7 @@ struct DriverApi {
                            CUstream, void**, void**) = nullptr;
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
 } g_drv;
 
 bool driver_load(std::string* err) {
@@ -122,6 +123,7 @@ bool driver_load(std::string* err) {
       {(void**)&g_drv.LaunchKernel, "cuLaunchKernel"},
       {(void**)&g_drv.OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor"},
       {(void**)&g_drv.GetErrorString, "cuGetErrorString"},
+      {(void**)&g_drv.FuncSetAttribute, "cuFuncSetAttribute"},
   };
   for (auto& s : syms) {
     cudaDriverEntryPointQueryResult q;
@@ -418,6 +420,8 @@ bool jit_occupancy(JitKernel* k, int device, int threads, size_t dyn_smem, int* 
   std::lock_guard<std::mutex> lk(g_mu);
   CUfunction fn;
   if (!function_on(k, device, &fn, err)) return false;
+  // static + dynamic shared memory may pass 48 KB (histogram edges and bins next to the tables): opt in
+  if (dyn_smem) g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn_smem);
   const CUresult r = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, dyn_smem);
   if (r != CUDA_SUCCESS) {
     *err = "cuOccupancyMaxActiveBlocksPerMultiprocessor: " + cu_err(r);
@@ -431,6 +435,7 @@ bool jit_launch(JitKernel* k, int device, int blocks, int threads, size_t dyn_sm
   std::lock_guard<std::mutex> lk(g_mu);
   CUfunction fn;
   if (!function_on(k, device, &fn, err)) return false;
+  if (dyn_smem) g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn_smem);
   const CUresult r = g_drv.LaunchKernel(fn, (unsigned)blocks, 1, 1, (unsigned)threads, 1, 1, (unsigned)dyn_smem,
                                         (CUstream)st, args, nullptr);
   if (r != CUDA_SUCCESS) {

@@ -60,6 +60,18 @@ struct StaticCopulaPlan {
   static constexpr int kinds[sizeof...(K) ? sizeof...(K) : 1] = {K...};
 };
 
+// Can the plan draw a truncated (inverse-CDF) normal? Only then does the kernel hold the Phi^-1 cell table.
+template <class Plan>
+__host__ __device__ constexpr bool plan_uses_icdf() {
+  if constexpr (Plan::is_static || Plan::is_static_copula) {
+    for (int i = 0; i < Plan::n; ++i)
+      if (Plan::kinds[i] == DK_NORMAL_ICDF || Plan::kinds[i] == DK_LOGNORMAL_ICDF) return true;
+    return false;
+  } else {
+    return false;   // kinds known at run time only: the cells are read from global memory (see icdf<>)
+  }
+}
+
 // Word offset of input J in a static plan, and the number of Philox calls a pair needs.
 template <class Plan, int J>
 __host__ __device__ constexpr int static_word_offset() {
@@ -126,8 +138,8 @@ struct CopulaMarginals {
           x0[J] = fma(phi_clamped(z0), in.b, in.a);
           x1[J] = fma(phi_clamped(z1), in.b, in.a);
         } else {
-          x0[J] = icdf<KIND>(in, tables, sm, phi_clamped(z0));
-          x1[J] = icdf<KIND>(in, tables, sm, phi_clamped(z1));
+          x0[J] = icdf<KIND, plan_uses_icdf<Plan>()>(in, tables, sm, phi_clamped(z0));
+          x1[J] = icdf<KIND, plan_uses_icdf<Plan>()>(in, tables, sm, phi_clamped(z1));
         }
       }
       CopulaMarginals<Plan, J + 1>::run(sp, L, tables, sm, e0, e1, x0, x1);
@@ -142,7 +154,7 @@ struct DrawAll {
                                              const FastMathSmem& sm, double* x0, double* x1) {
     if constexpr (J < Plan::n) {
       StaticWords<static_word_offset<Plan, J>()> ws{ph};
-      draw_pair<Plan::kinds[J]>(sp[J], ws, pc, (uint32_t)J, tables, sm, x0[J], x1[J]);
+      draw_pair<Plan::kinds[J], StaticWords<static_word_offset<Plan, J>()>, plan_uses_icdf<Plan>()>(sp[J], ws, pc, (uint32_t)J, tables, sm, x0[J], x1[J]);
       DrawAll<Plan, XCAP, J + 1>::run(sp, ph, pc, tables, sm, x0, x1);
     }
   }
@@ -219,7 +231,7 @@ struct BackAll {
                                              const double* tables, const FastMathSmem& sm,
                                              double* x0, double* x1) {
     if constexpr (J < Plan::n) {
-      draw_back<Plan::kinds[J]>(sp[J], st[J], pc, (uint32_t)J, tables, sm, x0[J], x1[J]);
+      draw_back<Plan::kinds[J], plan_uses_icdf<Plan>()>(sp[J], st[J], pc, (uint32_t)J, tables, sm, x0[J], x1[J]);
       BackAll<Plan, J + 1>::run(sp, st, pc, tables, sm, x0, x1);
     }
   }
@@ -339,6 +351,7 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
 
   const int tid = threadIdx.x;
   fastmath_init(s_fm, tid, kThreads);
+  if constexpr (plan_uses_icdf<Plan>()) icdf_init(tid, kThreads);
   if (MODE == 1) {
     for (int i = tid; i < p.nedges; i += kThreads) s_edges[i] = p.edges[i];
   }
@@ -468,6 +481,7 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
   typename LS::Ctx ctx;
   LS::setup(ctx, p.consts, p.n_consts, p.d, &s_fm);
   fastmath_init(s_fm, threadIdx.x, kThreads);
+  if constexpr (plan_uses_icdf<Plan>()) icdf_init(threadIdx.x, kThreads);
   if (threadIdx.x < p.d) s_plan[threadIdx.x] = p.plan[(int64_t)scenario * p.d + threadIdx.x];
   if (Plan::is_copula) {
     const double* L = p.chol + (p.chol_shared ? 0 : (int64_t)scenario * p.d * p.d);
@@ -557,12 +571,18 @@ struct LsLaunch {
   static cudaError_t occ2(int mode, size_t dyn, int* out) {
     if (mode == 0)
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, mc_kernel<LS, Plan, 0>, kThreads, dyn);
+    // histogram mode: static tables + dynamic edges and bins may pass 48 KB together: opt in
+    cudaFuncSetAttribute(mc_kernel<LS, Plan, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, mc_kernel<LS, Plan, 1>, kThreads, dyn);
   }
   template <class LS, class Plan>
   static cudaError_t launch2(int mode, const McParams& p, int blocks, size_t dyn, cudaStream_t st) {
-    if (mode == 0) mc_kernel<LS, Plan, 0><<<blocks, kThreads, dyn, st>>>(p);
-    else mc_kernel<LS, Plan, 1><<<blocks, kThreads, dyn, st>>>(p);
+    if (mode == 0) {
+      mc_kernel<LS, Plan, 0><<<blocks, kThreads, dyn, st>>>(p);
+    } else {
+      cudaFuncSetAttribute(mc_kernel<LS, Plan, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      mc_kernel<LS, Plan, 1><<<blocks, kThreads, dyn, st>>>(p);
+    }
     return cudaGetLastError();
   }
   template <class LS, class Plan>

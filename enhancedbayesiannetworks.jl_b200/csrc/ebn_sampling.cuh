@@ -147,12 +147,17 @@ __device__ __forceinline__ double table_quantile(const DevInput& in, const doubl
 
 // x = Q(u') for the inverse-CDF kinds, u' = c + u*d already mapped into the
 // truncation window.
-template <int KIND>
+// CELLS: the kernel holds the Phi^-1 cell table in shared memory (compile-time sampling plans that can
+// draw a truncated normal); otherwise the same cells are read from global memory (same bits, slower).
+template <int KIND, bool CELLS = false>
 __device__ __forceinline__ double icdf(const DevInput& in, const double* tables,
                                        const FastMathSmem& sm, double u) {
   const double up = fma(u, in.d, in.c);
-  if (KIND == DK_NORMAL_ICDF) return fma(normcdfinv_fast(up), in.b, in.a);
-  if (KIND == DK_LOGNORMAL_ICDF) return exp_fast(fma(normcdfinv_fast(up), in.b, in.a), sm);
+  if (KIND == DK_NORMAL_ICDF || KIND == DK_LOGNORMAL_ICDF) {
+    const double z = normcdfinv_fast<CELLS>(up);
+    const double y = fma(z, in.b, in.a);
+    return KIND == DK_LOGNORMAL_ICDF ? exp_fast(y, sm) : y;
+  }
   if (KIND == DK_GUMBEL) return fma(in.b, neg_log_pos(neg_log01(up, sm), sm), in.a);  // a - b ln(-ln u)
   if (KIND == DK_EXP_AFFINE) {   // a - b ln(1 - u'): the lean logarithm unless 1 - u' rounds to zero
     const double t = 1.0 - up;
@@ -188,7 +193,7 @@ __device__ __forceinline__ InState draw_front(const WS& ws, const FastMathSmem& 
   return st;
 }
 
-template <int KIND>
+template <int KIND, bool CELLS = false>
 __device__ __forceinline__ void draw_back(const DevInput& in, const InState& st, const PairCtr& pc,
                                           uint32_t j, const double* tables,
                                           const FastMathSmem& sm, double& x0, double& x1) {
@@ -218,6 +223,15 @@ __device__ __forceinline__ void draw_back(const DevInput& in, const InState& st,
   } else if (KIND == DK_GAMMA_MT) {
     x0 = gamma_mt(in, pc, j, 0u, sm);
     x1 = gamma_mt(in, pc, j, 1u, sm);
+  } else if (KIND == DK_NORMAL_ICDF || KIND == DK_LOGNORMAL_ICDF) {
+    double z0, z1;
+    normcdfinv_fast2<CELLS>(fma(u52w(st.w0, st.w1), in.d, in.c), fma(u52w(st.w2, st.w3), in.d, in.c), z0, z1);
+    x0 = fma(z0, in.b, in.a);
+    x1 = fma(z1, in.b, in.a);
+    if (KIND == DK_LOGNORMAL_ICDF) {
+      x0 = exp_fast(x0, sm);
+      x1 = exp_fast(x1, sm);
+    }
   } else {
     x0 = icdf<KIND>(in, tables, sm, u52w(st.w0, st.w1));
     x1 = icdf<KIND>(in, tables, sm, u52w(st.w2, st.w3));
@@ -226,11 +240,11 @@ __device__ __forceinline__ void draw_back(const DevInput& in, const InState& st,
 
 // Draws input j for both samples of a pair. KIND is a DevKind, WS a word source
 // positioned at the input's first word.
-template <int KIND, class WS>
+template <int KIND, class WS, bool CELLS = false>
 __device__ __forceinline__ void draw_pair(const DevInput& in, const WS& ws, const PairCtr& pc,
                                           uint32_t j, const double* tables,
                                           const FastMathSmem& sm, double& x0, double& x1) {
-  draw_back<KIND>(in, draw_front<KIND>(ws, sm), pc, j, tables, sm, x0, x1);
+  draw_back<KIND, CELLS>(in, draw_front<KIND>(ws, sm), pc, j, tables, sm, x0, x1);
 }
 
 // Runtime (warp-uniform) dispatch on the kind; the generic, slower path.

@@ -98,29 +98,30 @@ def _hi_word_top(coefs):
     return coefs[:-1] + [struct.unpack("<d", struct.pack("<Q", bits))[0]]
 
 
-ICDF_OCTAVES = 20      # q = min(p, 1-p) in [2^-(ICDF_OCTAVES+1), 1/2]; smaller q takes the library routine
+ICDF_OCTAVES = 16      # q = min(p, 1-p) in [2^-(ICDF_OCTAVES+1), 1/2]; smaller q (3e-5 of the unit interval)
+                       # takes the library routine
 ICDF_SUB_BITS = 4      # 16 cells per octave of q
 ICDF_DEG = 7
 
 
 def icdf_table():
     """Phi^-1 for q = min(p, 1 - p) = 2^-e m, m in [1, 2): one degree-7 polynomial in (m - centre) per cell
-    (octave e = 1..ICDF_OCTAVES+1, 16 cells per octave), near-minimax (Chebyshev nodes), max error
-    3e-16 relative to max(1, |z|). Row = 8 coefficients c0..c7 of z(q) <= 0. Rows run with DEcreasing q,
-    so that the row number is a constant minus the top 16 bits of q's high word: cell (e, j) is row
-    (e - 1) * 16 + (15 - j). The first octave (e = 1) only ever sees q = 1/2 exactly (m = 1)."""
+    (16 cells per octave), near-minimax (Chebyshev nodes), max error 3e-16 relative to max(1, |z|).
+    Row = 8 coefficients c0..c7 of z(q) <= 0. Rows run with DEcreasing q, so that the row number is a
+    constant minus the top 16 bits of q's high word: row 0 is the cell that holds q = 1/2 exactly
+    (e = 1, j = 0), and cell (e, j) of the octaves e = 2..ICDF_OCTAVES+1 is row 1 + (e - 2) * 16 + (15 - j)."""
     mp = mpmath
     sub = 1 << ICDF_SUB_BITS
     rows = []
-    for e in range(1, ICDF_OCTAVES + 2):
-        for j in reversed(range(sub)):
-            a = 1 + mp.mpf(j) / sub
-            b = 1 + mp.mpf(j + 1) / sub
+    cells = [(1, 0)] + [(e, j) for e in range(2, ICDF_OCTAVES + 2) for j in reversed(range(sub))]
+    for e, j in cells:
+        a = 1 + mp.mpf(j) / sub
+        b = 1 + mp.mpf(j + 1) / sub
 
-            def f(m, e=e):
-                q = m * mp.mpf(2) ** (-e)
-                return -mp.sqrt(2) * mp.erfinv(1 - 2 * q) if q < mp.mpf(1) / 2 else mp.sqrt(2) * mp.erfinv(2 * q - 1)
-            rows.append(_cheb_fit_centred(f, a, b, ICDF_DEG))
+        def f(m, e=e):
+            q = m * mp.mpf(2) ** (-e)
+            return -mp.sqrt(2) * mp.erfinv(1 - 2 * q) if q < mp.mpf(1) / 2 else mp.sqrt(2) * mp.erfinv(2 * q - 1)
+        rows.append(_cheb_fit_centred(f, a, b, ICDF_DEG))
     return rows
 
 
@@ -153,9 +154,11 @@ def main():
         f.write("#define EBN_COSD_COEFS " + ", ".join(float(c).hex() for c in cd) + "\n")
         f.write("// the highest-order coefficients again, as literals (immediates: their low words are zero)\n")
         f.write(f"#define EBN_SIND_TOP {float(sd[-1]).hex()}\n#define EBN_COSD_TOP {float(cd[-1]).hex()}\n")
-        f.write("// kIcdfTab[(e-1)*16 + 15 - j][k]: z = Phi^-1(q) = sum_k c_k (m - centre)^k for q = 2^-e m in cell j of octave e\n")
+        f.write("// kIcdfTab[row][k]: z = Phi^-1(q) = sum_k c_k (m - centre)^k for q = 2^-e m in cell j of octave e;\n")
+        f.write("// row 0: q = 1/2, then row = 1 + (e-2)*16 + 15 - j for e = 2..EBN_ICDF_OCTAVES+1\n")
         f.write(f"#define EBN_ICDF_OCTAVES {ICDF_OCTAVES}\n#define EBN_ICDF_SUB_BITS {ICDF_SUB_BITS}\n")
-        f.write(f"static __device__ const __align__(16) double kIcdfTab[{(ICDF_OCTAVES + 1) << ICDF_SUB_BITS}][8] = {{\n")
+        f.write(f"#define EBN_ICDF_ROWS {1 + (ICDF_OCTAVES << ICDF_SUB_BITS)}\n")
+        f.write("static __device__ const __align__(16) double kIcdfTab[EBN_ICDF_ROWS][8] = {\n")
         for co in icdf_table():
             f.write("  {" + ", ".join(float(c).hex() for c in co) + "},\n")
         f.write("};\n")
