@@ -307,16 +307,18 @@ __device__ __forceinline__ unsigned static_count_loop(const typename LS::Ctx& ct
   return cnt;
 }
 
-// Equally spaced edges: a direct index from one FMA, then an exact fix-up against the real
-// edges (at most a step or two), so the result is identical to the binary search.
+// Equally spaced edges (to 1e-9 of a step, checked by the host): the direct index floor((y - e0)/h) is
+// within one cell of the truth, so the number of edges <= y is k + [edges[k] <= y] + [edges[k+1] <= y]
+// with k the clamped estimate — two independent shared-memory loads and two comparisons, no loop and no
+// branch, identical to the binary search (NaN -> nedges).
 __device__ __forceinline__ int find_bin_uniform(const double* edges, int nedges, double y,
                                                 double e0, double inv_h) {
-  if (!(y == y)) return nedges;
-  const double pos = (y - e0) * inv_h;
-  int b = pos < 0.0 ? 0 : (pos >= (double)nedges ? nedges : (int)pos + 1);
-  while (b > 0 && y < edges[b - 1]) --b;
-  while (b < nedges && edges[b] <= y) ++b;
-  return b;
+  int k = __double2int_rd((y - e0) * inv_h);    // saturating; NaN -> 0
+  k = max(0, min(k, nedges - 1));
+  const int k1 = min(k + 1, nedges - 1);
+  const double lo = edges[k], hi = edges[k1];
+  int b = k + (int)(lo <= y) + (int)((k1 > k) & (hi <= y));
+  return (y == y) ? b : nedges;
 }
 
 __device__ __forceinline__ int find_bin(const double* edges, int nedges, double y) {

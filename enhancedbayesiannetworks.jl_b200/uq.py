@@ -9,6 +9,7 @@ There is no CPU fallback: a model that is not an `Expression`, a `Poly` or a `Ca
 """
 from __future__ import annotations
 
+import dataclasses
 import itertools
 import math
 from dataclasses import dataclass
@@ -514,11 +515,187 @@ def _monotone_on_replay(models, performance, inputs, dims, k: int, seed: int, ro
     return bool(np.all(D >= 0.0) or np.all(D <= 0.0))
 
 
+# Quantile of a p-box family as formula text over the family's parameters p0, p1 and ONE standard
+# variate s per sample (N(0,1) for the normal family, U(0,1) otherwise): every member of the family
+# sees the same s, which is what slices the p-box into an interval per sample.
+_PBOX_QUANTILE = {
+    "Normal": ("normal", "({p0} + {p1} * {s})"),
+    "LogNormal": ("normal", "exp({p0} + {p1} * {s})"),
+    "Uniform": ("uniform", "({p0} + ({p1} - {p0}) * {s})"),
+    "Gumbel": ("uniform", "({p0} - {p1} * log(-log({s})))"),
+}
+SLICING_LEVELS = (0.0, 0.5, 1.0)   # where each per-sample interval is probed: both ends and the middle
+
+
+def _slicing_texts(models, performance):
+    """(model name, text) chain + performance text of a chain that can be written as formulas."""
+    chain = []
+    consts: Dict[str, float] = {}
+    for m in models:
+        f = m.func
+        if isinstance(f, Expression):
+            consts.update(dict(f.constants))
+            chain.append((m.name, f.text))
+        elif isinstance(f, Poly):
+            chain.append((m.name, _poly_text(f)))
+        else:
+            return None
+    if isinstance(performance, Expression):
+        consts.update(dict(performance.constants))
+        perf = performance.text
+    elif isinstance(performance, Poly):
+        perf = _poly_text(performance)
+    elif isinstance(performance, str):
+        perf = f"df.{performance}"
+    elif performance is None and chain:
+        perf = f"df.{chain[-1][0]}"
+    else:
+        return None
+    return chain, perf, consts
+
+
+def random_slicing_general(models, performance, scenario_inputs, sim: CudaRandomSlicing, levels=SLICING_LEVELS):
+    """UQ.jl RandomSlicing (A6) for model chains that are formulas, without a monotonicity assumption.
+
+    Per sample an Interval input is its box [lb, ub]; a p-box input is sliced by ONE standard variate
+    into [min, max] of the family's quantile over the vertices of its parameter box (any number of
+    interval parameters). The model chain is then evaluated, inside the kernel, at every combination
+    of `levels` (ends and middle) of the per-sample intervals, and the failure indicator of the
+    sample's smallest / largest g is counted: pf_ub = P(min g < 0), pf_lb = P(max g < 0). Both sides
+    are scenarios of ONE ebn_pf_batch call on the same Philox streams.
+    The whole construction is a rewrite of the formulas (the candidates become one expression under
+    min / max), so it runs through EBN_LS_EXPRESSION with no extra kernel.
+    Exact when the per-sample extreme lies at a probed point (always for chains that are monotone or
+    convex/concave with the extreme at an end or the middle); otherwise an inner approximation that
+    tightens with more levels."""
+    import ast
+    import copy
+    texts = _slicing_texts(list(models), performance)
+    if texts is None:
+        raise UnsupportedModel("general RandomSlicing needs Expression / Poly models")
+    chain, perf_text, consts = texts
+    base = list(scenario_inputs[0])
+    norm = _expr._norm
+    # ---- columns of the rewritten job ---------------------------------------------------------
+    columns: List[str] = []             # input names of the rewritten job, in order
+    makers = []                         # per column: function(scenario inputs) -> UQ input
+    interval_of: Dict[str, Tuple[str, str]] = {}   # imprecise input -> (text of per-sample lower end, upper end)
+    for pos, inp in enumerate(base):
+        if isinstance(inp, Interval):
+            lo, hi = f"{inp.name}__lo", f"{inp.name}__hi"
+            columns += [lo, hi]
+            makers += [lambda ins, pos=pos, lo=lo: Parameter(float(ins[pos].lb), lo),
+                       lambda ins, pos=pos, hi=hi: Parameter(float(ins[pos].ub), hi)]
+            interval_of[norm(inp.name)] = (norm(lo), norm(hi))
+        elif isinstance(inp, ProbabilityBox):
+            fam = inp.family.__name__
+            if fam not in _PBOX_QUANTILE or len(inp.parameters) != 2:
+                raise UnsupportedModel(f"RandomSlicing on the device has no quantile formula for a {fam} p-box")
+            if inp.lb > -INF or inp.ub < INF:
+                raise UnsupportedModel("RandomSlicing on the device takes untruncated p-boxes")
+            kind, qtext = _PBOX_QUANTILE[fam]
+            sname = f"{inp.name}__s"
+            columns.append(sname)
+            makers.append(lambda ins, sname=sname, kind=kind:
+                          RandomVariable(Normal(0.0, 1.0), sname) if kind == "normal"
+                          else RandomVariable(_uniform01(), sname))
+            pnames = []
+            for k in range(2):
+                for side in ("lo", "hi"):
+                    nm = f"{inp.name}__p{k}{side}"
+                    columns.append(nm)
+                    makers.append(lambda ins, pos=pos, k=k, side=side, nm=nm:
+                                  Parameter(float(getattr(ins[pos].parameters[k], "lb" if side == "lo" else "ub")), nm))
+                pnames.append((norm(f"{inp.name}__p{k}lo"), norm(f"{inp.name}__p{k}hi")))
+            verts = [qtext.format(p0=a, p1=b, s=norm(sname)) for a in pnames[0] for b in pnames[1]]
+            interval_of[norm(inp.name)] = ("min(" + ", ".join(verts) + ")", "max(" + ", ".join(verts) + ")")
+        else:
+            columns.append(inp.name)
+            makers.append(lambda ins, pos=pos: ins[pos])
+    if not interval_of:
+        raise AssertionError("RandomSlicing needs at least one Interval / ProbabilityBox input")
+    columns.append("__side")
+    if len(columns) > L.EBN_MAX_INPUTS:
+        raise UnsupportedModel("too many columns after slicing the imprecise inputs")
+
+    # ---- the chain as ONE expression per candidate: model names and imprecise inputs substituted ----
+    class Subst(ast.NodeTransformer):
+        def __init__(self, table):
+            self.table = table
+
+        def visit_Name(self, node):
+            return copy.deepcopy(self.table[node.id]) if node.id in self.table else node
+
+    def tree(text):
+        t = _expr._parse(text)
+        if _expr._count_hidden(t):
+            raise UnsupportedModel("RandomSlicing on the device: in-model randomness cannot be sliced")
+        return t
+
+    model_trees = [(norm(n), tree(t)) for n, t in chain]
+    perf_tree = tree(perf_text)
+    ends = {name: (tree(lo), tree(hi)) for name, (lo, hi) in interval_of.items()}
+    names = list(ends)
+    cands = []
+    for combo in itertools.product(levels, repeat=len(names)):
+        table = {}
+        for name, lam in zip(names, combo):
+            lo, hi = ends[name]
+            if lam == 0.0:
+                table[name] = lo
+            elif lam == 1.0:
+                table[name] = hi
+            else:       # lo + lam * (hi - lo)
+                table[name] = ast.BinOp(copy.deepcopy(lo), ast.Add(),
+                                        ast.BinOp(ast.Constant(float(lam)), ast.Mult(),
+                                                  ast.BinOp(copy.deepcopy(hi), ast.Sub(), copy.deepcopy(lo))))
+        for mname, mt in model_trees:      # a later model sees the earlier ones already substituted
+            table[mname] = Subst(table).visit(copy.deepcopy(mt))
+        cands.append(ast.unparse(Subst(table).visit(copy.deepcopy(perf_tree))))
+    gmin = "min(" + ", ".join(cands) + ")" if len(cands) > 1 else cands[0]
+    gmax = "max(" + ", ".join(cands) + ")" if len(cands) > 1 else cands[0]
+    final = f"_ifelse(__side < 0.5, {gmax}, {gmin})"   # side 0: lower bound of pf, side 1: upper bound
+    try:
+        prog = _expr.compile_program(columns, [], final, consts)
+        L.expression_check(prog.consts, prog.d)
+    except (_expr.ExpressionError, L.EbnError) as e:
+        raise UnsupportedModel(f"RandomSlicing on the device: {e}") from None
+    low = Lowered(L.LS_EXPRESSION, prog.consts, columns, [], prog.columns)
+    # ---- one batch: every scenario twice (side 0 / 1) on the scenario's stream -------------------
+    rows, stream = [], []
+    for s, ins in enumerate(scenario_inputs):
+        if [type(i) for i in ins] != [type(i) for i in base]:
+            raise UnsupportedModel("RandomSlicing on the device: scenarios differ in the kind of their inputs")
+        real = [mk(list(ins)) for mk in makers]
+        for side in (0.0, 1.0):
+            rows.append(real + [Parameter(side, "__side")])
+            stream.append(s)
+    inner = sim.lb
+    job = build_job(low, rows, inner, stream_id=np.array(stream, dtype=np.uint32))
+    _, pf, _ = L.pf_batch(job)
+    out, n = [], inner.n
+    for s in range(len(scenario_inputs)):
+        lb, ub = float(pf[2 * s]), float(pf[2 * s + 1])
+        out.append(((lb, ub), (math.sqrt(max(lb - lb * lb, 0) / n), Samples(job, 2 * s, low.out_columns)),
+                    (math.sqrt(max(ub - ub * ub, 0) / n), Samples(job, 2 * s + 1, low.out_columns))))
+    return out
+
+
+def _uniform01():
+    from .distributions import Uniform
+    return Uniform(0.0, 1.0)
+
+
 def random_slicing(models, performance, scenario_inputs, sim: CudaRandomSlicing):
     """UQ.jl RandomSlicing (A6) for limit states monotone in each imprecise input: the per-sample
     extremes over the input boxes are then attained at the box vertices, so
     pf_lb / pf_ub are the extreme vertex probabilities (evaluated with common random numbers).
-    Returns [((lb, ub), (std_lb, Samples), (std_ub, Samples))] per scenario."""
+    Returns [((lb, ub), (std_lb, Samples), (std_ub, Samples))] per scenario.
+    Chains that are formulas (Expression / Poly) take `random_slicing_general` instead: per-sample
+    extremes over the sliced boxes inside the kernel, no monotonicity needed, p-boxes with two interval
+    parameters. What is left here are the catalogue functors (compiled-in limit states)."""
+    if _slicing_texts(list(models), performance) is not None:
+        return random_slicing_general(models, performance, scenario_inputs, sim)
     inner = sim.lb
     dims_per_s = [_imprecise_dims(inp) for inp in scenario_inputs]
     for inputs, dims in zip(scenario_inputs, dims_per_s):
@@ -550,8 +727,8 @@ def output_histograms(models, scenario_inputs, sim: CudaMonteCarlo, edges: Optio
     low = lower(models, None, input_names(scenario_inputs[0]), prefer_expression=big)
     job = build_job(low, scenario_inputs, sim)
     if edges is None:
-        pilot = L.Job(job.limit_state, job.consts, job.inputs, min(job.n, 1 << 16), job.seed, job.strict,
-                      tables=job.tables)
+        # every field of the job carries over to the pilot (copula factors, stream ids, fp32 sampling, tables)
+        pilot = dataclasses.replace(job, n=min(job.n, 1 << 16))
         _, s1, s2 = L.hist_batch(pilot, np.array([0.0]))
         m = s1 / pilot.n
         sd = np.sqrt(np.maximum(s2 / pilot.n - m * m, 0.0))

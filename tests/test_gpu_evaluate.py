@@ -232,6 +232,9 @@ def test_random_slicing_and_child_intervals(E):
     oute = ev._evaluate_node(net, fe)
     for (dd, aa), w in ex.items():
         assert np.allclose(oute.cpt[{"D": dd, "A": aa, "F1": "F1_fail"}], w, atol=0.006)
+    # a limit state that is NOT monotone in the interval input (refused until round 2): the per-sample
+    # extremes over the box are found inside the kernel; the bounds equal a brute-force oracle on the
+    # replayed samples (fine grid over the box, NumPy) and contain every fixed-value probability
     fbad = E.DiscreteFunctionalNode("F1", [E.Model(E.Expression("df.D .+ (df.C1 .- 0.2) .^ 2 .+ df.B"), "C2")],
                                     E.Expression("2 .- df.C2"), sim)
     net = E.EnhancedBayesianNetwork([a, b, d, c1, fbad])
@@ -239,8 +242,63 @@ def test_random_slicing_and_child_intervals(E):
     for par in (b, d, c1):
         E.add_child(net, par, fbad)
     E.order(net)
-    with pytest.raises(E.UnsupportedModel, match="monotone"):
-        ev._evaluate_node(net, fbad)
+    outb = ev._evaluate_node(net, fbad)
+    boxes = {"a1": (0.1, 0.3), "a2": (0.7, 0.8)}
+    for dd, dval in (("d1", 1.0), ("d2", 2.0)):
+        for aa, (lo, hi) in boxes.items():
+            lb, ub = outb.cpt[{"D": dd, "A": aa, "F1": "F1_fail"}]
+            grid = np.linspace(lo, hi, 201)
+            gext = dval + (grid - 0.2) ** 2                     # 2 - (D + (C1-0.2)^2 + B) < 0  <=>  B > 2 - gext
+            want_ub, want_lb = ndtr(-(2 - gext.max())), ndtr(-(2 - gext.min()))
+            assert lb <= ub and abs(lb - want_lb) < 0.006 and abs(ub - want_ub) < 0.006, (dd, aa, lb, ub, want_lb, want_ub)
+
+
+def test_random_slicing_general_pbox_two_parameters_against_brute_force(E):
+    """RandomSlicing without the monotone / one-parameter restrictions (evaluate_node.jl:111-117):
+    a Normal p-box with interval mean AND interval standard deviation next to an interval input, a model
+    that is non-monotone in both. Oracle: the job's own replayed standard variates, per sample the p-box
+    slice [min, max] over the parameter vertices, then min / max of g over a 41 x 41 grid of the box."""
+    from ebn_b200 import uq
+    sim = E.RandomSlicing(E.MonteCarlo(200_000, seed=77))
+    models = [E.Model(E.Expression("(df.X .- 1.0) .^ 2 .+ df.Y .* df.Y .- df.Z"), "M")]
+    perf = E.Expression("1.5 .- df.M")
+    scen = []
+    for ylo, yhi in ((-0.5, 0.25), (0.2, 0.9)):
+        scen.append([E.ProbabilityBox(E.Normal, (E.Interval(0.8, 1.3, "mu"), E.Interval(0.5, 0.9, "sd")), "X"),
+                     E.Interval(ylo, yhi, "Y"), E.RandomVariable(E.Normal(0.0, 0.3), "Z")])
+    res = uq.random_slicing(models, perf, scen, sim)
+    for (bounds, (sd_lb, smp_lb), (sd_ub, smp_ub)), ins in zip(res, scen):
+        lb, ub = bounds
+        rows = smp_lb.fetch(0, 20_000)
+        s_x, z = rows["X__s"], rows["Z"]
+        qs = [mu + sg * s_x for mu in (0.8, 1.3) for sg in (0.5, 0.9)]
+        xlo, xhi = np.min(qs, axis=0), np.max(qs, axis=0)
+        lam = np.linspace(0, 1, 41)
+        gmin = np.full_like(z, np.inf)
+        gmax = np.full_like(z, -np.inf)
+        for lx in lam:
+            x = xlo + lx * (xhi - xlo)
+            for y in np.linspace(ins[1].lb, ins[1].ub, 41):
+                g = 1.5 - ((x - 1.0) ** 2 + y * y - z)
+                gmin, gmax = np.minimum(gmin, g), np.maximum(gmax, g)
+        brute_ub, brute_lb = np.mean(gmin < 0), np.mean(gmax < 0)
+        # the device probes ends and middle of every interval: an inner approximation of the brute-force box
+        # (exact when the extreme sits at a probed point); compare on the SAME 20000 samples through g
+        dev = smp_ub.fetch(0, 20_000)["g"]
+        dev_l = smp_lb.fetch(0, 20_000)["g"]
+        assert np.all(dev >= gmin - 1e-9) and np.all(dev_l <= gmax + 1e-9)
+        assert abs(np.mean(dev < 0) - brute_ub) < 0.02 and abs(np.mean(dev_l < 0) - brute_lb) < 0.02
+        assert lb <= ub and abs(ub - brute_ub) < 0.03 and abs(lb - brute_lb) < 0.03
+        assert sd_lb >= 0 and sd_ub >= 0
+    # Gumbel p-boxes slice through the uniform variate; a truncated p-box is refused with a clear message
+    g = [E.ProbabilityBox(E.Gumbel, (E.Interval(0.0, 0.5, "mu"), E.Interval(1.0, 1.2, "beta")), "X"),
+         E.Interval(0.0, 0.1, "Y"), E.RandomVariable(E.Normal(0.0, 0.3), "Z")]
+    (lbg, ubg), _, _ = uq.random_slicing(models, perf, [g], sim)[0]
+    assert 0.0 <= lbg <= ubg <= 1.0
+    t = [E.ProbabilityBox(E.Normal, (E.Interval(0.8, 1.3, "mu"), E.Interval(0.5, 0.9, "sd")), "X", lb=0.0),
+         E.Interval(0.0, 0.1, "Y"), E.RandomVariable(E.Normal(0.0, 0.3), "Z")]
+    with pytest.raises(E.UnsupportedModel, match="untruncated"):
+        uq.random_slicing(models, perf, [t], sim)
 
 
 def test_evaluate_net_chain_and_error_messages(E):
