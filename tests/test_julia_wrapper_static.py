@@ -66,7 +66,11 @@ def test_constants_match_the_header():
     assert int(jl_ops.group(2)) == nops - 1 and len(names) == nops
     assert [n.replace("OP_", "") for n in names] == [n for n, _ in hdr_ops]
     assert [int(v) for _, v in hdr_ops] == list(range(nops))
-    assert re.search(r"#define EBN_JOB_FP32_SAMPLING 16u", HDR) and "UInt32(16)" in JL
+    flags = dict(re.findall(r"#define EBN_JOB_(\w+) (\d+)u", HDR))
+    jl_flags = re.search(r"const (JOB_\w+(?:, JOB_\w+)*) = UInt32\.\(\(([\d, ]+)\)\)", JL)
+    jl_names = [n.strip().replace("JOB_", "") for n in jl_flags.group(1).split(",")]
+    jl_vals = [v.strip() for v in jl_flags.group(2).split(",")]
+    assert dict(zip(jl_names, jl_vals)) == flags
 
 
 def test_every_symbol_the_wrapper_calls_is_declared_and_exported():
@@ -76,3 +80,41 @@ def test_every_symbol_the_wrapper_calls_is_declared_and_exported():
     for sym in called:
         assert re.search(r"\b%s\(" % sym, HDR), sym
         getattr(lib, sym)
+
+
+def test_every_job_field_and_every_marginal_kind_is_populated_by_some_wrapper_path():
+    """The wrapper builds ebn_job_t in ONE place (with_job): every pointer field must be fed from Julia data
+    (not hard-wired to C_NULL), and every EBN_IN_* kind must be produced by some `abi` method."""
+    ctor = re.search(r"job = Ref\(EbnJob\((.*?)\)\)\n", JL, re.S).group(1)
+    assert JL.count("Ref(EbnJob(") == 1
+    for needle in ("pointer(consts)", "pointer(inputs)", "pointer(chol)", "pointer(stream)", "pointer(tables)",
+                   "length(tables)", "sim.n", "sim.seed", "sim.strict", "job_flags(sim)", "jd.S", "jd.d"):
+        assert needle in ctor, needle
+    # 17 fields in the header, 17 arguments in the constructor call (commas at depth 0)
+    depth, args = 0, 1
+    for ch in ctor:
+        depth += ch in "([" 
+        depth -= ch in ")]"
+        args += ch == "," and depth == 0
+    assert args == len(_c_struct("ebn_job")) == 17
+    for kind in ("IN_PARAM", "IN_NORMAL", "IN_LOGNORMAL", "IN_UNIFORM", "IN_GUMBEL", "IN_GAMMA", "IN_EXP_AFFINE", "IN_TABULATED"):
+        assert re.search(r"EbnInput\(%s," % kind, JL), kind
+    # the imprecise simulations and the copula reach the job: stream ids, Cholesky factors, table pool
+    for needle in ("struct CudaDoubleLoop", "struct CudaRandomSlicing", "stream=stream", "cholesky(Symmetric(R))",
+                   "tabulated(d, lo, hi, pool)", "ImpreciseDiscreteProbability", "JointDistribution"):
+        assert needle in JL, needle
+
+
+def test_wrapper_is_syntactically_balanced():
+    """No Julia here: at least every block opener has its `end` and brackets balance (comments and strings stripped)."""
+    src = re.sub(r'"""(.*?)"""', '""', JL, flags=re.S)
+    src = re.sub(r'"(?:\\.|[^"\\])*"', '""', src)
+    src = re.sub(r"#.*", "", src)
+    for o, c in ("()", "[]", "{}"):
+        assert src.count(o) == src.count(c), (o, src.count(o), src.count(c))
+    lines = [ln.strip() for ln in src.splitlines()]
+    openers = sum(bool(re.match(r"(?:function|struct|mutable struct|if|for|while|let|module|try|quote)\b", ln)) for ln in lines)
+    openers += sum(bool(re.search(r"\bbegin$", ln)) for ln in lines)              # `x = begin`, `GC.@preserve a b begin`
+    openers += sum(bool(re.search(r"\bdo(\s+\w+)?$", ln)) for ln in lines)         # `f(args) do job`
+    ends = sum(ln == "end" or ln.startswith("end ") for ln in lines)
+    assert openers == ends, (openers, ends)
