@@ -23,7 +23,7 @@ from .distributions import (Normal, LogNormal, Uniform, Gumbel, Gamma, Exponenti
 from .nodes import (DiscreteConditionalProbabilityTable, ContinuousConditionalProbabilityTable,  # noqa: F401
                     ExactDiscretization, ApproximatedDiscretization, UnamedProbabilityBox, DiscreteNode,
                     ContinuousNode, DiscreteFunctionalNode, ContinuousFunctionalNode, Model, Poly, Catalogue, Expression,
-                    CudaMonteCarlo, MonteCarlo, CudaDoubleLoop, DoubleLoop, CudaRandomSlicing, RandomSlicing, FORM)
+                    CudaMonteCarlo, MonteCarlo, CudaSobolSampling, SobolSampling, CudaDoubleLoop, DoubleLoop, CudaRandomSlicing, RandomSlicing, FORM)
 from .network import (EnhancedBayesianNetwork, BayesianNetwork, CredalNetwork, add_child, order, parents,  # noqa: F401
                       children, discrete_ancestors, markov_blanket, markov_envelope)
 from .uq import probability_of_failure, UnsupportedModel  # noqa: F401

@@ -48,6 +48,7 @@ JOB_PARTIAL = 2
 JOB_JIT_PLAN = 4
 JOB_NO_JIT_PLAN = 8
 JOB_FP32_SAMPLING = 16
+JOB_QMC_SOBOL = 32
 
 ERROR_NAMES = {0: "EBN_OK", -1: "EBN_EINVAL", -2: "EBN_ELIMITSTATE", -3: "EBN_EMARGINAL",
                -4: "EBN_ECUDA", -5: "EBN_ENCCL", -6: "EBN_ENODEV", -7: "EBN_ENOMEM", -8: "EBN_ESTATE",
@@ -242,6 +243,7 @@ class Job:
     partial: bool = False          # EBN_JOB_PARTIAL: this shard's counts only
     jit_plan: Optional[bool] = None  # True: EBN_JOB_JIT_PLAN, False: EBN_JOB_NO_JIT_PLAN, None: library decides
     fp32_sampling: bool = False    # EBN_JOB_FP32_SAMPLING: untruncated normals through the fp32 Box-Muller
+    qmc: bool = False              # EBN_JOB_QMC_SOBOL: Owen-scrambled Sobol points instead of the Philox streams
 
     def __post_init__(self):
         self.consts = np.ascontiguousarray(self.consts, dtype=np.float64).ravel()
@@ -280,6 +282,8 @@ class Job:
             j.flags |= JOB_JIT_PLAN if self.jit_plan else JOB_NO_JIT_PLAN
         if self.fp32_sampling:
             j.flags |= JOB_FP32_SAMPLING
+        if self.qmc:
+            j.flags |= JOB_QMC_SOBOL
         if self.corr_chol is not None:
             j.corr_chol = self.corr_chol.ctypes.data
             if self.corr_chol.ndim == 2:

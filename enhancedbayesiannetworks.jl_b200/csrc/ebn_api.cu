@@ -430,7 +430,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
   if (!job->inputs) return fail(EBN_EINVAL, "inputs is NULL");
   if (job->n_per_scenario < 1) return fail(EBN_EINVAL, "n_per_scenario must be >= 1");
   if (job->sample_offset < 0) return fail(EBN_EINVAL, "sample_offset must be >= 0");
-  if (job->flags & ~(EBN_JOB_COPULA_SHARED | EBN_JOB_PARTIAL | EBN_JOB_JIT_PLAN | EBN_JOB_NO_JIT_PLAN | EBN_JOB_FP32_SAMPLING)) return fail(EBN_EINVAL, "unknown job flags 0x%x", job->flags);
+  if (job->flags & ~(EBN_JOB_COPULA_SHARED | EBN_JOB_PARTIAL | EBN_JOB_JIT_PLAN | EBN_JOB_NO_JIT_PLAN | EBN_JOB_FP32_SAMPLING | EBN_JOB_QMC_SOBOL)) return fail(EBN_EINVAL, "unknown job flags 0x%x", job->flags);
   int rc = check_limit_state(job->limit_state, job->consts, job->n_consts, job->n_inputs);
   if (rc) return rc;
   const int jw = job->shard_world <= 1 ? 1 : job->shard_world;
@@ -439,12 +439,21 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
   if (job->n_tables < 0 || (job->n_tables > 0 && !job->tables)) return fail(EBN_EINVAL, "tables is NULL");
   const int S = job->n_scenarios, d = job->n_inputs;
   const bool copula = job->corr_chol != nullptr;
+  const bool qmc = (job->flags & EBN_JOB_QMC_SOBOL) != 0;
+  if (qmc) {
+    if (copula) return fail(EBN_EINVAL, "EBN_JOB_QMC_SOBOL: a Gaussian copula is not supported with the Sobol sequence");
+    if ((double)job->sample_offset + (double)job->n_per_scenario > 4294967296.0)
+      return fail(EBN_EINVAL, "EBN_JOB_QMC_SOBOL: the sequence holds 2^32 points per scenario");
+  }
   P.plan.resize((size_t)S * d);
   for (int s = 0; s < S; ++s)
     for (int j = 0; j < d; ++j) {
       rc = canonicalise(job->inputs[(size_t)s * d + j], copula, (job->flags & EBN_JOB_FP32_SAMPLING) != 0,
                         P.plan[(size_t)s * d + j], s, j, job->n_tables);
       if (rc) return rc;
+      if (qmc && P.plan[(size_t)s * d + j].kind == DK_GAMMA_MT)
+        return fail(EBN_EMARGINAL, "input (%d,%d): Gamma has no closed-form quantile on the device; under "
+                    "EBN_JOB_QMC_SOBOL pass it as an inverse-CDF table (EBN_IN_TABULATED)", s, j);
     }
   // word offsets in the pair's Philox stream (layout v3): inputs consume words in order;
   // under a copula every random input takes the 2 words of its Box-Muller pair
@@ -472,6 +481,8 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
       }
     }
     P.plan_class = PLAN_COPULA;
+  } else if (qmc) {
+    P.plan_class = PLAN_QMC;
   } else {
     const int which = static_plan_matches(job->limit_state, P.plan.data(), S, d);
     if (which >= 0) P.plan_class = PLAN_STATIC0 + which;
@@ -488,7 +499,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
     const bool forced = (job->flags & EBN_JOB_JIT_PLAN) != 0;
     if (never && forced) return fail(EBN_EINVAL, "EBN_JOB_JIT_PLAN and EBN_JOB_NO_JIT_PLAN are exclusive");
     bool plan_jit = false;
-    if (!expr && (P.plan_class == PLAN_DYNAMIC || P.plan_class == PLAN_COPULA) && uniform && !never) {
+    if (!expr && !qmc && (P.plan_class == PLAN_DYNAMIC || P.plan_class == PLAN_COPULA) && uniform && !never) {
       const char* env = getenv("EBN_JIT_PLAN");  // "0": never, "1": always (experiments)
       const bool big = (double)job->n_per_scenario * S >= kJitPlanMinSamples;
       if (forced || (env && env[0] == '1')) {
@@ -505,9 +516,10 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
       P.jit_spec.d = d;
       P.jit_spec.strict = job->strict != 0;
       P.jit_spec.copula = copula;
+      P.jit_spec.qmc = qmc;
       P.jit_spec.consts = job->consts;
       P.jit_spec.n_consts = job->n_consts;
-      if (uniform && !(expr && never))
+      if (uniform && !(expr && never) && !qmc)
         for (int j = 0; j < d; ++j) P.jit_spec.kinds.push_back(P.plan[j].kind);
       if (!P.jit_spec.kinds.empty() && !copula) P.plan_class = PLAN_STATIC0;
     }
@@ -814,7 +826,7 @@ int run_batch(const ebn_job_t* job_in, int mode, const double* edges, int nedges
   g.stats.samples = my_samples;
   g.stats.launches = (int)nd * (mode == 1 ? 2 : 1);
   g.stats.devices = (int)nd;
-  g.stats.specialised = P.plan_class >= PLAN_STATIC0 || !P.jit_spec.kinds.empty();
+  g.stats.specialised = (P.plan_class >= PLAN_STATIC0 && P.plan_class != PLAN_QMC) || !P.jit_spec.kinds.empty();
   g.stats.jit_compiles = P.jit_compiles;
   if (getenv("EBN_TRACE")) {  // one line per call on stderr: which kernel path ran, how long
     const LsInfo* li = ls_info(job->limit_state);

@@ -180,7 +180,8 @@ bool make_unit(const JitSpec& spec, JitRole role, Unit* u, std::string* err) {
   }
   const std::string functor = fmt("ebn::%s<ebn::%s>", ls, spec.strict ? "StrictOps" : "FastOps");
   std::string plan;
-  if (spec.kinds.empty()) plan = spec.copula ? "ebn::CopulaPlan" : "ebn::DynamicPlan";
+  if (spec.qmc) plan = "ebn::QmcPlan";
+  else if (spec.kinds.empty()) plan = spec.copula ? "ebn::CopulaPlan" : "ebn::DynamicPlan";
   else {
     plan = spec.copula ? "ebn::StaticCopulaPlan<" : "ebn::StaticPlan<";
     for (size_t j = 0; j < spec.kinds.size(); ++j) plan += fmt(j ? ",%d" : "%d", spec.kinds[j]);

@@ -20,6 +20,7 @@ struct JitSpec {
   int d = 0;
   bool strict = false;
   bool copula = false;
+  bool qmc = false;                // EBN_JOB_QMC_SOBOL: QmcPlan
   std::vector<int> kinds;          // d DevKinds -> StaticPlan<kinds...>; empty -> DynamicPlan / CopulaPlan
   const double* consts = nullptr;  // expression program (EBN_LS_EXPRESSION only)
   int n_consts = 0;

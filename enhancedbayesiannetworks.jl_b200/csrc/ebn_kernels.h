@@ -8,7 +8,7 @@ namespace ebn {
 
 // PLAN_STATIC0 + i: the i-th compile-time plan of the limit state (or, for a run-time compiled kernel,
 // the job's own kinds)
-enum PlanClass { PLAN_DYNAMIC = 0, PLAN_COPULA = 1, PLAN_STATIC0 = 2 };
+enum PlanClass { PLAN_DYNAMIC = 0, PLAN_COPULA = 1, PLAN_STATIC0 = 2, PLAN_QMC = 100 };  // PLAN_STATIC0 + i, i < kMaxStaticPlans
 constexpr int kMaxStaticPlans = 8;
 
 #ifndef __CUDACC_RTC__

@@ -48,6 +48,18 @@ struct CopulaPlan {
   static constexpr bool is_copula = true;
   static constexpr bool is_static_copula = false;
 };
+// Quasi-Monte Carlo: scrambled Sobol points instead of the Philox words, every marginal by inverse CDF
+// (ebn_qmc.cuh). Kinds are dispatched at run time.
+struct QmcPlan {
+  static constexpr bool is_static = false;
+  static constexpr bool is_copula = false;
+  static constexpr bool is_static_copula = false;
+  static constexpr bool is_qmc = true;
+};
+template <class Plan, class = void>
+struct plan_is_qmc { static constexpr bool value = false; };
+template <class Plan>
+struct plan_is_qmc<Plan, decltype((void)Plan::is_qmc)> { static constexpr bool value = Plan::is_qmc; };
 // Gaussian copula with the marginal kinds known at compile time (instantiated at run time only,
 // ebn_jit.cu): the eps draws, the triangular product z = L eps and the marginal transforms are
 // unrolled over registers instead of looping over local-memory arrays.
@@ -68,7 +80,9 @@ __host__ __device__ constexpr bool plan_uses_icdf() {
       if (Plan::kinds[i] == DK_NORMAL_ICDF || Plan::kinds[i] == DK_LOGNORMAL_ICDF) return true;
     return false;
   } else {
-    return false;   // kinds known at run time only: the cells are read from global memory (see icdf<>)
+    // kinds known at run time only: the cells are read from global memory (see icdf<>), except under
+    // quasi-Monte Carlo, where every normal goes through Phi^-1
+    return plan_is_qmc<Plan>::value;
   }
 }
 
@@ -191,6 +205,32 @@ __device__ __forceinline__ void draw_inputs(const DevInput* sp, const double* sL
       if (j < d) draw_pair_dyn(sp[j], pc, cache, cached_call, (uint32_t)j, tables, sm, x0[j], x1[j]);
     }
   }
+}
+
+// Quasi-Monte Carlo draw of one pair: `st` stands at the pair's even sample; Parameters take no dimension.
+template <int XCAP>
+__device__ __forceinline__ void draw_inputs_qmc(const DevInput* sp, int d, const QmcState& st, const double* tables,
+                                                const FastMathSmem& sm, double* x0, double* x1) {
+  const uint32_t* V = sobol_smem();
+  int r = 0;
+#pragma unroll
+  for (int j = 0; j < XCAP; ++j) {
+    if (j < d) {
+      if (sp[j].kind == DK_CONST) {
+        x0[j] = sp[j].a;
+        x1[j] = sp[j].a;
+      } else {
+        draw_pair_qmc(sp[j], st.v[r], V[r * 32], st.key[r], tables, sm, x0[j], x1[j]);
+        ++r;
+      }
+    }
+  }
+}
+// number of random (non-Parameter) inputs of a scenario = Sobol dimensions it uses
+__device__ __forceinline__ int qmc_dims(const DevInput* sp, int d) {
+  int nd = 0;
+  for (int j = 0; j < d; ++j) nd += sp[j].kind != DK_CONST;
+  return nd;
 }
 
 // All Philox calls of one pair for a static plan.
@@ -354,6 +394,7 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
   const int tid = threadIdx.x;
   fastmath_init(s_fm, tid, kThreads);
   if constexpr (plan_uses_icdf<Plan>()) icdf_init(tid, kThreads);
+  if constexpr (plan_is_qmc<Plan>::value) sobol_init(tid, kThreads);
   if (MODE == 1) {
     for (int i = tid; i < p.nedges; i += kThreads) s_edges[i] = p.edges[i];
   }
@@ -398,12 +439,24 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
       const bool interior = (q_begin << 1) >= p.first && (q_end << 1) <= p.last;
       cnt = interior ? static_count_loop<LS, Plan, false>(ctx, r_plan, pc, q_begin, q_end, tid, p, s_fm)
                      : static_count_loop<LS, Plan, true>(ctx, r_plan, pc, q_begin, q_end, tid, p, s_fm);
-    } else
+    } else {
+    QmcState qs;
+    int qmc_nd = 0;
+    if constexpr (plan_is_qmc<Plan>::value) {
+      qmc_nd = qmc_dims(s_plan, p.d);
+      qmc_keys(qs, pc.stream, pc.k0, pc.k1, qmc_nd);
+      qmc_seek(qs, (uint32_t)((q_begin + tid) << 1), qmc_nd);
+    }
     for (int64_t q = q_begin + tid; q < q_end; q += kThreads) {
       pc.qlo = (uint32_t)q;
       pc.qhi = (uint32_t)((uint64_t)q >> 32);
       double x0[XCAP], x1[XCAP];
-      draw_inputs<Plan, XCAP>(plan_ptr, s_chol, p.d, pc, p.tables, s_fm, x0, x1);
+      if constexpr (plan_is_qmc<Plan>::value) {
+        qmc_move(qs, (uint32_t)(q << 1), qmc_nd);
+        draw_inputs_qmc<XCAP>(s_plan, p.d, qs, p.tables, s_fm, x0, x1);
+      } else {
+        draw_inputs<Plan, XCAP>(plan_ptr, s_chol, p.d, pc, p.tables, s_fm, x0, x1);
+      }
       const int64_t i0 = q << 1;
       const bool v0 = i0 >= p.first;           // i0 < last holds by construction
       const bool v1 = (i0 + 1) < p.last;       // i0+1 >= first holds by construction
@@ -427,6 +480,7 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
           if (g1 == g1) { sum += g1; sumsq = fma(g1, g1, sumsq); }
         }
       }
+    }
     }
 
     if (MODE == 0) {
@@ -484,6 +538,7 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
   LS::setup(ctx, p.consts, p.n_consts, p.d, &s_fm);
   fastmath_init(s_fm, threadIdx.x, kThreads);
   if constexpr (plan_uses_icdf<Plan>()) icdf_init(threadIdx.x, kThreads);
+  if constexpr (plan_is_qmc<Plan>::value) sobol_init(threadIdx.x, kThreads);
   if (threadIdx.x < p.d) s_plan[threadIdx.x] = p.plan[(int64_t)scenario * p.d + threadIdx.x];
   if (Plan::is_copula) {
     const double* L = p.chol + (p.chol_shared ? 0 : (int64_t)scenario * p.d * p.d);
@@ -500,7 +555,15 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
     pc.qlo = (uint32_t)q;
     pc.qhi = (uint32_t)((uint64_t)q >> 32);
     double x0[XCAP], x1[XCAP];
-    draw_inputs<Plan, XCAP>(s_plan, s_chol, p.d, pc, p.tables, s_fm, x0, x1);
+    if constexpr (plan_is_qmc<Plan>::value) {
+      QmcState qs;
+      const int nd = qmc_dims(s_plan, p.d);
+      qmc_keys(qs, pc.stream, pc.k0, pc.k1, nd);
+      qmc_seek(qs, (uint32_t)(q << 1), nd);
+      draw_inputs_qmc<XCAP>(s_plan, p.d, qs, p.tables, s_fm, x0, x1);
+    } else {
+      draw_inputs<Plan, XCAP>(s_plan, s_chol, p.d, pc, p.tables, s_fm, x0, x1);
+    }
     const int64_t i0 = q << 1;
     double y0[XCAP], y1[XCAP];
 #pragma unroll
@@ -604,6 +667,7 @@ struct LsLaunch {
   template <class F>
   static cudaError_t with_plan(int plan_class, F&& f) {
     if (plan_class == PLAN_COPULA) return f.template operator()<CopulaPlan>();
+    if (plan_class == PLAN_QMC) return f.template operator()<QmcPlan>();
     if constexpr (sizeof...(SPlans) > 0) {
       if (plan_class >= PLAN_STATIC0) return pick_static<F, SPlans...>(plan_class - PLAN_STATIC0, static_cast<F&&>(f));
     }

@@ -21,6 +21,7 @@
 #include "ebn_device.cuh"
 #include "ebn_fastmath.cuh"
 #include "ebn_rng.cuh"
+#include "ebn_qmc.cuh"
 
 namespace ebn {
 
@@ -266,6 +267,39 @@ static __device__ __noinline__ void draw_pair_dyn(const DevInput& in, const Pair
     case DK_NORMAL_BM32: draw_pair<DK_NORMAL_BM32>(in, ws, pc, j, tables, sm, x0, x1); break;
     case DK_LOGNORMAL_BM32: draw_pair<DK_LOGNORMAL_BM32>(in, ws, pc, j, tables, sm, x0, x1); break;
     default: draw_pair<DK_TABLE>(in, ws, pc, j, tables, sm, x0, x1); break;
+  }
+}
+
+// One input of a sample pair under quasi-Monte Carlo (ebn_qmc.cuh): Sobol coordinate v of the even sample
+// (the odd one differs by the first direction number of the dimension) -> Owen-scrambled uniform -> the
+// marginal's inverse CDF on its truncation window. Untruncated normals take Phi^-1 like the truncated
+// ones: a Box-Muller pair would tie two samples to one radius and spend two dimensions per normal.
+static __device__ __noinline__ void draw_pair_qmc(const DevInput& in, uint32_t v, uint32_t odd_xor, uint32_t key,
+                                                  const double* tables, const FastMathSmem& sm,
+                                                  double& x0, double& x1) {
+  const double u0 = qmc_unit(owen_scramble(v, key));
+  const double u1 = qmc_unit(owen_scramble(v ^ odd_xor, key));
+  switch (in.kind) {
+    case DK_UNIFORM:
+      x0 = fma(u0, in.b, in.a);
+      x1 = fma(u1, in.b, in.a);
+      break;
+    case DK_NORMAL_BM: case DK_LOGNORMAL_BM: case DK_NORMAL_BM32: case DK_LOGNORMAL_BM32: {
+      double z0, z1;                         // no window: c = 0, d = 1
+      normcdfinv_fast2<true>(u0, u1, z0, z1);
+      x0 = fma(z0, in.b, in.a);
+      x1 = fma(z1, in.b, in.a);
+      if (in.kind == DK_LOGNORMAL_BM || in.kind == DK_LOGNORMAL_BM32) {
+        x0 = exp_fast(x0, sm);
+        x1 = exp_fast(x1, sm);
+      }
+      break;
+    }
+    case DK_NORMAL_ICDF: x0 = icdf<DK_NORMAL_ICDF, true>(in, tables, sm, u0); x1 = icdf<DK_NORMAL_ICDF, true>(in, tables, sm, u1); break;
+    case DK_LOGNORMAL_ICDF: x0 = icdf<DK_LOGNORMAL_ICDF, true>(in, tables, sm, u0); x1 = icdf<DK_LOGNORMAL_ICDF, true>(in, tables, sm, u1); break;
+    case DK_GUMBEL: x0 = icdf<DK_GUMBEL, true>(in, tables, sm, u0); x1 = icdf<DK_GUMBEL, true>(in, tables, sm, u1); break;
+    case DK_EXP_AFFINE: x0 = icdf<DK_EXP_AFFINE, true>(in, tables, sm, u0); x1 = icdf<DK_EXP_AFFINE, true>(in, tables, sm, u1); break;
+    default: x0 = icdf<DK_TABLE, true>(in, tables, sm, u0); x1 = icdf<DK_TABLE, true>(in, tables, sm, u1); break;   // DK_TABLE
   }
 }
 

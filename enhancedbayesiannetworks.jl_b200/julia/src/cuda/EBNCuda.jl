@@ -24,7 +24,7 @@ using Distributions
 using DataFrames
 using LinearAlgebra
 
-export CudaMonteCarlo, CudaDoubleLoop, CudaRandomSlicing, CudaModel, CudaExprModel, ebn_init, ebn_shutdown
+export CudaMonteCarlo, CudaSobolSampling, CudaDoubleLoop, CudaRandomSlicing, CudaModel, CudaExprModel, ebn_init, ebn_shutdown
 
 const LIB = Ref{String}(get(ENV, "EBNCUDA_LIB", "libebncuda.so"))
 
@@ -36,7 +36,7 @@ const OP_INPUT, OP_PARAM, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_A
     OP_SIN, OP_COS, OP_MIN, OP_MAX, OP_POW, OP_POWI, OP_LT, OP_SELECT, OP_STORE = 0:20
 const IN_PARAM, IN_NORMAL, IN_LOGNORMAL, IN_UNIFORM, IN_GUMBEL, IN_GAMMA, IN_EXP_AFFINE, IN_TABULATED = 0:7
 # EBN_JOB_* flags
-const JOB_COPULA_SHARED, JOB_PARTIAL, JOB_JIT_PLAN, JOB_NO_JIT_PLAN, JOB_FP32_SAMPLING = UInt32.((1, 2, 4, 8, 16))
+const JOB_COPULA_SHARED, JOB_PARTIAL, JOB_JIT_PLAN, JOB_NO_JIT_PLAN, JOB_FP32_SAMPLING, JOB_QMC_SOBOL = UInt32.((1, 2, 4, 8, 16, 32))
 const TABLE_POINTS = 4097      # points of an inverse-CDF table (uniform grid in u)
 
 # typedef struct ebn_input { int32 kind; int32 flags; double p[4]; double lo; double hi; }  (56 bytes)
@@ -102,6 +102,8 @@ hoists reciprocals (|Δg| ~ 1e-13, count differences only on ties). For a chain 
 `performance` is the node's performance function as a quoted expression (`:(2 .- df.C)`); the
 node's own `performance::Function` cannot be translated. Default: the last model's column.
 `fp32_sampling=true` sets EBN_JOB_FP32_SAMPLING (untruncated normals drawn in fp32, limit state in fp64).
+`qmc=true` (or the constructor `CudaSobolSampling`) sets EBN_JOB_QMC_SOBOL: UQ.jl's `SobolSampling` on the
+device — sample i is point i of an Owen-scrambled Sobol sequence, every marginal through its inverse CDF.
 """
 struct CudaMonteCarlo <: UncertaintyQuantification.AbstractMonteCarlo
     n::Int
@@ -109,10 +111,14 @@ struct CudaMonteCarlo <: UncertaintyQuantification.AbstractMonteCarlo
     strict::Bool
     performance::Any
     fp32_sampling::Bool
+    qmc::Bool
 end
-CudaMonteCarlo(n::Integer; seed::Integer=0x5EED0001, strict::Bool=false, performance=nothing, fp32_sampling::Bool=false) =
-    CudaMonteCarlo(n, UInt64(seed), strict, performance, fp32_sampling)
-job_flags(sim::CudaMonteCarlo) = sim.fp32_sampling ? JOB_FP32_SAMPLING : UInt32(0)
+CudaMonteCarlo(n::Integer; seed::Integer=0x5EED0001, strict::Bool=false, performance=nothing,
+    fp32_sampling::Bool=false, qmc::Bool=false) =
+    CudaMonteCarlo(n, UInt64(seed), strict, performance, fp32_sampling, qmc)
+"Quasi-Monte Carlo counterpart of UQ.jl's `SobolSampling(n)`; a power of two for `n` keeps the point set a net."
+CudaSobolSampling(n::Integer; kwargs...) = CudaMonteCarlo(n; qmc=true, kwargs...)
+job_flags(sim::CudaMonteCarlo) = (sim.fp32_sampling ? JOB_FP32_SAMPLING : UInt32(0)) | (sim.qmc ? JOB_QMC_SOBOL : UInt32(0))
 
 """
     CudaDoubleLoop(lb::CudaMonteCarlo, ub = lb; method = :optimise, grid = 33)
@@ -360,7 +366,7 @@ struct JobData
 end
 
 function build_job(scenario_inputs::Vector{<:Vector}, columns::Vector{Symbol}, hidden::Int;
-    stream::Vector{UInt32}=UInt32[])
+    stream::Vector{UInt32}=UInt32[], qmc::Bool=false)
     S = length(scenario_inputs)
     d = length(columns) + hidden
     M = Vector{EbnInput}(undef, S * d)
@@ -373,8 +379,8 @@ function build_job(scenario_inputs::Vector{<:Vector}, columns::Vector{Symbol}, h
         for (j, c) in enumerate(columns)
             haskey(byname, c) || error("limit state needs input $c which the node's parents do not provide")
             inp = byname[c]
-            # no closed-form quantile on the device: Gamma under a copula is shipped tabulated
-            M[(s-1)*d+j] = (any_copula && inp isa RandomVariable && inp.dist isa Gamma) ?
+            # no closed-form quantile on the device: Gamma under a copula or a Sobol sequence is shipped tabulated
+            M[(s-1)*d+j] = ((any_copula || qmc) && inp isa RandomVariable && inp.dist isa Gamma) ?
                            tabulated(inp.dist, -Inf, Inf, pool; npts=8193) : abi(inp, pool)
         end
         for j in 1:hidden
@@ -461,7 +467,7 @@ end
 function pf_batch(models::Vector, performance, scenario_inputs::Vector{<:Vector}, sim::CudaMonteCarlo;
     stream::Vector{UInt32}=UInt32[])
     low = lower(models, performance, input_names(scenario_inputs[1]))
-    return run_pf(low.limit_state, low.consts, build_job(scenario_inputs, low.columns, low.hidden; stream=stream), sim)
+    return run_pf(low.limit_state, low.consts, build_job(scenario_inputs, low.columns, low.hidden; stream=stream, qmc=sim.qmc), sim)
 end
 
 # UQ.jl-style single-scenario entry (demo/vehicle_suspension.jl:68)
@@ -766,8 +772,8 @@ function EnhancedBayesianNetworks._evaluate_node(net::EnhancedBayesianNetwork,
     # "performance" is that column
     low = lower(collect(node.models), node.models[end] isa CudaExprModel ? node.models[end].name : nothing,
         input_names(scen[1]))
-    jd = build_job(scen, low.columns, low.hidden)
-    pilot = CudaMonteCarlo(min(sim.n, 1 << 16), sim.seed, sim.strict, nothing, sim.fp32_sampling)
+    jd = build_job(scen, low.columns, low.hidden; qmc=sim.qmc)
+    pilot = CudaMonteCarlo(min(sim.n, 1 << 16), sim.seed, sim.strict, nothing, sim.fp32_sampling, sim.qmc)
     _, s1, s2 = run_hist(low.limit_state, low.consts, jd, pilot, [0.0])        # moments only
     μ = s1 ./ pilot.n
     σ = sqrt.(max.(s2 ./ pilot.n .- μ .^ 2, 0.0))

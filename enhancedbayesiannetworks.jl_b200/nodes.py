@@ -440,9 +440,22 @@ class CudaMonteCarlo:
     seed: int = 0x5EED0001
     strict: bool = False
     fp32_sampling: bool = False   # EBN_JOB_FP32_SAMPLING: untruncated normals through the fp32 Box-Muller
+    qmc: bool = False             # EBN_JOB_QMC_SOBOL (set by CudaSobolSampling)
 
 
-MonteCarlo = CudaMonteCarlo  # the only AbstractMonteCarlo this package implements
+MonteCarlo = CudaMonteCarlo
+
+
+@dataclass(frozen=True)
+class CudaSobolSampling(CudaMonteCarlo):
+    """UQ.jl `SobolSampling(n)`, a quasi-Monte Carlo `AbstractMonteCarlo` (accepted by
+    `ContinuousFunctionalNode.simulation::AbstractMonteCarlo`, src/nodes/functionalnodes.jl:4): sample i of a
+    scenario is point i of an Owen-scrambled Sobol sequence, every marginal through its inverse CDF.
+    A power of two for `n` keeps the point set a net."""
+    qmc: bool = True
+
+
+SobolSampling = CudaSobolSampling
 
 
 @dataclass(frozen=True)

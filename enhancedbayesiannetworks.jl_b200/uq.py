@@ -245,8 +245,8 @@ def build_job(low: Lowered, scenario_inputs: Sequence[Sequence], sim: CudaMonteC
         row = []
         for c in low.columns:
             inp = by_name[c]
-            if copulas and isinstance(inp, RandomVariable) and isinstance(inp.dist, Gamma):
-                # no closed-form quantile on the device: Gamma under a copula is shipped tabulated
+            if (copulas or getattr(sim, "qmc", False)) and isinstance(inp, RandomVariable) and isinstance(inp.dist, Gamma):
+                # no closed-form quantile on the device: Gamma under a copula or a Sobol sequence is shipped tabulated
                 off, n = pool.add(table_for(inp.dist, -INF, INF, 8193))
                 row.append((L.IN_TABULATED, float(off), float(n), 0.0, 0.0, -INF, INF))
             else:
@@ -264,7 +264,7 @@ def build_job(low: Lowered, scenario_inputs: Sequence[Sequence], sim: CudaMonteC
             chols.append(np.eye(d))
     return L.Job(low.limit_state, low.consts, L.make_inputs(rows), int(sim.n), int(sim.seed), bool(sim.strict),
                  stream_id=stream_id, tables=pool.array(), corr_chol=np.stack(chols) if any_copula else None,
-                 fp32_sampling=bool(getattr(sim, "fp32_sampling", False)))
+                 fp32_sampling=bool(getattr(sim, "fp32_sampling", False)), qmc=bool(getattr(sim, "qmc", False)))
 
 
 class Samples:

@@ -182,6 +182,12 @@ typedef struct ebn_input {
                                     normal agrees with the fp64 draw to ~1e-6 sigma, tail to 6.7 sigma);
                                     the limit state stays in fp64. About 1.3x faster on the vehicle
                                     workload. Ignored under a copula.                               */
+#define EBN_JOB_QMC_SOBOL 32u    /* quasi-Monte Carlo (UQ.jl SobolSampling, an AbstractMonteCarlo): sample i of a
+                                    scenario is point i of an Owen-scrambled Sobol sequence (Joe-Kuo direction
+                                    numbers, hash-based nested uniform scrambling keyed by seed and stream id),
+                                    every marginal through its inverse CDF. At most 2^32 points per scenario,
+                                    no Gaussian copula, Gamma as EBN_IN_TABULATED. pf = count/n as before;
+                                    `var` is still (pf - pf^2)/n, an upper bound in practice                */
 #define EBN_JOB_PARTIAL 2u       /* sharded job: return THIS shard's counts, no all-reduce
                                     (the caller combines shards; also used to emulate
                                     several ranks on one GPU in tests)                  */

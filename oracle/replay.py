@@ -287,6 +287,84 @@ def copula_sample_matrix(inputs_row, L, stream: int, seed: int, first: int, n: i
     return X
 
 
+# ---- quasi-Monte Carlo: the Sobol twin (csrc/ebn_qmc.cuh) --------------------------------------------
+def sobol_direction_numbers():
+    """Joe & Kuo direction numbers of the first 16 dimensions, recomputed from the primitive polynomials
+    (tools/gen_sobol_tables.py holds the table; tests check both against scipy.stats.qmc.Sobol)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "gen_sobol_tables.py")
+    spec = importlib.util.spec_from_file_location("gen_sobol_tables", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return np.array(mod.direction_numbers(), dtype=np.uint64)
+
+
+def sobol_points(first: int, n: int, nd: int, V=None):
+    """Unscrambled 32-bit Sobol coordinates of samples first..first+n-1 (gray-code order), shape (n, nd)."""
+    V = sobol_direction_numbers() if V is None else V
+    idx = np.arange(first, first + n, dtype=np.uint64)
+    g = idx ^ (idx >> np.uint64(1))
+    out = np.zeros((n, nd), dtype=np.uint64)
+    for k in range(32):
+        bit = ((g >> np.uint64(k)) & np.uint64(1)).astype(bool)
+        out[bit] ^= V[:nd, k]
+    return out
+
+
+def _brev32(x):
+    x = np.asarray(x, dtype=np.uint64)
+    r = np.zeros_like(x)
+    for k in range(32):
+        r |= ((x >> np.uint64(k)) & np.uint64(1)) << np.uint64(31 - k)
+    return r
+
+
+def owen_scramble(x, key: int):
+    """Hash-based nested uniform scrambling (Laine & Karras 2011 / Burley 2020), uint32 arithmetic."""
+    m = np.uint64(0xFFFFFFFF)
+    x = _brev32(x)
+    x = (x + np.uint64(key)) & m
+    for c in (0x6C50B47C, 0xB82F1E52, 0xC7AFE638, 0x8D22F6E6):
+        x = x ^ ((x * np.uint64(c)) & m)
+    return _brev32(x)
+
+
+def qmc_sample_matrix(inputs_row, stream: int, seed: int, first: int, n: int, tables=None, scramble: bool = True):
+    """EBN_JOB_QMC_SOBOL: sample i is point i of the scrambled Sobol sequence; random input number r (Parameters
+    take no dimension) uses dimension r, key = Philox(counter (r, 0, stream, 'SOBL'), seed).w0; every
+    marginal through its quantile on the truncation window (SciPy)."""
+    d = len(inputs_row)
+    random = [j for j in range(d) if int(inputs_row[j]["kind"]) != IN_PARAM]
+    P = sobol_points(first, n, len(random))
+    X = np.empty((n, d))
+    for j in range(d):
+        inp = inputs_row[j]
+        kind, p = int(inp["kind"]), inp["p"]
+        lo, hi = float(inp["lo"]), float(inp["hi"])
+        if kind == IN_PARAM:
+            X[:, j] = p[0]
+            continue
+        r = random.index(j)
+        w = P[:, r]
+        if scramble:
+            key = int(philox4x32_10(np.uint64(r), np.uint64(0), np.uint64(stream), np.uint64(0x534F424C),
+                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)[0])
+            w = owen_scramble(w, key)
+        u = (w.astype(np.float64) + 0.5) * 2.0**-32
+        if kind == IN_UNIFORM:
+            a, b = max(p[0], lo), min(p[1], hi)
+            X[:, j] = a + u * (b - a)
+        elif kind == IN_GAMMA:
+            raise ValueError("Gamma under quasi-Monte Carlo must be tabulated")
+        elif kind in (IN_NORMAL, IN_LOGNORMAL) and not (np.isfinite(lo) or np.isfinite(hi)):
+            v = p[0] + p[1] * special.ndtri(u)
+            X[:, j] = np.exp(v) if kind == IN_LOGNORMAL else v
+        else:
+            X[:, j] = _quantile(inp, u, tables)
+    return X
+
+
 # ---- limit states in NumPy, Julia evaluation order (second restatement) -----
 def _jl_min(a, b):
     return np.where(np.isnan(a), a, np.where(np.isnan(b), b, np.minimum(a, b)))

@@ -170,3 +170,22 @@ def test_structural_sampler_marginals():
             E = stats.expon(0, 2.0)
             p = (E.cdf(3.0) - E.cdf(1.0)) / E.cdf(3.0)
         assert abs(pf - p) < 4 * math.sqrt(p * (1 - p) / n), (j, pf, p)
+
+
+def test_sobol_direction_numbers_and_scrambling():
+    """The device's direction-number table (csrc/ebn_sobol_tables.inc) equals the Joe-Kuo construction and
+    scipy.stats.qmc.Sobol point for point; the hash-based Owen scrambling keeps every one-dimensional
+    projection of 2^m points stratified (one point per interval of length 2^-m)."""
+    import re
+    from scipy.stats import qmc
+    txt = open(os.path.join(os.path.dirname(GOLD), "..", "enhancedbayesiannetworks.jl_b200", "csrc", "ebn_sobol_tables.inc")).read()
+    rows = re.findall(r"\{([^{}]+)\}", txt[txt.index("kSobolV[16]"):])
+    V = np.array([[int(x.strip().rstrip("u"), 16) for x in r.split(",")] for r in rows], dtype=np.uint64)
+    assert V.shape == (16, 32) and np.array_equal(V, replay.sobol_direction_numbers())
+    P = replay.sobol_points(0, 2048, 16, V)
+    assert np.array_equal(P.astype(np.float64) * 2.0**-32, qmc.Sobol(d=16, scramble=False, bits=32).random(2048))
+    assert np.array_equal(replay.sobol_points(1000, 48, 16, V), P[1000:1048])
+    for dim, key in ((0, 1), (5, 0xDEADBEEF), (15, 12345)):
+        w = replay.owen_scramble(P[:, dim], key)
+        assert np.array_equal(np.bincount((w >> np.uint64(21)).astype(np.int64), minlength=2048), np.ones(2048, dtype=np.int64))
+        assert not np.array_equal(w, P[:, dim])
