@@ -884,20 +884,9 @@ int ebn_shutdown(void) {
   return EBN_OK;
 }
 
-int ebn_init(const int* devices, int ndev) {
-  if (g.ready) ebn_shutdown();
-  if (ndev < 0 || (ndev > 0 && !devices)) return fail(EBN_EINVAL, "bad device list");
-  const int avail = ebn_device_count();
-  if (avail < 1) return fail(EBN_ENODEV, "no CUDA device is visible; libebncuda has no CPU fallback");
-  std::vector<int> ids;
-  if (ndev == 0) ids.push_back(0);
-  for (int i = 0; i < ndev; ++i) {
-    if (devices[i] < 0 || devices[i] >= avail)
-      return fail(EBN_ENODEV, "device %d requested but only %d visible", devices[i], avail);
-    for (int k = 0; k < i; ++k)
-      if (devices[k] == devices[i]) return fail(EBN_EINVAL, "device %d listed twice", devices[i]);
-    ids.push_back(devices[i]);
-  }
+// Brings the devices up; on any failure the half-built state (streams, events, communicators) is torn
+// down again through ebn_shutdown, so a later ebn_init starts clean.
+static int init_devices(const std::vector<int>& ids) {
   g.devs.resize(ids.size());
   for (size_t k = 0; k < ids.size(); ++k) {
     Dev& dv = g.devs[k];
@@ -916,12 +905,35 @@ int ebn_init(const int* devices, int ndev) {
   }
   if (ids.size() > 1) {
     int rc = nccl_load();
-    if (rc) { g.devs.clear(); return rc; }
+    if (rc) return rc;
     std::vector<ncclComm_t> comms(ids.size());
     NC(g_nccl.CommInitAll(comms.data(), (int)ids.size(), ids.data()));
     for (size_t k = 0; k < ids.size(); ++k) g.devs[k].comm = comms[k];
   }
   CU(cudaSetDevice(g.devs[0].id));
+  return EBN_OK;
+}
+
+int ebn_init(const int* devices, int ndev) {
+  if (g.ready || !g.devs.empty()) ebn_shutdown();
+  if (ndev < 0 || (ndev > 0 && !devices)) return fail(EBN_EINVAL, "bad device list");
+  const int avail = ebn_device_count();
+  if (avail < 1) return fail(EBN_ENODEV, "no CUDA device is visible; libebncuda has no CPU fallback");
+  std::vector<int> ids;
+  if (ndev == 0) ids.push_back(0);
+  for (int i = 0; i < ndev; ++i) {
+    if (devices[i] < 0 || devices[i] >= avail)
+      return fail(EBN_ENODEV, "device %d requested but only %d visible", devices[i], avail);
+    for (int k = 0; k < i; ++k)
+      if (devices[k] == devices[i]) return fail(EBN_EINVAL, "device %d listed twice", devices[i]);
+    ids.push_back(devices[i]);
+  }
+  const int rc = init_devices(ids);
+  if (rc) {
+    const std::string why = ebn_last_error();   // ebn_shutdown must not hide the reason
+    ebn_shutdown();
+    return fail(rc, "%s", why.c_str());
+  }
   g.ready = true;
   return EBN_OK;
 }
@@ -1007,7 +1019,9 @@ int ebn_eval_matrix(int limit_state, const double* consts, int n_consts, const d
   if ((rc = dv.consts.ensure((size_t)n_consts * sizeof(double)))) return rc;
   if ((rc = dv.counts.ensure(sizeof(unsigned long long)))) return rc;
   if (g_out && (rc = dv.gout.ensure((size_t)n * sizeof(double)))) return rc;
-  CU(cudaMemcpyAsync(dv.mat.p, X, xb, cudaMemcpyHostToDevice, dv.st));
+  // a column-major matrix with ld > n only guarantees (d-1)*ld + n elements on the host side
+  const size_t xcopy = d > 0 ? ((size_t)(d - 1) * ld + (size_t)n) * sizeof(double) : 0;
+  if (xcopy) CU(cudaMemcpyAsync(dv.mat.p, X, xcopy, cudaMemcpyHostToDevice, dv.st));
   if (n_consts) CU(cudaMemcpyAsync(dv.consts.p, consts, (size_t)n_consts * sizeof(double), cudaMemcpyHostToDevice, dv.st));
   CU(cudaMemsetAsync(dv.counts.p, 0, sizeof(unsigned long long), dv.st));
   int64_t blocks = (n + threads_per_block() - 1) / threads_per_block();

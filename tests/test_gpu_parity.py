@@ -756,3 +756,25 @@ def test_golden_fixtures(ebn):
         X = ebn.sample_matrix(job, 3, first, 64)
         ref = s[f"first_{first}"]
         assert np.max(np.abs(X - ref) / np.maximum(np.abs(ref), 1.0)) < 5e-12
+
+
+def test_eval_matrix_with_a_leading_dimension_larger_than_n(ebn):
+    """A column-major matrix with ld > n owns (d-1)*ld + n elements, not ld*d: the library must not read past them."""
+    import ctypes as C
+    from ebn_b200 import workloads as W
+    L = ebn._lib
+    rng = np.random.default_rng(5)
+    n, d, ld = 1000, 6, 1024
+    X = _vehicle_matrix(rng, n)
+    flat = np.full((d - 1) * ld + n, np.nan)
+    for j in range(d):
+        flat[j * ld:j * ld + n] = X[:, j]
+    k = W.vehicle_consts()
+    cnt = C.c_int64(0)
+    g = np.empty(n)
+    dp = C.POINTER(C.c_double)
+    rc = L.load().ebn_eval_matrix(L.LS_VEHICLE_SUSPENSION, k.ctypes.data_as(dp), k.size, flat.ctypes.data_as(dp), n, d, ld, 1,
+                                  C.byref(cnt), g.ctypes.data_as(dp))
+    assert rc == 0
+    want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_VEHICLE, k, X, want_g=True)
+    assert cnt.value == want_cnt and np.array_equal(g, want_g)
