@@ -47,13 +47,13 @@ __constant__ FastMathConst kFm = {
 // not the constant cache, which serialises divergent addresses).
 struct FastMathSmem {
   double2 logtab[1 << EBN_LOG_TAB_BITS];
-  double2 sctab[1 << EBN_SC_TAB_BITS];   // sqrt(2)*(sin, cos) at the cell centres of the first quadrant
+  double2 sctab[4 << EBN_SC_TAB_BITS];   // sqrt(2)*(sin, cos) at the cell centres of the full circle
   double exptab[64];
 };
 
 __device__ __forceinline__ void fastmath_init(FastMathSmem& sm, int tid, int nthreads) {
   for (int i = tid; i < (1 << EBN_LOG_TAB_BITS); i += nthreads) sm.logtab[i] = kLogTab[i];
-  for (int i = tid; i < (1 << EBN_SC_TAB_BITS); i += nthreads) sm.sctab[i] = kSinCosTab[i];
+  for (int i = tid; i < (4 << EBN_SC_TAB_BITS); i += nthreads) sm.sctab[i] = kSinCosTab[i];
   for (int i = tid; i < 64; i += nthreads) sm.exptab[i] = kExpTab[i];
 }
 
@@ -67,7 +67,8 @@ __device__ __forceinline__ void fastmath_init(FastMathSmem& sm, int tid, int nth
 //  16  r = u * (rc 2^e) - 1 with the exponent added to the table entry's high word (one IMAD) instead of
 //      rebuilding the mantissa m = u 2^e as a new register pair (LOP3 + MOV); the same value bit for bit
 #ifndef EBN_BM_OPT
-#define EBN_BM_OPT 47   // measured best on B200 (profiles/r02_tune_w1.txt); 16 costs 1 %
+#define EBN_BM_OPT 39   // measured best on B200 with stream layout v4 (profiles/r02_tune_w1.txt): 8 (I2F on the XU pipe)
+                        // helped layout v3 by 1 % and costs 6 % now, 16 costs 3 %
 #endif
 
 // High word of the double in [1,2) whose top 20 mantissa bits are the low 20 bits of w:
@@ -270,13 +271,13 @@ __device__ __forceinline__ double sqrt_pos(double t) {
   return fma(a * e, c, a);
 }
 
-// Box-Muller for the sample pair from two 32-bit words (64 bits = 42 + 20 + 2):
+// Box-Muller for the sample pair from two 32-bit words (64 bits = 42 + 22):
 //   radius  u = (M + 1/2) 2^-42 in (0,1), M = 42 bits: all of w0 (low 20 bits most significant)
 //           followed by bits 0..9 of w1; reaches 7.6 sigma, P(lost tail) = 2^-43 per draw
-//   angle   first-quadrant angle (pi/2)(A + 1/2) 2^-20, A = bits 10..29 of w1
-//   signs   bits 31 and 30 of w1
-// z0 = s0*R*sin(phi), z1 = s1*R*cos(phi) with R = sqrt(-2 ln u), phi uniform in (0, pi/2):
-// a uniformly random direction, so (z0, z1) are independent standard normals.
+//   angle   Phi = (pi/2)(A + 1/2) 2^-20 in (0, 2 pi), A = bits 10..31 of w1 (22 bits: quadrant and 20-bit offset)
+// z0 = R*sin(Phi), z1 = R*cos(Phi) with R = sqrt(-2 ln u), Phi uniform on the circle: a uniformly random
+// direction, so (z0, z1) are independent standard normals. (Layout v3 took a first-quadrant angle and two
+// sign bits: the same distribution, three integer instructions more per pair.)
 //
 // Split in two so that the count loop can software-pipeline it: the FRONT end (integer bit
 // placement, the table load and the two fp64 operations that consume it) runs one pair ahead,
@@ -317,18 +318,18 @@ __device__ __forceinline__ double bm_neg_log(const BmFront& f) {
   return fma(r * r, p, f.base - r);
 }
 
-// sqrt(2)*(sin, cos) of the pair's first-quadrant angle.
-// Angle phi = (pi/2)(A + 1/2) 2^-20, A = bits 10..29 of w1: the top B = EBN_SC_TAB_BITS bits of A
-// pick one of 2^B cells whose centre carries sqrt(2)*(sin, cos) in shared memory; the low 20-B
-// bits give the offset inside the cell, delta = (pi/2) t with |t| <= 2^-(B+1), short enough for
-// two 2-3 term polynomials (10-11 fp64 operations instead of the 20 of a full-quadrant pair).
-// The offset bits stay where they are in the low mantissa word: d = 1 + r 2^-42,
-// t = (r + 1/2) 2^-20 - 2^-(B+1) = d 2^22 - (2^22 + 2^-(B+1) - 2^-21), exact.
+// sqrt(2)*(sin, cos) of the pair's angle.
+// Angle Phi = (pi/2)(A + 1/2) 2^-20 over the FULL circle, A = bits 10..31 of w1 (22 bits): the top B + 2 bits
+// (B = EBN_SC_TAB_BITS) pick one of 4*2^B cells whose centre carries sqrt(2)*(sin, cos) in shared memory —
+// a plain shift of w1, no mask, and no sign handling afterwards; the low 20-B bits give the offset inside the
+// cell, delta = (pi/2) t with |t| <= 2^-(B+1), short enough for two 2-3 term polynomials (10-11 fp64
+// operations instead of the 20 of a full-quadrant pair). The offset bits stay where they are in the low
+// mantissa word: d = 1 + r 2^-42, t = (r + 1/2) 2^-20 - 2^-(B+1) = d 2^22 - (2^22 + 2^-(B+1) - 2^-21), exact.
 __device__ __forceinline__ void bm_trig(uint32_t w1, const FastMathSmem& sm, double& cps, double& cms) {
   constexpr int B = EBN_SC_TAB_BITS;
   constexpr uint32_t kOffsetMask = ((1u << (20 - B)) - 1u) << 10;
   constexpr double kHalfCell = 1.0 / (double)(1 << (B + 1));
-  const double2 sc = sm.sctab[(w1 >> (30 - B)) & ((1u << B) - 1u)];
+  const double2 sc = sm.sctab[w1 >> (30 - B)];
   double td, sd, cm;
   if (EBN_BM_OPT & 32) {
     // the top coefficients are immediates (low word zero, tools/gen_fastmath_tables.py), every other
@@ -350,16 +351,12 @@ __device__ __forceinline__ void bm_trig(uint32_t w1, const FastMathSmem& sm, dou
   cms = fma(-sc.x, sd, fma(sc.y, cm, sc.y));   // sqrt(2) cos(phi)
 }
 
-__device__ __forceinline__ double flip_sign(double a, uint32_t sign_bit) {
-  return __hiloint2double(__double2hiint(a) ^ (int)(sign_bit & 0x80000000u), __double2loint(a));
-}
-
 __device__ __forceinline__ void box_muller_back(const BmFront& f, const FastMathSmem& sm, double& z0, double& z1) {
   double cps, cms;
   bm_trig(f.w1, sm, cps, cms);
   const double rr = sqrt_pos(bm_neg_log(f));           // sqrt(-ln u) = R / sqrt(2)
-  z0 = flip_sign(rr * cps, f.w1);        // s0 R sin(phi)
-  z1 = flip_sign(rr * cms, f.w1 << 1);   // s1 R cos(phi)
+  z0 = rr * cps;        // R sin(Phi)
+  z1 = rr * cms;        // R cos(Phi)
 }
 
 // x = mu + sigma z for both samples of the pair.
@@ -369,8 +366,8 @@ __device__ __forceinline__ void box_muller_back_affine(const BmFront& f, const F
     double cps, cms;
     bm_trig(f.w1, sm, cps, cms);
     const double rs = sqrt_pos(bm_neg_log(f)) * sigma;   // sigma R / sqrt(2)
-    x0 = fma(flip_sign(rs, f.w1), cps, mu);
-    x1 = fma(flip_sign(rs, f.w1 << 1), cms, mu);
+    x0 = fma(rs, cps, mu);
+    x1 = fma(rs, cms, mu);
   } else {
     double z0, z1;
     box_muller_back(f, sm, z0, z1);
@@ -387,11 +384,13 @@ __device__ __forceinline__ void box_muller_back_affine(const BmFront& f, const F
 __device__ __forceinline__ void box_muller_words_f32(uint32_t w0, uint32_t w1, double& z0, double& z1) {
   const float u = fmaf(__uint2float_rz(w0 << 12 | w0 >> 20), 0x1p-32f, 0x1p-33f);   // rotl(w0, 12): the bit order of the fp64 path
   const float r = __fsqrt_rn(-1.3862943611198906f * __log2f(u));                     // sqrt(-2 ln u)
-  const float v = __uint_as_float(0x3F800000u | ((w1 >> 7) & 0x007FFFF8u)) - (1.0f - 0x1p-21f);  // (A + 1/2) 2^-20
+  // fraction of the circle f = (A + 1/2) 2^-22, A = bits 10..31 of w1, exact in fp32; the hardware sine is
+  // most accurate on [-pi, pi]: evaluate at 2 pi (f - 1/2) = Phi - pi, where sin and cos are minus those of Phi
+  const float f = __uint_as_float(0x3F800000u | ((w1 >> 9) | 1u)) - 1.5f;
   float s, c;
-  __sincosf(1.5707963267948966f * v, &s, &c);
-  z0 = (double)__uint_as_float(__float_as_uint(r * s) ^ (w1 & 0x80000000u));
-  z1 = (double)__uint_as_float(__float_as_uint(r * c) ^ ((w1 << 1) & 0x80000000u));
+  __sincosf(6.283185307179586f * f, &s, &c);
+  z0 = (double)(-(r * s));
+  z1 = (double)(-(r * c));
 }
 
 __device__ __forceinline__ void box_muller_words(uint32_t w0, uint32_t w1, const FastMathSmem& sm,

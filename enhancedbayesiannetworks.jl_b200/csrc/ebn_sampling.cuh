@@ -3,18 +3,18 @@
 // (reference call sites src/networks/ebn/evaluation/evaluate_node.jl:24,83;
 // the marginals that reach it are listed in SURVEY.md F7 / rows 2 and 5).
 //
-// Random streams, layout v3: for scenario stream s and sample pair
+// Random streams, layout v4: for scenario stream s and sample pair
 // q = sample index >> 1 the word stream is
 //     W[4c .. 4c+3] = Philox4x32-10(counter = (q lo, q hi, s, c), key = seed)
 // and the inputs consume words in input order:
 //     Parameter                         0 words
 //     Uniform                           2 words  (one 32-bit uniform per sample)
 //     untruncated Normal / LogNormal    2 words  (Box-Muller across the pair:
-//                                       42-bit radius, 20-bit angle, 2 sign bits; box_muller_front)
+//                                       42-bit radius, 22-bit angle on the full circle; box_muller_front)
 // Bit placement: U52(lo, hi) = ((hi & 0xfffff) * 2^32 + lo + 0.5) * 2^-52,
 //                U32(w) = (rotl(w, 12) + 0.5) * 2^-32.
 //     inverse-CDF marginals             4 words  (one 52-bit uniform per sample)
-//     Gamma (Marsaglia-Tsang)           0 words  (own counters, see gamma_mt)
+//     Gamma (Marsaglia-Tsang)           0 words  (own counters, see gamma_mt_pair)
 // Under a Gaussian copula every random input takes 2 words (its Box-Muller pair).
 #pragma once
 #include "../../include/ebncuda.h"
@@ -85,22 +85,28 @@ struct DynWords {
 // 0x80000000 | j<<16 | e<<15 | t: normal from (w0,w1,w2) (first Box-Muller
 // output), acceptance uniform from w3. The boost uniform is call t = 0x7fff.
 // in.c = d = shape' - 1/3 and in.d = c = 1/sqrt(9 d) are precomputed on the host.
-// One Marsaglia-Tsang attempt: returns true and v = (1 + c z)^3 when accepted.
-__device__ __forceinline__ bool gamma_attempt(double dd, double cc, uint32_t qlo, uint32_t qhi,
-                                              uint32_t stream, uint32_t slot, uint32_t k0,
-                                              uint32_t k1, const FastMathSmem& sm, double& v) {
-  const Philox4 w = philox4x32_10(qlo, qhi, stream, slot, k0, k1);
-  double z, z_unused;
-  box_muller_words(w.w0, w.w1, sm, z, z_unused);
+// The acceptance test of one Marsaglia-Tsang attempt: true and v = (1 + c z)^3 when accepted.
+__device__ __forceinline__ bool gamma_accept(double dd, double cc, double z, double u, const FastMathSmem& sm,
+                                             double& v) {
   const double t1 = fma(cc, z, 1.0);
   v = t1 * t1 * t1;
-  const double u = u32w(w.w3);
   const double z2 = z * z;
   // squeeze, then the exact test; both evaluated branch-free (in a warp some lane needs
   // the logarithms almost always), t1 <= 0 gives NaN/false below and is rejected explicitly
   const bool squeeze = u < fma(-0.0331 * z2, z2, 1.0);
   const bool exact = -neg_log01(u, sm) < fma(dd, 1.0 - v - neg_log_pos(fmax(v, 0x1p-1000), sm), 0.5 * z2);
   return t1 > 0.0 && (squeeze || exact);
+}
+
+// A retry (attempt t >= 1 of one sample): its own Philox call, normal from (w0, w1) (first Box-Muller
+// output), acceptance uniform from w3.
+__device__ __forceinline__ bool gamma_attempt(double dd, double cc, uint32_t qlo, uint32_t qhi,
+                                              uint32_t stream, uint32_t slot, uint32_t k0,
+                                              uint32_t k1, const FastMathSmem& sm, double& v) {
+  const Philox4 w = philox4x32_10(qlo, qhi, stream, slot, k0, k1);
+  double z, z_unused;
+  box_muller_words(w.w0, w.w1, sm, z, z_unused);
+  return gamma_accept(dd, cc, z, u32w(w.w3), sm, v);
 }
 
 // Slow path (about 0.3 % of the samples at shape 25): attempts 1..63, all arguments by value
@@ -122,17 +128,30 @@ static __device__ __noinline__ double gamma_boost(double shape, uint32_t qlo, ui
   return pow(u52w(w.w0, w.w1), 1.0 / shape);
 }
 
-// in.c = d = shape' - 1/3 and in.d = c = 1/sqrt(9 d) are precomputed on the host. The first
-// attempt is inlined (no call, no spills); rejected lanes go to gamma_retry.
-__device__ __forceinline__ double gamma_mt(const DevInput& in, const PairCtr& pc, uint32_t j,
-                                           uint32_t e, const FastMathSmem& sm) {
-  const uint32_t base = 0x80000000u | (j << 16) | (e << 15);
-  double v;
-  if (!gamma_attempt(in.c, in.d, pc.qlo, pc.qhi, pc.stream, base, pc.k0, pc.k1, sm, v))
-    v = gamma_retry(in.c, in.d, pc.qlo, pc.qhi, pc.stream, base, pc.k0, pc.k1, &sm);
-  double x = in.c * v;
-  if (in.a < 1.0) x *= gamma_boost(in.a, pc.qlo, pc.qhi, pc.stream, base, pc.k0, pc.k1);
-  return x * in.b;
+// Both samples of a pair. in.c = d = shape' - 1/3 and in.d = c = 1/sqrt(9 d) are precomputed on the host.
+// Layout v4: the FIRST attempt of the two samples shares one Philox call (counter word 3 =
+// 0x80000000 | j<<16): one Box-Muller gives z for sample 0 and z for sample 1, the acceptance uniforms are
+// w2 and w3 — half the generator calls and half the transforms of v3 on the common path. A rejected sample
+// retries on its own counters (0x80000000 | j<<16 | e<<15 | t, t = 1..63), the shape < 1 boost reads
+// call t = 0x7fff of its sample.
+__device__ __forceinline__ void gamma_mt_pair(const DevInput& in, const PairCtr& pc, uint32_t j,
+                                              const FastMathSmem& sm, double& x0, double& x1) {
+  const uint32_t base = 0x80000000u | (j << 16);
+  const Philox4 w = philox4x32_10(pc.qlo, pc.qhi, pc.stream, base, pc.k0, pc.k1);
+  double z0, z1, v0, v1;
+  box_muller_words(w.w0, w.w1, sm, z0, z1);
+  const bool ok0 = gamma_accept(in.c, in.d, z0, u32w(w.w2), sm, v0);
+  const bool ok1 = gamma_accept(in.c, in.d, z1, u32w(w.w3), sm, v1);
+  if (!ok0) v0 = gamma_retry(in.c, in.d, pc.qlo, pc.qhi, pc.stream, base, pc.k0, pc.k1, &sm);
+  if (!ok1) v1 = gamma_retry(in.c, in.d, pc.qlo, pc.qhi, pc.stream, base | (1u << 15), pc.k0, pc.k1, &sm);
+  x0 = in.c * v0;
+  x1 = in.c * v1;
+  if (in.a < 1.0) {
+    x0 *= gamma_boost(in.a, pc.qlo, pc.qhi, pc.stream, base, pc.k0, pc.k1);
+    x1 *= gamma_boost(in.a, pc.qlo, pc.qhi, pc.stream, base | (1u << 15), pc.k0, pc.k1);
+  }
+  x0 *= in.b;
+  x1 *= in.b;
 }
 
 __device__ __forceinline__ double table_quantile(const DevInput& in, const double* tables,
@@ -222,8 +241,7 @@ __device__ __forceinline__ void draw_back(const DevInput& in, const InState& st,
       x1 = exp_fast(x1, sm);
     }
   } else if (KIND == DK_GAMMA_MT) {
-    x0 = gamma_mt(in, pc, j, 0u, sm);
-    x1 = gamma_mt(in, pc, j, 1u, sm);
+    gamma_mt_pair(in, pc, j, sm, x0, x1);
   } else if (KIND == DK_NORMAL_ICDF || KIND == DK_LOGNORMAL_ICDF) {
     double z0, z1;
     normcdfinv_fast2<CELLS>(fma(u52w(st.w0, st.w1), in.d, in.c), fma(u52w(st.w2, st.w3), in.d, in.c), z0, z1);

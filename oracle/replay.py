@@ -1,7 +1,7 @@
 """NumPy twin of the device sampler (test infrastructure, see oracle/__init__.py).
 
 Restates, independently of the CUDA sources, the stream layout of DESIGN.md
-("Random streams, layout v3") so that the uniforms the GPU consumed can be
+("Random streams, layout v4") so that the uniforms the GPU consumed can be
 regenerated on the CPU:
 
     key     = (seed & 0xffffffff, seed >> 32)
@@ -16,13 +16,14 @@ regenerated on the CPU:
     inverse-CDF kinds  : sample 2q uses U52(W[o], W[o+1]), sample 2q+1 uses U52(W[o+2], W[o+3])
     (Log)Normal        : Box-Muller across the pair from 64 bits (w0, w1) = (W[o], W[o+1]):
                          R = sqrt(-2 ln u), u = (M + 1/2) 2^-42, M = rotl(w0, 12) * 2^10 + (w1 & 0x3ff);
-                         phi = (pi/2) (A + 1/2) 2^-20, A = (w1 >> 10) & 0xfffff;
-                         z(2q) = s0 R sin(phi), z(2q+1) = s1 R cos(phi),
-                         s0 = -1 if w1 bit 31, s1 = -1 if w1 bit 30
-    Gamma (Marsaglia-Tsang): attempt t of sample e of input j is the Philox call with counter
-                         word 3 = 0x80000000 | j << 16 | e << 15 | t: normal = first Box-Muller
-                         output of (w0, w1), acceptance uniform U32(w3); the shape < 1 boost
-                         uniform is U52(w0, w1) of call t = 0x7fff
+                         Phi = (pi/2) (A + 1/2) 2^-20 in (0, 2 pi), A = w1 >> 10 (22 bits);
+                         z(2q) = R sin(Phi), z(2q+1) = R cos(Phi)
+    Gamma (Marsaglia-Tsang): the first attempt of the pair's two samples is ONE Philox call, counter
+                         word 3 = 0x80000000 | j << 16: Box-Muller of (w0, w1) gives the normal of
+                         sample 2q and of sample 2q+1, acceptance uniforms U32(w2), U32(w3); retry t >= 1
+                         of sample e reads call 0x80000000 | j << 16 | e << 15 | t (normal = first
+                         Box-Muller output, uniform U32(w3)); the shape < 1 boost uniform is
+                         U52(w0, w1) of call e << 15 | 0x7fff
     Gaussian copula    : every random input takes 2 words (its Box-Muller pair), z = L eps
 
 Philox4x32-10 itself is pinned by the Random123 known-answer vectors in
@@ -96,12 +97,10 @@ def _box_muller(w0, w1):
     rot = ((w0 << np.uint64(12)) & _MASK) | (w0 >> np.uint64(20))  # rotate left by 12
     M = (rot << np.uint64(10)) | (w1 & np.uint64(0x3FF))             # 42 bits
     u = (M.astype(np.float64) + 0.5) * 2.0**-42
-    A = (w1 >> np.uint64(10)) & np.uint64(0xFFFFF)                   # 20 bits
+    A = w1 >> np.uint64(10)                                          # 22 bits: the full circle
     R = np.sqrt(-2.0 * np.log(u))
-    phi = (np.pi / 2) * ((A.astype(np.float64) + 0.5) * 2.0**-20)
-    s0 = np.where(w1 & np.uint64(0x80000000), -1.0, 1.0)
-    s1 = np.where(w1 & np.uint64(0x40000000), -1.0, 1.0)
-    return s0 * R * np.sin(phi), s1 * R * np.cos(phi)
+    phi = (np.pi / 2) * ((A.astype(np.float64) + 0.5) * 2.0**-20)    # (0, 2 pi)
+    return R * np.sin(phi), R * np.cos(phi)
 
 
 def _box_muller_f32(w0, w1):
@@ -112,11 +111,10 @@ def _box_muller_f32(w0, w1):
     rot = ((w0 << np.uint64(12)) & _MASK) | (w0 >> np.uint64(20))
     u = rot.astype(f32) * f32(2.0**-32) + f32(2.0**-33)
     R = np.sqrt(f32(-2.0) * np.log(u))
-    A = (w1 >> np.uint64(10)) & np.uint64(0xFFFFF)
-    phi = f32(np.pi / 2) * ((A.astype(f32) + f32(0.5)) * f32(2.0**-20))
-    s0 = np.where(w1 & np.uint64(0x80000000), -1.0, 1.0)
-    s1 = np.where(w1 & np.uint64(0x40000000), -1.0, 1.0)
-    return s0 * (R * np.sin(phi)).astype(np.float64), s1 * (R * np.cos(phi)).astype(np.float64)
+    A = w1 >> np.uint64(10)
+    f = ((A.astype(np.float64) + 0.5) * 2.0**-22 - 0.5).astype(f32)      # exact in float32
+    ang = f32(2 * np.pi) * f                                              # Phi - pi
+    return (-(R * np.sin(ang))).astype(np.float64), (-(R * np.cos(ang))).astype(np.float64)
 
 
 def words_of(inp) -> int:
@@ -131,31 +129,44 @@ def words_of(inp) -> int:
     return 4
 
 
-def _gamma_mt(pairs, e: int, shape: float, scale: float, stream: int, j: int, seed: int):
+def _gamma_mt_pair(pairs, shape: float, scale: float, stream: int, j: int, seed: int):
+    """Both samples of every pair (layout v4): the first attempt shares one Philox call — Box-Muller of
+    (w0, w1) gives z of sample 0 and z of sample 1, acceptance uniforms w2 and w3; rejected samples retry on
+    their own counters base | e<<15 | t (normal from the first Box-Muller output, uniform from w3)."""
     a = shape + 1.0 if shape < 1.0 else shape
     dd = a - 1.0 / 3.0
     cc = 1.0 / np.sqrt(9.0 * dd)
-    base = 0x80000000 | (j << 16) | (e << 15)
-    out = np.empty(len(pairs))
-    todo = np.arange(len(pairs))
-    t = 0
-    while len(todo):
-        w0, w1, w2, w3 = _call(pairs[todo], stream, base | t, seed)
-        z, _ = _box_muller(w0, w1)
+    base = 0x80000000 | (j << 16)
+
+    def accept(z, u):
         t1 = 1.0 + cc * z
         v = t1 * t1 * t1
-        u = _u32(w3)
         z2 = z * z
         with np.errstate(invalid="ignore", divide="ignore"):
             ok = (t1 > 0.0) & ((u < 1.0 - 0.0331 * z2 * z2) | (np.log(u) < 0.5 * z2 + dd * (1.0 - v + np.log(v))))
-        out[todo[ok]] = dd * v[ok]
-        todo = todo[~ok]
-        t += 1
-        assert t < 64
-    if shape < 1.0:
-        w0, w1, _, _ = _call(pairs, stream, base | 0x7FFF, seed)
-        out = out * _u52(w0, w1) ** (1.0 / shape)
-    return out * scale
+        return ok, v
+
+    w0, w1, w2, w3 = _call(pairs, stream, base, seed)
+    z0, z1 = _box_muller(w0, w1)
+    outs = []
+    for e, (z, u) in enumerate(((z0, _u32(w2)), (z1, _u32(w3)))):
+        ok, v = accept(z, u)
+        out = np.where(ok, dd * v, np.nan)
+        todo = np.flatnonzero(~ok)
+        t = 1
+        while len(todo):
+            r0, r1, _, r3 = _call(pairs[todo], stream, base | (e << 15) | t, seed)
+            z, _ = _box_muller(r0, r1)
+            ok, v = accept(z, _u32(r3))
+            out[todo[ok]] = dd * v[ok]
+            todo = todo[~ok]
+            t += 1
+            assert t < 64
+        if shape < 1.0:
+            b0, b1, _, _ = _call(pairs, stream, base | (e << 15) | 0x7FFF, seed)
+            out = out * _u52(b0, b1) ** (1.0 / shape)
+        outs.append(out * scale)
+    return outs[0], outs[1]
 
 
 def _window(inp):
@@ -239,8 +250,7 @@ def sample_matrix(inputs_row, stream: int, seed: int, first: int, n: int, tables
             X[:, j] = np.exp(v) if kind == IN_LOGNORMAL else v
         elif kind == IN_GAMMA:
             assert not (np.isfinite(lo) or np.isfinite(hi))
-            g0 = _gamma_mt(upairs, 0, p[0], p[1], stream, j, seed)
-            g1 = _gamma_mt(upairs, 1, p[0], p[1], stream, j, seed)
+            g0, g1 = _gamma_mt_pair(upairs, p[0], p[1], stream, j, seed)
             X[:, j] = np.where(odd, g1[inv], g0[inv])
         else:
             u = np.where(odd, _u52(W[off + 2], W[off + 3])[inv], _u52(W[off], W[off + 1])[inv])

@@ -68,7 +68,7 @@ def main():
     blocks = {}
     for first in (0, 7, 2**33 + 5):
         blocks[f"first_{first}"] = replay.sample_matrix(inputs[0], 3, seed, first, 64, tables=TABLE)
-    np.savez_compressed(os.path.join(HERE, "stream_v3.npz"), inputs=inputs, table=TABLE, seed=np.uint64(seed),
+    np.savez_compressed(os.path.join(HERE, "stream_v4.npz"), inputs=inputs, table=TABLE, seed=np.uint64(seed),
                         stream=np.uint32(3), **blocks)
     # expression programs: the two demos' closures as text, compiled by the product's text compiler
     # (pins the compiler's instruction order) and evaluated by the oracle's stack machine on the same

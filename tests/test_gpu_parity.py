@@ -746,7 +746,7 @@ def test_golden_fixtures(ebn):
     assert c == int(z["vehicle_count"]) and np.array_equal(g, z["vehicle_g"])
     c, g = ebn.eval_matrix(ebn._lib.LS_EXPRESSION, e["straub_program"], z["straub_X"], strict=True, want_g=True)
     assert c == int(z["straub_count"]) and np.max(np.abs(g - z["straub_g"])) < 1e-9
-    s = np.load(os.path.join(gold, "stream_v3.npz"))
+    s = np.load(os.path.join(gold, "stream_v4.npz"))
     inputs = s["inputs"].view(ebn.INPUT_DTYPE).reshape(1, -1)
     inputs4 = np.repeat(inputs, 4, axis=0)  # scenario 3 is stream 3
     d = inputs.shape[1]

@@ -60,7 +60,7 @@ def test_golden_expression_programs():
 
 
 def test_golden_stream_layout():
-    z = np.load(os.path.join(GOLD, "stream_v3.npz"))
+    z = np.load(os.path.join(GOLD, "stream_v4.npz"))
     inputs = z["inputs"].view(ocpu.INPUT_DTYPE).reshape(1, -1)
     for first in (0, 7, 2**33 + 5):
         X = replay.sample_matrix(inputs[0], int(z["stream"]), int(z["seed"]), first, 64, tables=z["table"])

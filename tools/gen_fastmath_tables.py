@@ -68,15 +68,15 @@ def _cheb_fit_centred(f, a, b, deg):
 
 
 def sincos_table(bits):
-    """2^bits cells over the first quadrant: sqrt(2)*(sin, cos) of phi_j = (pi/2)(j + 1/2)/2^bits,
-    correctly rounded, and the two short polynomials for the offset inside a cell,
+    """2^bits cells per quadrant over the FULL circle (4 * 2^bits entries): sqrt(2)*(sin, cos) of
+    phi_j = (pi/2)(j + 1/2)/2^bits, correctly rounded, and the two short polynomials for the offset inside a cell,
     delta = (pi/2) t with |t| <= 2^-(bits+1):  sin(delta) = t*Sd(t^2), cos(delta) - 1 = t^2*Cd(t^2).
     7 bits: 3 + 2 coefficients; 10 bits: 2 + 2 (truncation below 1e-17 either way)."""
     mp = mpmath
     hp = mp.pi / 2
     n = 1 << bits
     rows = []
-    for j in range(n):
+    for j in range(4 * n):
         phi = hp * (mp.mpf(j) + mp.mpf(1) / 2) / n
         rows.append((float(mp.sqrt(2) * mp.sin(phi)), float(mp.sqrt(2) * mp.cos(phi))))
     wmax = mp.mpf(2) ** (-2 * (bits + 1))
@@ -144,9 +144,9 @@ def main():
             f.write(f"  {v.hex()},\n")
         f.write("};\n")
         sc_rows, sd, cd = sincos_table(sc_bits)
-        f.write("// kSinCosTab[j] = sqrt(2)*{sin, cos}((pi/2)(j + 1/2)/2^bits); inside a cell, delta = (pi/2) t:\n")
+        f.write("// kSinCosTab[j] = sqrt(2)*{sin, cos}((pi/2)(j + 1/2)/2^bits), j < 4*2^bits (full circle); inside a cell, delta = (pi/2) t:\n")
         f.write("// sin(delta) = t*(d0 + d1 t^2 [+ d2 t^4]), cos(delta) - 1 = t^2*(e0 + e1 t^2)\n")
-        f.write("static __device__ const double2 kSinCosTab[1 << EBN_SC_TAB_BITS] = {\n")
+        f.write("static __device__ const double2 kSinCosTab[4 << EBN_SC_TAB_BITS] = {\n")
         for a, b in sc_rows:
             f.write(f"  {{{a.hex()}, {b.hex()}}},\n")
         f.write("};\n")
