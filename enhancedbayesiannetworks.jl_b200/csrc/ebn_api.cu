@@ -978,9 +978,99 @@ int ebn_comm_destroy(void) {
   return EBN_OK;
 }
 
+// Scenarios whose marginal KINDS differ cannot share a compile-time sampling plan: the Uniform / Exponential-tail
+// rows `_approximate` puts next to each other (reference discretize.jl:83-91), a parent that is truncated in some
+// states only. Instead of sending the whole job through the runtime-dispatched plan (2-5x slower), a large job is
+// split by kind signature: every group is an ordinary job of its own (its scenarios keep their Philox streams, so
+// the counts are bit-identical to the unsplit call) and finds a compiled-in plan, or gets one compiled at run time.
+constexpr double kSplitMinSamples = 2e9;   // below this the extra launches are not worth it
+constexpr size_t kSplitMaxGroups = 16;
+
+int run_batch_split(const ebn_job_t* job, int mode, const double* edges, int nedges, int64_t* counts_out,
+                    double* sum_out, double* sumsq_out) {
+  const auto whole = [&]() { return run_batch(job, mode, edges, nedges, counts_out, sum_out, sumsq_out); };
+  // count mode only: the moments of histogram mode are summed per work item in item order, and the item grid
+  // depends on the number of scenarios, so a split would change their last bits
+  if (mode != 0 || !job || !job->inputs || job->n_scenarios < 2 || job->n_inputs < 1 || job->corr_chol ||
+      (job->flags & (EBN_JOB_QMC_SOBOL | EBN_JOB_NO_JIT_PLAN)) || job->limit_state == EBN_LS_EXPRESSION ||
+      (double)job->n_per_scenario * job->n_scenarios < kSplitMinSamples)
+    return whole();
+  if (const char* env = getenv("EBN_SPLIT_KINDS"))   // "0": never (experiments)
+    if (env[0] == '0') return whole();
+  const int S = job->n_scenarios, d = job->n_inputs;
+  std::vector<DevInput> plan((size_t)S * d);
+  for (int s = 0; s < S; ++s)
+    for (int j = 0; j < d; ++j)
+      if (canonicalise(job->inputs[(size_t)s * d + j], false, (job->flags & EBN_JOB_FP32_SAMPLING) != 0,
+                       plan[(size_t)s * d + j], s, j, job->n_tables))
+        return whole();   // the ordinary path reports the error
+  std::vector<std::vector<int>> groups;
+  for (int s = 0; s < S; ++s) {
+    size_t g = 0;
+    for (; g < groups.size(); ++g) {
+      bool same = true;
+      for (int j = 0; j < d && same; ++j) same = plan[(size_t)groups[g][0] * d + j].kind == plan[(size_t)s * d + j].kind;
+      if (same) break;
+    }
+    if (g == groups.size()) {
+      if (groups.size() == kSplitMaxGroups) return whole();
+      groups.emplace_back();
+    }
+    groups[g].push_back(s);
+  }
+  if (groups.size() < 2) return whole();
+  // worth it only if some group ends up on a compile-time plan
+  bool gain = false;
+  for (const auto& grp : groups) {
+    std::vector<DevInput> rows;
+    for (int s : grp) rows.insert(rows.end(), plan.begin() + (size_t)s * d, plan.begin() + (size_t)(s + 1) * d);
+    if (static_plan_matches(job->limit_state, rows.data(), (int)grp.size(), d) >= 0 ||
+        ((double)job->n_per_scenario * grp.size() >= kJitPlanMinSamples && jit_available(nullptr)))
+      gain = true;
+  }
+  if (!gain) return whole();
+  const int nb = mode == 0 ? 1 : nedges + 1;
+  ebn_stats_t total{};
+  total.specialised = 1;
+  for (const auto& grp : groups) {
+    const int n = (int)grp.size();
+    std::vector<ebn_input_t> rows;
+    std::vector<uint32_t> streams(n);
+    for (int i = 0; i < n; ++i) {
+      const int s = grp[i];
+      rows.insert(rows.end(), job->inputs + (size_t)s * d, job->inputs + (size_t)(s + 1) * d);
+      streams[i] = job->stream_id ? job->stream_id[s] : (uint32_t)s;
+    }
+    ebn_job_t sub = *job;
+    sub.n_scenarios = n;
+    sub.inputs = rows.data();
+    sub.stream_id = streams.data();
+    std::vector<int64_t> cnt((size_t)n * nb);
+    std::vector<double> s1(n), s2(n);
+    const int rc = run_batch(&sub, mode, edges, nedges, cnt.data(), mode == 1 ? s1.data() : nullptr,
+                             mode == 1 ? s2.data() : nullptr);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+      for (int b = 0; b < nb; ++b) counts_out[(size_t)grp[i] * nb + b] = cnt[(size_t)i * nb + b];
+      if (mode == 1 && sum_out) sum_out[grp[i]] = s1[i];
+      if (mode == 1 && sumsq_out) sumsq_out[grp[i]] = s2[i];
+    }
+    total.kernel_ms += g.stats.kernel_ms;
+    total.h2d_bytes += g.stats.h2d_bytes;
+    total.d2h_bytes += g.stats.d2h_bytes;
+    total.samples += g.stats.samples;
+    total.launches += g.stats.launches;
+    total.devices = g.stats.devices;
+    total.specialised &= g.stats.specialised;
+    total.jit_compiles += g.stats.jit_compiles;
+  }
+  g.stats = total;
+  return EBN_OK;
+}
+
 int ebn_pf_batch(const ebn_job_t* job, int64_t* fail_count, double* pf, double* var) {
   if (!fail_count) return fail(EBN_EINVAL, "fail_count is NULL");
-  int rc = run_batch(job, 0, nullptr, 0, fail_count, nullptr, nullptr);
+  int rc = run_batch_split(job, 0, nullptr, 0, fail_count, nullptr, nullptr);
   if (rc) return rc;
   const double n = (double)job->n_per_scenario;
   for (int s = 0; s < job->n_scenarios; ++s) {
@@ -1000,7 +1090,7 @@ int ebn_hist_batch(const ebn_job_t* job, const double* edges, int nedges, int64_
     if (std::isnan(edges[i])) return fail(EBN_EINVAL, "edge %d is NaN", i);
     if (i && !(edges[i] > edges[i - 1])) return fail(EBN_EINVAL, "edges must be strictly increasing");
   }
-  return run_batch(job, 1, edges, nedges, counts, sum, sumsq);
+  return run_batch_split(job, 1, edges, nedges, counts, sum, sumsq);
 }
 
 int ebn_eval_matrix(int limit_state, const double* consts, int n_consts, const double* X, int64_t n,

@@ -778,3 +778,34 @@ def test_eval_matrix_with_a_leading_dimension_larger_than_n(ebn):
     assert rc == 0
     want_cnt, want_g = ocpu.eval_matrix(ocpu.LS_VEHICLE, k, X, want_g=True)
     assert cnt.value == want_cnt and np.array_equal(g, want_g)
+
+
+def test_large_jobs_with_mixed_marginal_kinds_are_split_by_kind_signature(ebn):
+    """Scenarios whose marginal kinds differ (here: C truncated in four of the 20 scenarios, Ck in two others) cannot
+    share a compile-time sampling plan. A large job is split by kind signature inside the library, every group runs
+    on its own plan with the scenarios' original Philox streams: the counts are bit-identical to the unsplit call
+    through the runtime-dispatched plan (EBN_SPLIT_KINDS=0), and faster."""
+    import os
+    from ebn_b200 import workloads as W
+    job = W.w1_vehicle(n=10**8)
+    job.inputs[2:6, 3]["lo"] = 400.0
+    job.inputs[10:12, 4]["hi"] = 1500.0
+    job.jit_plan = None
+    cnt, _, _ = ebn.pf_batch(job)
+    st = ebn.last_stats()
+    assert st["launches"] == 3 and st["samples"] == 20 * 10**8
+    os.environ["EBN_SPLIT_KINDS"] = "0"
+    try:
+        whole, _, _ = ebn.pf_batch(job)
+        st0 = ebn.last_stats()
+    finally:
+        del os.environ["EBN_SPLIT_KINDS"]
+    assert st0["launches"] == 1 and st0["specialised"] == 0
+    assert np.array_equal(cnt, whole)
+    assert st["kernel_ms"] < 0.6 * st0["kernel_ms"], (st["kernel_ms"], st0["kernel_ms"])
+    # histogram mode is never split (its moments are summed in work-item order, which depends on the scenario count)
+    edges = np.linspace(-2.0, 2.0, 65)
+    small = W.w1_vehicle(n=10**8)
+    small.inputs[0, 3]["lo"] = 400.0
+    ebn.hist_batch(small, edges)
+    assert ebn.last_stats()["launches"] == 2 and ebn.last_stats()["specialised"] == 0
