@@ -243,8 +243,15 @@ def _evaluate_continuous(net, node: ContinuousFunctionalNode, collect_samples=Tr
     info = {}
     for s, ev in enumerate(evidences):
         cpt[ev] = EmpiricalDistribution(edges, counts[s], job.n, float(s1[s]), float(s2[s]))
+        # outputs below the first / above the last edge (heavy tails) or NaN: the shared grid is mean +- 8 sd of a
+        # pilot run, so this is normally 0; say so when it is not instead of folding it away silently
+        outside = float(counts[s][0] + counts[s][-1]) / float(job.n)
+        if outside > 1e-3:
+            import warnings
+            warnings.warn(f"node {node.name}, scenario {tuple(ev.values())}: {100 * outside:.2f} % of the outputs fall "
+                          "outside the histogram grid (heavy tail or NaN); they are kept in the edge bins")
         if collect_samples:
-            info[tuple(ev.values())] = {"samples": uq.Samples(job, s, low.out_columns)}
+            info[tuple(ev.values())] = {"samples": uq.Samples(job, s, low.out_columns), "mass_outside_grid": outside}
     return ContinuousNode(node.name, cpt, disc, info)
 
 

@@ -41,6 +41,8 @@ run("W3 Straub-style copula, 64 scenarios (looping copula plan)", w3)
 w3.jit_plan = True
 run("W3 copula compiled at run time (unrolled plan, coefficient table rewritten as a formula)", w3)
 from ebn_b200 import expr  # noqa: E402
+import dataclasses  # noqa: E402
+run("W1 vehicle, quasi-Monte Carlo (EBN_JOB_QMC_SOBOL: Owen-scrambled Sobol, inverse-CDF marginals)", dataclasses.replace(W.w1_vehicle(n=10**8), qmc=True))
 run("W5 vehicle grid, 1024 scenarios", W.w5_vehicle_grid(n=4 * 10**6))
 run("W4 vehicle, V fixed: 4 states x 25 outer-loop values", W.w4_vehicle_fixed_v(np.linspace(7, 12, 25), n=2 * 10**7))
 j = W.w1_vehicle(n=10**8)
