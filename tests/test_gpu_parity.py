@@ -809,3 +809,34 @@ def test_large_jobs_with_mixed_marginal_kinds_are_split_by_kind_signature(ebn):
     small.inputs[0, 3]["lo"] = 400.0
     ebn.hist_batch(small, edges)
     assert ebn.last_stats()["launches"] == 2 and ebn.last_stats()["specialised"] == 0
+
+
+def test_truncated_normal_cells_reach_full_precision(ebn):
+    """The table-driven Phi^-1 of the truncated-normal kinds (normcdfinv_cells: 16 cells per octave of min(p, 1-p),
+    degree 7) against SciPy on windows in the centre, across the median and deep in both tails, through the
+    compile-time plan (shared-memory cells) and the runtime-dispatched one (the same cells from global memory):
+    1e-15 relative to max(1, |x|) in the centre and the lower tail; the upper-tail window lives at p = 1 - 3e-5,
+    where c + u d itself carries a relative error of 1e-12 in 1 - p (the reference's `truncated` quantile has the
+    same cancellation), so it gets the twin's general 5e-12. The two plans give the same bits."""
+    from ebn_b200 import workloads as W
+    L = ebn._lib
+    n = 200_000
+    job = W.w1_vehicle(n=n, strict=True)
+    wins = {3: (400.0, 460.0), 4: (-INF, 1440.0), 5: (95.0, INF)}          # C central, Ck lower tail (-3.5 sigma), K upper tail (+4 sigma)
+    for col, (lo, hi) in wins.items():
+        job.inputs[:, col]["lo"], job.inputs[:, col]["hi"] = lo, hi
+    ebn.pf_batch(job)
+    assert ebn.last_stats()["specialised"] == 1
+    X = ebn.sample_matrix(job, 3, 0, n)
+    ref = replay.sample_matrix(job.inputs[3], 3, job.seed, 0, n)
+    err = np.max(np.abs(X - ref) / np.maximum(np.abs(ref), 1.0), axis=0)
+    assert np.all(err[3:5] < 1e-15) and err[5] < 5e-12, err
+    assert X[:, 3].min() >= 400.0 and X[:, 3].max() <= 460.0 and X[:, 4].max() <= 1440.0 and X[:, 5].min() >= 95.0
+    mixed = W.w1_vehicle(n=n, strict=True)
+    mixed.inputs[:] = job.inputs
+    mixed.inputs[0, 2]["kind"] = L.IN_PARAM                                  # scenario 0 differs: no compile-time plan
+    mixed.inputs[0, 2]["p"] = [9.0, 0, 0, 0]
+    mixed.inputs[0, 2]["lo"], mixed.inputs[0, 2]["hi"] = -INF, INF
+    ebn.pf_batch(mixed)
+    assert ebn.last_stats()["specialised"] == 0
+    assert np.array_equal(ebn.sample_matrix(mixed, 3, 0, n), X)
