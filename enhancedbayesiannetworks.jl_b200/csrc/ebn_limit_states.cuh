@@ -175,7 +175,7 @@ struct StraubFrame {
   static constexpr int ID = EBN_LS_STRAUB_FRAME;
   static constexpr bool HAS_FAILS = false;
 #ifndef EBN_STRAUB_BLOCKS
-#define EBN_STRAUB_BLOCKS EBN_BLOCKS_FOR_WARPS(8)  // measured: 8 warps/SM 3.39e10, 16 warps/SM 3.28e10 samples/s
+#define EBN_STRAUB_BLOCKS EBN_BLOCKS_FOR_WARPS(12)  // register cap 168; measured (profiles/r02_tune_w2.txt): bound 2 4.30e10, 3 4.35e10, 4 4.16e10 samples/s
 #endif
   static constexpr int MIN_BLOCKS = EBN_STRAUB_BLOCKS;
   static constexpr int D = 8;

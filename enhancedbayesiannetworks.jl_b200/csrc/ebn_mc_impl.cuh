@@ -312,6 +312,13 @@ __device__ __forceinline__ unsigned static_count_step(const typename LS::Ctx& ct
   return f0 + f1;
 }
 
+// Plans with more random inputs than this keep front and back end of a pair in the same trip: the state that
+// would have to be carried (and copied) between trips grows with the number of inputs, and at eight inputs
+// (Straub frame) the copies cost more than the overlap gains (profiles/r02_tune_w2.txt).
+#ifndef EBN_PIPE_MAX_INPUTS
+#define EBN_PIPE_MAX_INPUTS 7
+#endif
+
 template <class LS, class Plan, bool CHECK>
 __device__ __forceinline__ unsigned static_count_loop(const typename LS::Ctx& ctx,
                                                       const DevInput* r_plan, PairCtr pc,
@@ -320,6 +327,24 @@ __device__ __forceinline__ unsigned static_count_loop(const typename LS::Ctx& ct
   constexpr int NC = static_calls<Plan>() > 0 ? static_calls<Plan>() : 1;
   unsigned cnt = 0;
   int64_t q = q_begin + tid;
+  if constexpr (Plan::n > EBN_PIPE_MAX_INPUTS) {
+    constexpr int XCAP = LS::XCAP;
+    for (; q < q_end; q += kThreads) {
+      pc.qlo = (uint32_t)q;
+      pc.qhi = (uint32_t)((uint64_t)q >> 32);
+      double x0[XCAP], x1[XCAP];
+      draw_inputs<Plan, XCAP>(r_plan, nullptr, p.d, pc, p.tables, sm, x0, x1);
+      const unsigned f0 = sample_fails<LS>(ctx, x0) ? 1u : 0u;
+      const unsigned f1 = sample_fails<LS>(ctx, x1) ? 1u : 0u;
+      if (CHECK) {
+        const int64_t i0 = q << 1;
+        cnt += ((i0 >= p.first) ? f0 : 0u) + (((i0 + 1) < p.last) ? f1 : 0u);
+      } else {
+        cnt += f0 + f1;
+      }
+    }
+    return cnt;
+  }
   InState nxt[Plan::n];
   {
     Philox4 ph[NC];
