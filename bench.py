@@ -361,7 +361,7 @@ def main():
                 "n_per_scenario": n_per_scenario, "scenarios": job.S, "strict_fp": bool(args.strict),
                 "parallelism": mode,
                 "l2": "256 MiB flush written between timed iterations; inputs are O(KB) descriptors",
-                "rng": "Philox4x32-10, 32-bit uniforms, Box-Muller from 64 bits per normal pair (42-bit radius, 20-bit angle); "
+                "rng": "Philox4x32-10, 32-bit uniforms, Box-Muller from 64 bits per normal pair (42-bit radius, 22-bit full-circle angle); "
                        "coarser than Julia's 52-bit rand, see DESIGN.md section 4",
             },
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
