@@ -347,6 +347,10 @@ def main():
         ncu_line = {k: ncu.get(k) for k in ("fp64_pipe_active_pct", "alu_pipe_active_pct", "fmaheavy_pipe_active_pct",
                                             "issue_slots_active_pct", "tensor_pipe_active_pct", "shared_wavefronts_pct_of_peak",
                                             "registers_per_thread", "capture")}
+        if ncu.get("fp64_warp_instructions") and ncu.get("samples_in_capture"):
+            # SURVEY 8d cross-check: executed fp64 thread instructions per sample in the capture vs the SASS figure
+            ncu_line["fp64_thread_instructions_per_sample_executed"] = round(
+                ncu["fp64_warp_instructions"] * 32.0 / ncu["samples_in_capture"], 3)
         ncu_line["stale"] = ncu.get("build_id") != prof["build_id"]
         ncu_line["source"] = "profiles/w1_kernel_profile.json (tools/freeze_profile.py --ncu; build id checked above)"
         mode = (f"one process, {n_gpus} devices (ncclCommInitAll inside the library)" if single

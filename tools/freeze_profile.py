@@ -58,6 +58,24 @@ def sass_half():
             "fp64_by_distinct_register_pair_sources": dict(dsrc), "listing": "profiles/w1_hot_loop.sass"}
 
 
+SAMPLES_IN_CAPTURE = 2e8     # tools/run_workload.py w1 2e8: 20 scenarios x 1e7 samples in the captured launch
+
+
+def fp64_executed(rep):
+    """Executed warp instructions on the fp64 pipe, summed over the SASS lines of the source page
+    (`--set full` carries the pipe's utilisation but not its instruction count)."""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    head = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    src, ex = rows[head].index("Source"), rows[head].index("Instructions Executed")
+    total = 0
+    for r in rows[head + 1:]:
+        if len(r) > ex and A.PIPE.get(A.opcode(r[src].strip())[0]) == "fp64":
+            total += int(r[ex])
+    return float(total)
+
+
 def ncu_half(rep, build_id):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -80,7 +98,8 @@ def ncu_half(rep, build_id):
             rows[1][rows[0].index("dram__bytes_write.sum")], 1.0),
         "registers_per_thread": g("launch__registers_per_thread"),
         "warp_instructions": g("smsp__inst_executed.sum"),
-        "fp64_warp_instructions": g("smsp__inst_executed_pipe_fp64.sum") if "smsp__inst_executed_pipe_fp64.sum" in m else None,
+        "fp64_warp_instructions": fp64_executed(rep),
+        "samples_in_capture": SAMPLES_IN_CAPTURE,
         "warps_issue_stalled_per_issue": stalls,
     }
 
