@@ -308,7 +308,7 @@ def main():
         step(shard(W.w5_vehicle_grid(n=1_000_000)))
         ms, wl, _ = timed(w5, 1)
         extras["strong"] = {
-            "workload": f"W5 vehicle_suspension grid (BASELINE configs[4] at 1/10 of its size): 1024 scenarios x "
+            "workload": f"W5 vehicle_suspension grid (BASELINE configs[4] at {args.strong_n / 1e10:.3g} of its size): 1024 scenarios x "
                         f"{int(args.strong_n):.3g} samples = {1024 * int(args.strong_n):.4g} limit-state evaluations in "
                         "total, sharded over the ranks",
             "scaling": "strong", "n_gpus": n_gpus, "value": 1024 * int(args.strong_n) / (ms * 1e-3), "unit": UNIT,
