@@ -355,6 +355,9 @@ struct Prepared {
   int64_t first = 0, last = 0, pair_base = 0, pairs_per_item = 0, items_per_scenario = 0;
   int world = 1;  // job world * devices
   // run-time compiled kernels (expression limit states, sampling plans without a compiled-in plan)
+  // the kernel dispatches marginal kinds at run time and some scenario draws a truncated normal: the launch
+  // carries the Phi^-1 cell table in dynamic shared memory (McParams::icdf_dyn)
+  bool icdf_dyn = false;
   bool jit = false;
   JitSpec jit_spec;
   JitKernel* jit_kernel[4] = {nullptr, nullptr, nullptr, nullptr};  // by JitRole
@@ -523,6 +526,10 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
         for (int j = 0; j < d; ++j) P.jit_spec.kinds.push_back(P.plan[j].kind);
       if (!P.jit_spec.kinds.empty() && !copula) P.plan_class = PLAN_STATIC0;
     }
+  }
+  if (P.plan_class == PLAN_DYNAMIC || (P.plan_class == PLAN_COPULA && P.jit_spec.kinds.empty())) {
+    for (const DevInput& in : P.plan)
+      if (in.kind == DK_NORMAL_ICDF || in.kind == DK_LOGNORMAL_ICDF) { P.icdf_dyn = true; break; }
   }
   P.world = jw * (ndev_override > 0 ? ndev_override : (int)g.devs.size());
   P.first = job->sample_offset;
@@ -734,7 +741,7 @@ int run_batch(const ebn_job_t* job_in, int mode, const double* edges, int nedges
   if (jw > 1 && nd > 1)
     return fail(EBN_ESTATE, "multi-device init and multi-rank sharding cannot be combined");
   const size_t ncnt = mode == 0 ? (size_t)S : (size_t)S * (nedges + 1);
-  const size_t dyn = mode == 0 ? 0 : (size_t)nedges * sizeof(double) + (size_t)(nedges + 1) * sizeof(unsigned);
+  const size_t dyn = hist_dyn_bytes(mode == 0 ? 0 : nedges) + (P.icdf_dyn ? (size_t)kIcdfDynBytes : 0);
   std::vector<void*> ci(nd), cf(nd);
   std::vector<McParams> mps(nd);
   std::vector<int> blocks(nd);
@@ -746,6 +753,7 @@ int run_batch(const ebn_job_t* job_in, int mode, const double* edges, int nedges
     const int rank = jr * (int)nd + (int)k;
     if ((rc = stage(dv, job, P, rank, mps[k], h2d))) return rc;
     McParams& mp = mps[k];
+    mp.icdf_dyn = P.icdf_dyn ? 1 : 0;
     if ((rc = dv.counts.ensure(ncnt * sizeof(unsigned long long)))) return rc;
     CU(cudaMemsetAsync(dv.counts.p, 0, ncnt * sizeof(unsigned long long), dv.st));
     mp.counts = (unsigned long long*)dv.counts.p;

@@ -74,6 +74,14 @@ struct McParams {
   int32_t ncols;  // replay: columns written per sample (d inputs + model outputs)
   int32_t hist_uniform;  // HIST: edges are equally spaced -> direct bin index + exact fix-up
   double hist_e0, hist_inv_h;
+  int32_t icdf_dyn;  // run-time dispatched plans: the launch carries kIcdfDynBytes of dynamic shared memory for the Phi^-1 cells
 };
+
+// Dynamic shared memory of mc_kernel (ebn_mc_impl.cuh): the histogram's edges and bins, rounded up to 16
+// bytes, then — for run-time dispatched plans that draw truncated normals — the Phi^-1 cell table.
+constexpr int kIcdfDynBytes = 257 * 5 * 16;   // EBN_ICDF_ROWS rows, kIcdfStride double2 apart (ebn_fastmath.cuh)
+__host__ __device__ constexpr size_t hist_dyn_bytes(int nedges) {
+  return nedges > 0 ? (((size_t)nedges * sizeof(double) + (size_t)(nedges + 1) * sizeof(unsigned)) + 15) / 16 * 16 : 0;
+}
 
 }  // namespace ebn

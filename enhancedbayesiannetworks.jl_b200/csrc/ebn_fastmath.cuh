@@ -204,9 +204,35 @@ __device__ __forceinline__ void icdf_init(int tid, int nthreads) {
   for (int i = tid; i < EBN_ICDF_ROWS * 4; i += nthreads) t[(i >> 2) * kIcdfStride + (i & 3)] = g[i];
 }
 
-// SMEM: read the cell from the shared-memory copy (compile-time sampling plans), else from the global
-// table behind L1 (run-time dispatched plans: no shared memory is spent on a table most jobs never touch;
-// the arithmetic is the same, so both give the same bits).
+// Run-time dispatched plans: where the cells are read from is decided per launch. A job whose plan holds a
+// truncated normal gets a copy of the table in DYNAMIC shared memory (the host adds kIcdfDynBytes to the
+// launch, McParams::icdf_dyn); every other job reads the global table behind L1 and spends no shared
+// memory on it. Behind L1 the 32 lanes' rows are 32 cache lines per load (one tag stage each): W1 with two
+// truncated normals ran at 2.6e10 samples/s that way against 1.0e11 from shared memory.
+struct IcdfDyn {
+  const double2* base;
+  int stride;   // double2 per row
+};
+static_assert(kIcdfDynBytes == EBN_ICDF_ROWS * kIcdfStride * 16, "ebn_device.cuh: kIcdfDynBytes");
+__device__ __forceinline__ IcdfDyn& icdf_dyn() {
+  __shared__ IcdfDyn s_icdf_dyn;
+  return s_icdf_dyn;
+}
+// Called by every thread of the block before a __syncthreads(); `smem` = 16-byte aligned room for the copy
+// or nullptr.
+__device__ __forceinline__ void icdf_dyn_init(int tid, int nthreads, void* smem) {
+  const double2* g = reinterpret_cast<const double2*>(kIcdfTab);
+  if (smem) {
+    double2* t = reinterpret_cast<double2*>(smem);
+    for (int i = tid; i < EBN_ICDF_ROWS * 4; i += nthreads) t[(i >> 2) * kIcdfStride + (i & 3)] = g[i];
+    if (tid == 0) icdf_dyn() = IcdfDyn{t, kIcdfStride};
+  } else if (tid == 0) {
+    icdf_dyn() = IcdfDyn{g, 4};
+  }
+}
+
+// SMEM: read the cell from the static shared-memory copy (compile-time sampling plans), else through the
+// block's IcdfDyn handle (run-time dispatched plans). The arithmetic is the same, so all give the same bits.
 template <bool SMEM>
 __device__ __forceinline__ double normcdfinv_cells(double p, bool& rare) {
   const bool lower = p < 0.5;
@@ -224,8 +250,9 @@ __device__ __forceinline__ double normcdfinv_cells(double p, bool& rare) {
     const double2* co = icdf_smem() + kIcdfStride * row;
     c01 = co[0], c23 = co[1], c45 = co[2], c67 = co[3];
   } else {
-    const double2* co = reinterpret_cast<const double2*>(kIcdfTab[row]);
-    c01 = __ldg(co), c23 = __ldg(co + 1), c45 = __ldg(co + 2), c67 = __ldg(co + 3);
+    const IcdfDyn t = icdf_dyn();
+    const double2* co = t.base + t.stride * (int)row;
+    c01 = co[0], c23 = co[1], c45 = co[2], c67 = co[3];
   }
   double z = fma(dm, c67.y, c67.x);
   z = fma(dm, z, c45.y);

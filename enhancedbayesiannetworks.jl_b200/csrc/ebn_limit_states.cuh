@@ -174,6 +174,11 @@ template <class Ops>
 struct StraubFrame {
   static constexpr int ID = EBN_LS_STRAUB_FRAME;
   static constexpr bool HAS_FAILS = false;
+// Resident warps per SM the variadic limit states (polynomial program, min of affine forms) are compiled
+// for: 65536 / (32 warps) registers per thread.
+#ifndef EBN_GENERIC_WARPS
+#define EBN_GENERIC_WARPS 24
+#endif
 #ifndef EBN_STRAUB_BLOCKS
 #define EBN_STRAUB_BLOCKS EBN_BLOCKS_FOR_WARPS(12)  // register cap 168; measured (profiles/r02_tune_w2.txt): bound 2 4.30e10, 3 4.35e10, 4 4.16e10 samples/s
 #endif
@@ -307,7 +312,7 @@ template <class Ops>
 struct PolynomialProgram {
   static constexpr int ID = EBN_LS_POLYNOMIAL;
   static constexpr bool HAS_FAILS = false;
-  static constexpr int MIN_BLOCKS = EBN_BLOCKS_FOR_WARPS(24);
+  static constexpr int MIN_BLOCKS = EBN_BLOCKS_FOR_WARPS(EBN_GENERIC_WARPS);
   static constexpr int D = -1;  // variadic
   static constexpr int XCAP = EBN_MAX_INPUTS;
   static constexpr int NC = -1;
@@ -340,6 +345,40 @@ struct PolynomialProgram {
     }
     return acc;
   }
+  // Both samples of a pair in ONE pass over the (warp-uniform) program: the decoding — loads, integer
+  // conversions, loop control — is paid once, every sample still sees the operations of eval() in order.
+  static constexpr bool HAS_EVAL_PAIR = true;
+  __device__ __forceinline__ static void eval_pair(const Ctx& c, double* x0, double* x1, double& g0, double& g1) {
+    const double* p = c.prog;
+    const int T = (int)__ldg(p);
+    int pos = 1, col = c.d;
+    double a0 = 0.0, a1 = 0.0;
+    for (int t = 0; t < T; ++t) {
+      const int nterms = (int)__ldg(p + pos++);
+      a0 = 0.0;
+      a1 = 0.0;
+      for (int k = 0; k < nterms; ++k) {
+        const double coef = __ldg(p + pos);
+        const int nf = (int)__ldg(p + pos + 1);
+        pos += 2;
+        double t0 = coef, t1 = coef;
+        for (int f = 0; f < nf; ++f) {
+          const int j = (int)__ldg(p + pos++);
+          t0 = Ops::mul(t0, x0[j]);
+          t1 = Ops::mul(t1, x1[j]);
+        }
+        a0 = (k == 0) ? t0 : Ops::add(a0, t0);
+        a1 = (k == 0) ? t1 : Ops::add(a1, t1);
+      }
+      if (col < XCAP) {
+        x0[col] = a0;
+        x1[col] = a1;
+      }
+      ++col;
+    }
+    g0 = a0;
+    g1 = a1;
+  }
 };
 
 // ---------------------------------------------------------------------------
@@ -350,7 +389,7 @@ template <class Ops>
 struct MinAffine {
   static constexpr int ID = EBN_LS_MIN_AFFINE;
   static constexpr bool HAS_FAILS = false;
-  static constexpr int MIN_BLOCKS = EBN_BLOCKS_FOR_WARPS(24);
+  static constexpr int MIN_BLOCKS = EBN_BLOCKS_FOR_WARPS(EBN_GENERIC_WARPS);
   static constexpr int D = -1;
   static constexpr int XCAP = EBN_MAX_INPUTS;
   static constexpr int NC = -1;
@@ -372,6 +411,25 @@ struct MinAffine {
       g = (r == 0) ? acc : Ops::min(g, acc);
     }
     return g;
+  }
+  static constexpr bool HAS_EVAL_PAIR = true;   // see PolynomialProgram::eval_pair
+  __device__ __forceinline__ static void eval_pair(const Ctx& c, double* x0, double* x1, double& g0, double& g1) {
+    const int K = (int)__ldg(c.k);
+    double m0 = 0.0, m1 = 0.0;
+    for (int r = 0; r < K; ++r) {
+      const double* row = c.k + 1 + r * (1 + c.d);
+      const double b = __ldg(row);
+      double a0 = b, a1 = b;
+      for (int j = 0; j < c.d; ++j) {
+        const double w = __ldg(row + 1 + j);
+        a0 = Ops::add(a0, Ops::mul(w, x0[j]));
+        a1 = Ops::add(a1, Ops::mul(w, x1[j]));
+      }
+      m0 = (r == 0) ? a0 : Ops::min(m0, a0);
+      m1 = (r == 0) ? a1 : Ops::min(m1, a1);
+    }
+    g0 = m0;
+    g1 = m1;
   }
 };
 

@@ -29,6 +29,17 @@ constexpr int kPairUnroll = EBN_UNROLL;  // pairs per trip of the static count l
 #define EBN_PINGPONG 0
 #endif
 
+// Runtime-dispatched plans under a variadic limit state: marginal transforms inlined into the input loop (1)
+// or one out-of-line call per input (0).
+#ifndef EBN_DYN_INLINE
+#define EBN_DYN_INLINE 1
+#endif
+// The same input loop for fixed-arity limit states under a run-time dispatched plan (1), or their unrolled
+// per-input calls (0).
+#ifndef EBN_DYN_LOOP_ALL
+#define EBN_DYN_LOOP_ALL 1
+#endif
+
 // Compile-time sampling plans ------------------------------------------------
 template <int... K>
 struct StaticPlan {
@@ -84,6 +95,13 @@ __host__ __device__ constexpr bool plan_uses_icdf() {
     // quasi-Monte Carlo, where every normal goes through Phi^-1
     return plan_is_qmc<Plan>::value;
   }
+}
+
+// Plans whose kinds are known at run time only (dynamic, looping copula): they read the Phi^-1 cells through
+// the block's IcdfDyn handle and the pair's Philox words from a buffer (pair_words).
+template <class Plan>
+__host__ __device__ constexpr bool plan_reads_icdf_dyn() {
+  return !Plan::is_static && !Plan::is_static_copula && !plan_is_qmc<Plan>::value;
 }
 
 // Word offset of input J in a static plan, and the number of Philox calls a pair needs.
@@ -175,7 +193,7 @@ struct DrawAll {
 };
 
 // sp: the scenario's plan (registers for a static plan, shared memory otherwise).
-template <class Plan, int XCAP>
+template <class Plan, int XCAP, bool LOOPED = false>
 __device__ __forceinline__ void draw_inputs(const DevInput* sp, const double* sL, int d,
                                             const PairCtr& pc, const double* tables,
                                             const FastMathSmem& sm, double* x0, double* x1) {
@@ -198,31 +216,50 @@ __device__ __forceinline__ void draw_inputs(const DevInput* sp, const double* sL
   } else if constexpr (Plan::is_copula) {
     draw_pair_copula(sp, sL, d, pc, tables, sm, x0, x1);
   } else {
-    Philox4 cache;
-    int cached_call = -1;
+    __align__(16) uint32_t wbuf[kMaxPairWords];
+    pair_words(pc, wbuf);
+    if constexpr (LOOPED) {
+      // variadic limit states index x[] at run time anyway: a real loop over the d inputs keeps the columns
+      // in local memory instead of a 16-way predicated unroll with compare trees for every x[k]
+#pragma unroll 1
+      for (int j = 0; j < d; ++j) {
+#if EBN_DYN_INLINE
+        draw_pair_dyn_body(sp[j], pc, wbuf, (uint32_t)j, tables, sm, x0[j], x1[j]);
+#else
+        draw_pair_dyn(sp[j], pc, wbuf, (uint32_t)j, tables, sm, x0[j], x1[j]);
+#endif
+      }
+    } else {
 #pragma unroll
-    for (int j = 0; j < XCAP; ++j) {
-      if (j < d) draw_pair_dyn(sp[j], pc, cache, cached_call, (uint32_t)j, tables, sm, x0[j], x1[j]);
+      for (int j = 0; j < XCAP; ++j) {
+        if (j < d) draw_pair_dyn(sp[j], pc, wbuf, (uint32_t)j, tables, sm, x0[j], x1[j]);
+      }
     }
   }
 }
 
 // Quasi-Monte Carlo draw of one pair: `st` stands at the pair's even sample; Parameters take no dimension.
-template <int XCAP>
+template <int XCAP, bool LOOPED = false>
 __device__ __forceinline__ void draw_inputs_qmc(const DevInput* sp, int d, const QmcState& st, const double* tables,
                                                 const FastMathSmem& sm, double* x0, double* x1) {
   const uint32_t* V = sobol_smem();
   int r = 0;
+  auto one = [&](int j) {
+    if (sp[j].kind == DK_CONST) {
+      x0[j] = sp[j].a;
+      x1[j] = sp[j].a;
+    } else {
+      draw_pair_qmc(sp[j], st.v[r], V[r * 32], st.key[r], tables, sm, x0[j], x1[j]);
+      ++r;
+    }
+  };
+  if constexpr (LOOPED) {   // see draw_inputs
+#pragma unroll 1
+    for (int j = 0; j < d; ++j) one(j);
+  } else {
 #pragma unroll
-  for (int j = 0; j < XCAP; ++j) {
-    if (j < d) {
-      if (sp[j].kind == DK_CONST) {
-        x0[j] = sp[j].a;
-        x1[j] = sp[j].a;
-      } else {
-        draw_pair_qmc(sp[j], st.v[r], V[r * 32], st.key[r], tables, sm, x0[j], x1[j]);
-        ++r;
-      }
+    for (int j = 0; j < XCAP; ++j) {
+      if (j < d) one(j);
     }
   }
 }
@@ -251,6 +288,21 @@ __device__ __forceinline__ bool sample_fails(const typename LS::Ctx& ctx, double
     return LS::fails(ctx, x);
   } else {
     return LS::eval(ctx, x) < 0.0;
+  }
+}
+
+// Limit states that decode a program per evaluation may offer eval_pair (both samples of a pair in one pass).
+template <class LS, class = void>
+struct ls_has_eval_pair { static constexpr bool value = false; };
+template <class LS>
+struct ls_has_eval_pair<LS, decltype((void)LS::HAS_EVAL_PAIR)> { static constexpr bool value = LS::HAS_EVAL_PAIR; };
+template <class LS>
+__device__ __forceinline__ void eval_two(const typename LS::Ctx& ctx, double* x0, double* x1, double& g0, double& g1) {
+  if constexpr (ls_has_eval_pair<LS>::value) {
+    LS::eval_pair(ctx, x0, x1, g0, g1);
+  } else {
+    g0 = LS::eval(ctx, x0);
+    g1 = LS::eval(ctx, x1);
   }
 }
 
@@ -407,7 +459,9 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
   __shared__ double s_chol[Plan::is_copula ? EBN_MAX_INPUTS * EBN_MAX_INPUTS : 1];
   __shared__ unsigned int s_red[kWarps];
   __shared__ double s_sum[MODE == 1 ? 2 * kWarps : 1];
-  extern __shared__ unsigned char s_dyn[];  // MODE 1: edges (double) then bins (u32)
+  // dynamic shared memory: MODE 1: edges (double) then bins (u32); then, 16-byte aligned, the Phi^-1 cells of a
+  // run-time dispatched plan that draws truncated normals (p.icdf_dyn)
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   double* s_edges = reinterpret_cast<double*>(s_dyn);
   unsigned int* s_bins = reinterpret_cast<unsigned int*>(s_dyn + sizeof(double) * (MODE == 1 ? p.nedges : 0));
 
@@ -419,6 +473,8 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
   const int tid = threadIdx.x;
   fastmath_init(s_fm, tid, kThreads);
   if constexpr (plan_uses_icdf<Plan>()) icdf_init(tid, kThreads);
+  if constexpr (plan_reads_icdf_dyn<Plan>())
+    icdf_dyn_init(tid, kThreads, p.icdf_dyn ? s_dyn + hist_dyn_bytes(MODE == 1 ? p.nedges : 0) : nullptr);
   if constexpr (plan_is_qmc<Plan>::value) sobol_init(tid, kThreads);
   if (MODE == 1) {
     for (int i = tid; i < p.nedges; i += kThreads) s_edges[i] = p.edges[i];
@@ -444,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
     pc.stream = p.stream_id ? p.stream_id[s] : (uint32_t)s;
     pc.k0 = p.k0;
     pc.k1 = p.k1;
+    pc.ncalls = plan_reads_icdf_dyn<Plan>() ? pair_calls(s_plan, p.d, Plan::is_copula) : 0;
 
     const int64_t q_begin = p.pair_base + c * p.pairs_per_item;
     int64_t q_end = q_begin + p.pairs_per_item;
@@ -478,20 +535,28 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
       double x0[XCAP], x1[XCAP];
       if constexpr (plan_is_qmc<Plan>::value) {
         qmc_move(qs, (uint32_t)(q << 1), qmc_nd);
-        draw_inputs_qmc<XCAP>(s_plan, p.d, qs, p.tables, s_fm, x0, x1);
+        draw_inputs_qmc<XCAP, (LS::D < 0 || EBN_DYN_LOOP_ALL)>(s_plan, p.d, qs, p.tables, s_fm, x0, x1);
       } else {
-        draw_inputs<Plan, XCAP>(plan_ptr, s_chol, p.d, pc, p.tables, s_fm, x0, x1);
+        draw_inputs<Plan, XCAP, (LS::D < 0 || EBN_DYN_LOOP_ALL)>(plan_ptr, s_chol, p.d, pc, p.tables, s_fm, x0, x1);
       }
       const int64_t i0 = q << 1;
       const bool v0 = i0 >= p.first;           // i0 < last holds by construction
       const bool v1 = (i0 + 1) < p.last;       // i0+1 >= first holds by construction
       if (MODE == 0) {
-        const bool f0 = sample_fails<LS>(ctx, x0);
-        const bool f1 = sample_fails<LS>(ctx, x1);
+        bool f0, f1;
+        if constexpr (ls_has_eval_pair<LS>::value && !LS::HAS_FAILS) {
+          double g0, g1;
+          eval_two<LS>(ctx, x0, x1, g0, g1);
+          f0 = g0 < 0.0;
+          f1 = g1 < 0.0;
+        } else {
+          f0 = sample_fails<LS>(ctx, x0);
+          f1 = sample_fails<LS>(ctx, x1);
+        }
         cnt += (unsigned)(v0 && f0) + (unsigned)(v1 && f1);
       } else {
-        const double g0 = LS::eval(ctx, x0);
-        const double g1 = LS::eval(ctx, x1);
+        double g0, g1;
+        eval_two<LS>(ctx, x0, x1, g0, g1);
         const int b0 = p.hist_uniform ? find_bin_uniform(s_edges, p.nedges, g0, p.hist_e0, p.hist_inv_h)
                                       : find_bin(s_edges, p.nedges, g0);
         const int b1 = p.hist_uniform ? find_bin_uniform(s_edges, p.nedges, g1, p.hist_e0, p.hist_inv_h)
@@ -563,6 +628,7 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
   LS::setup(ctx, p.consts, p.n_consts, p.d, &s_fm);
   fastmath_init(s_fm, threadIdx.x, kThreads);
   if constexpr (plan_uses_icdf<Plan>()) icdf_init(threadIdx.x, kThreads);
+  if constexpr (plan_reads_icdf_dyn<Plan>()) icdf_dyn_init(threadIdx.x, kThreads, nullptr);
   if constexpr (plan_is_qmc<Plan>::value) sobol_init(threadIdx.x, kThreads);
   if (threadIdx.x < p.d) s_plan[threadIdx.x] = p.plan[(int64_t)scenario * p.d + threadIdx.x];
   if (Plan::is_copula) {
@@ -574,6 +640,7 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
   pc.stream = p.stream_id ? p.stream_id[scenario] : (uint32_t)scenario;
   pc.k0 = p.k0;
   pc.k1 = p.k1;
+  pc.ncalls = plan_reads_icdf_dyn<Plan>() ? pair_calls(s_plan, p.d, Plan::is_copula) : 0;
   const int64_t q_last = (p.last + 1) >> 1;
   for (int64_t q = p.pair_base + (int64_t)blockIdx.x * kThreads + threadIdx.x; q < q_last;
        q += (int64_t)gridDim.x * kThreads) {
@@ -659,8 +726,10 @@ template <template <class> class LST, class... SPlans>
 struct LsLaunch {
   template <class LS, class Plan>
   static cudaError_t occ2(int mode, size_t dyn, int* out) {
-    if (mode == 0)
+    if (mode == 0) {
+      if (dyn) cudaFuncSetAttribute(mc_kernel<LS, Plan, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, mc_kernel<LS, Plan, 0>, kThreads, dyn);
+    }
     // histogram mode: static tables + dynamic edges and bins may pass 48 KB together: opt in
     cudaFuncSetAttribute(mc_kernel<LS, Plan, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, mc_kernel<LS, Plan, 1>, kThreads, dyn);
@@ -668,6 +737,7 @@ struct LsLaunch {
   template <class LS, class Plan>
   static cudaError_t launch2(int mode, const McParams& p, int blocks, size_t dyn, cudaStream_t st) {
     if (mode == 0) {
+      if (dyn) cudaFuncSetAttribute(mc_kernel<LS, Plan, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       mc_kernel<LS, Plan, 0><<<blocks, kThreads, dyn, st>>>(p);
     } else {
       cudaFuncSetAttribute(mc_kernel<LS, Plan, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

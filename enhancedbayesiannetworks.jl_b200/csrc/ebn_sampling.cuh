@@ -29,6 +29,7 @@ struct PairCtr {
   uint32_t qlo, qhi;  // pair index
   uint32_t stream;    // scenario stream id
   uint32_t k0, k1;    // key
+  int ncalls;         // run-time dispatched plans: Philox calls one pair of the scenario consumes (pair_calls)
 };
 
 // 52-bit uniform in (0,1) from two words: mantissa = (hi & 0xfffff) : lo.
@@ -59,25 +60,36 @@ struct StaticWords {
     return (W & 3) == 0 ? p.w0 : (W & 3) == 1 ? p.w1 : (W & 3) == 2 ? p.w2 : p.w3;
   }
 };
-// Dynamic: runtime offset, one cached call (inputs walk the stream in order).
-struct DynWords {
-  const PairCtr* pc;
-  Philox4* cache;
-  int* cached_call;
-  int off;
-  __device__ __forceinline__ uint32_t at(int k) const {
-    const int W = off + k;
-    const int c = W >> 2;
-    if (c != *cached_call) {
-      *cache = philox4x32_10(pc->qlo, pc->qhi, pc->stream, (uint32_t)c, pc->k0, pc->k1);
-      *cached_call = c;
-    }
-    const int r = W & 3;
-    return r == 0 ? cache->w0 : r == 1 ? cache->w1 : r == 2 ? cache->w2 : cache->w3;
-  }
+// Dynamic: the offsets are known at run time only. All Philox calls of the pair are made first, by ONE
+// loop, into a word buffer in local memory; an input then reads words at its offset (a load each).
+// (A call generated on demand behind every word access put a copy of the generator and a branch at each
+// of them: 400 of the 1150 instructions a W1 pair with two truncated normals took.)
+constexpr int kMaxPairWords = 4 * EBN_MAX_INPUTS;
+struct BufWords {
+  const uint32_t* words;
+  __device__ __forceinline__ uint32_t at(int k) const { return words[k]; }
   template <int K>
-  __device__ __forceinline__ uint32_t w() const { return at(K); }
+  __device__ __forceinline__ uint32_t w() const { return words[K]; }
 };
+// Philox calls per pair of a scenario: inputs consume words in order (woff), so the last input ends the
+// stream. Under a copula every random input owns the two words of its Box-Muller pair.
+__device__ __forceinline__ int pair_calls(const DevInput* sp, int d, bool copula) {
+  int tw = 0;
+  for (int j = 0; j < d; ++j) {
+    const int k = sp[j].kind;
+    const int n = copula ? (k == DK_CONST ? 0 : 2) : words_of_kind(k);
+    tw = max(tw, sp[j].woff + n);
+  }
+  return (tw + 3) >> 2;
+}
+// wbuf: 16-byte aligned, kMaxPairWords words
+__device__ __forceinline__ void pair_words(const PairCtr& pc, uint32_t* wbuf) {
+#pragma unroll 1
+  for (int c = 0; c < pc.ncalls; ++c) {
+    const Philox4 ph = philox4x32_10(pc.qlo, pc.qhi, pc.stream, (uint32_t)c, pc.k0, pc.k1);
+    *reinterpret_cast<uint4*>(wbuf + 4 * c) = make_uint4(ph.w0, ph.w1, ph.w2, ph.w3);
+  }
+}
 
 // Marsaglia & Tsang (2000) for shape >= 1 (shape < 1 boosted by u^(1/shape)),
 // the algorithm class Distributions.jl's Gamma sampler uses. Attempt t of sample
@@ -267,11 +279,11 @@ __device__ __forceinline__ void draw_pair(const DevInput& in, const WS& ws, cons
 }
 
 // Runtime (warp-uniform) dispatch on the kind; the generic, slower path.
-static __device__ __noinline__ void draw_pair_dyn(const DevInput& in, const PairCtr& pc,
-                                                  Philox4& cache, int& cached_call, uint32_t j,
-                                                  const double* tables, const FastMathSmem& sm,
-                                                  double& x0, double& x1) {
-  DynWords ws{&pc, &cache, &cached_call, in.woff};
+__device__ __forceinline__ void draw_pair_dyn_body(const DevInput& in, const PairCtr& pc,
+                                                   const uint32_t* wbuf, uint32_t j,
+                                                   const double* tables, const FastMathSmem& sm,
+                                                   double& x0, double& x1) {
+  BufWords ws{wbuf + in.woff};
   switch (in.kind) {
     case DK_CONST: draw_pair<DK_CONST>(in, ws, pc, j, tables, sm, x0, x1); break;
     case DK_UNIFORM: draw_pair<DK_UNIFORM>(in, ws, pc, j, tables, sm, x0, x1); break;
@@ -286,6 +298,13 @@ static __device__ __noinline__ void draw_pair_dyn(const DevInput& in, const Pair
     case DK_LOGNORMAL_BM32: draw_pair<DK_LOGNORMAL_BM32>(in, ws, pc, j, tables, sm, x0, x1); break;
     default: draw_pair<DK_TABLE>(in, ws, pc, j, tables, sm, x0, x1); break;
   }
+}
+// out of line: the unrolled per-input loops of the fixed-arity limit states would hold a copy per input
+static __device__ __noinline__ void draw_pair_dyn(const DevInput& in, const PairCtr& pc,
+                                                  const uint32_t* wbuf, uint32_t j,
+                                                  const double* tables, const FastMathSmem& sm,
+                                                  double& x0, double& x1) {
+  draw_pair_dyn_body(in, pc, wbuf, j, tables, sm, x0, x1);
 }
 
 // One input of a sample pair under quasi-Monte Carlo (ebn_qmc.cuh): Sobol coordinate v of the even sample
@@ -336,15 +355,14 @@ static __device__ __noinline__ void draw_pair_copula(const DevInput* plan, const
                                                      const FastMathSmem& sm, double* x0,
                                                      double* x1) {
   double e0[EBN_MAX_INPUTS], e1[EBN_MAX_INPUTS];
-  Philox4 cache;
-  int cached_call = -1;
+  __align__(16) uint32_t wbuf[kMaxPairWords];
+  pair_words(pc, wbuf);
   for (int j = 0; j < d; ++j) {
     e0[j] = 0.0;
     e1[j] = 0.0;
     if (plan[j].kind != DK_CONST) {
-      DynWords ws{&pc, &cache, &cached_call, plan[j].woff};
-      const uint32_t a = ws.at(0), b = ws.at(1);
-      box_muller_words(a, b, sm, e0[j], e1[j]);
+      const uint32_t* w = wbuf + plan[j].woff;
+      box_muller_words(w[0], w[1], sm, e0[j], e1[j]);
     }
   }
   for (int j = 0; j < d; ++j) {

@@ -6,6 +6,7 @@ Bars (BASELINE.json north_star):
   * independent-RNG estimates of pf within 3 standard errors of the oracle's;
   * counts independent of partition, grid, chunking and sharding.
 """
+import dataclasses
 import math
 
 import numpy as np
@@ -559,6 +560,33 @@ def test_hist_batch_matches_numpy_on_replayed_samples(ebn):
     # same call twice → identical moments (fixed-order reduction)
     counts2, s1b, s2b = ebn.hist_batch(job, edges)
     assert np.array_equal(counts, counts2) and np.array_equal(s1, s1b) and np.array_equal(s2, s2b)
+
+
+def test_truncated_normal_under_a_runtime_dispatched_plan(ebn):
+    """A run-time dispatched plan that draws a truncated normal reads the Phi^-1 cells from a copy in DYNAMIC
+    shared memory placed behind the histogram's edges and bins (McParams::icdf_dyn); the sampler replay reads
+    the same cells from global memory. Both must give the same bits, in count and in histogram mode, whatever
+    the number of edges (the copy's offset) is; the large edge sets need the > 48 KB opt-in."""
+    rows = [[(0, a, 0, 0, 0, -INF, INF), (1, 0.5, 1.0, 0, 0, lo, hi)]
+            for a, lo, hi in ((1.0, 0.0, INF), (2.0, -INF, 0.75), (3.0, -0.5, 2.5))]
+    prog = poly_program([[(1.0, [0]), (1.0, [1])]])
+    n = 300_001
+    job = ebn.Job(ebn._lib.LS_POLYNOMIAL, prog, ebn.make_inputs(rows), n=n, seed=11, strict=True, jit_plan=False)
+    ys = []
+    for s, (a, lo, hi) in enumerate(((1.0, 0.0, INF), (2.0, -INF, 0.75), (3.0, -0.5, 2.5))):
+        X = ebn.sample_matrix(job, s, 0, n)
+        assert X[:, 1].min() >= lo and X[:, 1].max() <= hi and np.all(X[:, 0] == a)
+        ys.append(X[:, 0] + X[:, 1])
+    cnt, _, _ = ebn.pf_batch(dataclasses.replace(job, consts=poly_program([[(-2.0, []), (1.0, [0]), (1.0, [1])]])))
+    assert ebn.last_stats()["specialised"] == 0
+    assert np.array_equal(cnt, [int(((y - 2.0) < 0).sum()) for y in ys])
+    for edges in (np.array([0.0, 1.0, 2.5, 4.0]), np.linspace(-1.0, 6.0, 7), np.linspace(-1.0, 6.0, 1024),
+                  np.linspace(-1.0, 6.0, 1025)):
+        counts, s1, s2 = ebn.hist_batch(job, edges)
+        for s, y in enumerate(ys):
+            want = np.bincount(np.searchsorted(edges, y, side="right"), minlength=len(edges) + 1)
+            assert np.array_equal(counts[s], want), (len(edges), s)
+            assert abs(s1[s] - y.sum()) < 1e-6 * n
 
 
 # ---------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-"""Runs one secondary workload a few times (for ncu): python tools/run_workload.py w1|w2|w3|hist [total samples]"""
+"""Runs one secondary workload a few times (for ncu): python tools/run_workload.py w1|w2|w3|w1t2|poly|hist [total samples]"""
 import os
 import sys
 
@@ -17,6 +17,12 @@ elif wl == "w2":
     job = W.w2_straub(n=n)
 elif wl == "w3":
     job = W.w3_straub_copula(n=n // 64)
+    job.jit_plan = False
+elif wl == "w1t2":   # W1 with C and Ck truncated: runtime-dispatched plan, Phi^-1 cells in dynamic shared memory
+    job = W.w1_vehicle(n=n // 20)
+    job.inputs[:, 3]["lo"] = 400.0
+    job.inputs[:, 4]["hi"] = 1500.0
+    job.jit_plan = False
 else:
     prog = np.array([1, 2, 1.0, 1, 0, 1.0, 1, 1])
     rows = [[(0, a, 0, 0, 0, -np.inf, np.inf), (1, 0.0, 1.0, 0, 0, -np.inf, np.inf)] for a in np.linspace(0, 3, 20)]
