@@ -355,8 +355,8 @@ struct Prepared {
   int64_t first = 0, last = 0, pair_base = 0, pairs_per_item = 0, items_per_scenario = 0;
   int world = 1;  // job world * devices
   // run-time compiled kernels (expression limit states, sampling plans without a compiled-in plan)
-  // the kernel dispatches marginal kinds at run time and some scenario draws a truncated normal: the launch
-  // carries the Phi^-1 cell table in dynamic shared memory (McParams::icdf_dyn)
+  // the kernel dispatches marginal kinds at run time, or samples under a copula, and some scenario draws a
+  // truncated normal: the launch carries the Phi^-1 cell table in dynamic shared memory (McParams::icdf_dyn)
   bool icdf_dyn = false;
   bool jit = false;
   JitSpec jit_spec;
@@ -369,6 +369,10 @@ struct Prepared {
 // first time it is seen (then cached in memory, and on disk when EBN_JIT_CACHE names a directory):
 // break-even near 1e11 samples.
 constexpr double kJitPlanMinSamples = 1e11;
+// Under a Gaussian copula the looping plan keeps scores, columns and words in local memory and runs at
+// 1.5e10 samples/s against 3.3e10 for the unrolled plan (profiles/r02_aa_workloads.txt): break-even near 5e10,
+// below BASELINE config 3's 6.4e10.
+constexpr double kJitCopulaMinSamples = 5e10;
 
 int jit_kernel_of(Prepared& P, JitRole role, JitKernel** out) {
   if (!P.jit_kernel[role]) {
@@ -504,7 +508,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
     bool plan_jit = false;
     if (!expr && !qmc && (P.plan_class == PLAN_DYNAMIC || P.plan_class == PLAN_COPULA) && uniform && !never) {
       const char* env = getenv("EBN_JIT_PLAN");  // "0": never, "1": always (experiments)
-      const bool big = (double)job->n_per_scenario * S >= kJitPlanMinSamples;
+      const bool big = (double)job->n_per_scenario * S >= (copula ? kJitCopulaMinSamples : kJitPlanMinSamples);
       if (forced || (env && env[0] == '1')) {
         std::string why;
         if (!jit_available(&why)) return fail(EBN_EJIT, "EBN_JOB_JIT_PLAN: %s", why.c_str());
@@ -527,7 +531,7 @@ int prepare(const ebn_job_t* job, int mode, Prepared& P, int ndev_override = 0) 
       if (!P.jit_spec.kinds.empty() && !copula) P.plan_class = PLAN_STATIC0;
     }
   }
-  if (P.plan_class == PLAN_DYNAMIC || (P.plan_class == PLAN_COPULA && P.jit_spec.kinds.empty())) {
+  if (P.plan_class == PLAN_DYNAMIC || P.plan_class == PLAN_COPULA) {
     for (const DevInput& in : P.plan)
       if (in.kind == DK_NORMAL_ICDF || in.kind == DK_LOGNORMAL_ICDF) { P.icdf_dyn = true; break; }
   }

@@ -283,6 +283,43 @@ __device__ __forceinline__ void normcdfinv_fast2(double p0, double p1, double& z
   }
 }
 
+// Phi(z), clamped to [2^-60, 1 - 2^-53] so that quantile functions of it stay finite — the step between the
+// correlated normal scores of a Gaussian copula and a non-normal marginal. a = min(|z|, 9.5) picks the cell
+// k = round(16 a) centred on c = k/16; the cell's degree-7 polynomial in dm = a - c gives
+// Phi(-(c + dm)) exp(c dm), and exp(-c dm) with |c dm| <= 0.3 comes from exp_fast: 4.4e-16 relative to
+// Phi(-a) over the whole range, tail included (tools/gen_fastmath_tables.py). 25 fp64 operations, no branch,
+// against ~55 plus two branches and ~60 constant moves of CUDA's normcdf (which W3's kernel calls four
+// times per sample pair). The 154-row table (12 KB at the bank-spreading 80-byte stride, see kIcdfStride)
+// is a function-scope __shared__ array: only copula kernels allocate it; they fill it with phi_init().
+__device__ __forceinline__ double2* phi_smem() {
+  __shared__ double2 s_phi[EBN_PHI_ROWS * kIcdfStride];
+  return s_phi;
+}
+__device__ __forceinline__ void phi_init(int tid, int nthreads) {
+  double2* t = phi_smem();
+  const double2* g = reinterpret_cast<const double2*>(kPhiTab);
+  for (int i = tid; i < EBN_PHI_ROWS * 4; i += nthreads) t[(i >> 2) * kIcdfStride + (i & 3)] = g[i];
+}
+__device__ __forceinline__ double phi_clamped(double z, const FastMathSmem& sm) {
+  const double a = fmin(fabs(z), EBN_PHI_AMAX);
+  const double t = fma(a, 16.0, 6755399441055744.0);   // k = round(16 a) in the low word
+  const int k = __double2loint(t);
+  const double kf = t - 6755399441055744.0;
+  const double dm = fma(kf, -0.0625, a);               // exact
+  const double2* co = phi_smem() + kIcdfStride * k;
+  const double2 c01 = co[0], c23 = co[1], c45 = co[2], c67 = co[3];
+  double p = fma(dm, c67.y, c67.x);
+  p = fma(dm, p, c45.y);
+  p = fma(dm, p, c45.x);
+  p = fma(dm, p, c23.y);
+  p = fma(dm, p, c23.x);
+  p = fma(dm, p, c01.y);
+  p = fma(dm, p, c01.x);
+  const double q = p * exp_fast((kf * dm) * -0.0625, sm);   // Phi(-|z|)
+  const double r = z < 0.0 ? q : 1.0 - q;
+  return fmin(fmax(r, 0x1p-60), 0x1.fffffffffffffp-1);
+}
+
 // sqrt(t) for t in [2^-60, 2^60]: MUFU.RSQ64H seed y ~ t^-1/2 (relative error e0 ~ 2^-20),
 // then one third-order correction: with a = t*y and e = 1 - a*y,
 //   sqrt(t) = a / sqrt(1 - e) = a * (1 + e/2 + 3 e^2/8 + O(e^3)),   truncation 5 e^3/16 < 2^-58.

@@ -86,22 +86,28 @@ struct StaticCopulaPlan {
 // Can the plan draw a truncated (inverse-CDF) normal? Only then does the kernel hold the Phi^-1 cell table.
 template <class Plan>
 __host__ __device__ constexpr bool plan_uses_icdf() {
-  if constexpr (Plan::is_static || Plan::is_static_copula) {
+  if constexpr (Plan::is_static) {
     for (int i = 0; i < Plan::n; ++i)
       if (Plan::kinds[i] == DK_NORMAL_ICDF || Plan::kinds[i] == DK_LOGNORMAL_ICDF) return true;
     return false;
   } else {
-    // kinds known at run time only: the cells are read from global memory (see icdf<>), except under
-    // quasi-Monte Carlo, where every normal goes through Phi^-1
+    // kinds known at run time only, and every copula plan (whose kernels already hold the Phi cells in static
+    // shared memory: a second static table would pass the 48 KB limit): the cells are read through the
+    // block's IcdfDyn handle (see icdf<>). Under quasi-Monte Carlo every normal goes through Phi^-1.
     return plan_is_qmc<Plan>::value;
   }
 }
 
-// Plans whose kinds are known at run time only (dynamic, looping copula): they read the Phi^-1 cells through
-// the block's IcdfDyn handle and the pair's Philox words from a buffer (pair_words).
+// Plans whose kinds are known at run time only (dynamic, looping copula): the pair's Philox words come from
+// a buffer (pair_words).
+template <class Plan>
+__host__ __device__ constexpr bool plan_is_runtime_dispatched() {
+  return !Plan::is_static && !Plan::is_static_copula && !plan_is_qmc<Plan>::value;
+}
+// Plans that read the Phi^-1 cells through the block's IcdfDyn handle: those, and the unrolled copula plans.
 template <class Plan>
 __host__ __device__ constexpr bool plan_reads_icdf_dyn() {
-  return !Plan::is_static && !Plan::is_static_copula && !plan_is_qmc<Plan>::value;
+  return !Plan::is_static && !plan_is_qmc<Plan>::value;
 }
 
 // Word offset of input J in a static plan, and the number of Philox calls a pair needs.
@@ -167,11 +173,11 @@ struct CopulaMarginals {
           x0[J] = exp_fast(fma(z0, in.b, in.a), sm);
           x1[J] = exp_fast(fma(z1, in.b, in.a), sm);
         } else if constexpr (KIND == DK_UNIFORM) {
-          x0[J] = fma(phi_clamped(z0), in.b, in.a);
-          x1[J] = fma(phi_clamped(z1), in.b, in.a);
+          x0[J] = fma(phi_clamped(z0, sm), in.b, in.a);
+          x1[J] = fma(phi_clamped(z1, sm), in.b, in.a);
         } else {
-          x0[J] = icdf<KIND, plan_uses_icdf<Plan>()>(in, tables, sm, phi_clamped(z0));
-          x1[J] = icdf<KIND, plan_uses_icdf<Plan>()>(in, tables, sm, phi_clamped(z1));
+          x0[J] = icdf<KIND, plan_uses_icdf<Plan>()>(in, tables, sm, phi_clamped(z0, sm));
+          x1[J] = icdf<KIND, plan_uses_icdf<Plan>()>(in, tables, sm, phi_clamped(z1, sm));
         }
       }
       CopulaMarginals<Plan, J + 1>::run(sp, L, tables, sm, e0, e1, x0, x1);
@@ -476,6 +482,7 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
   if constexpr (plan_reads_icdf_dyn<Plan>())
     icdf_dyn_init(tid, kThreads, p.icdf_dyn ? s_dyn + hist_dyn_bytes(MODE == 1 ? p.nedges : 0) : nullptr);
   if constexpr (plan_is_qmc<Plan>::value) sobol_init(tid, kThreads);
+  if constexpr (Plan::is_copula) phi_init(tid, kThreads);
   if (MODE == 1) {
     for (int i = tid; i < p.nedges; i += kThreads) s_edges[i] = p.edges[i];
   }
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
     pc.stream = p.stream_id ? p.stream_id[s] : (uint32_t)s;
     pc.k0 = p.k0;
     pc.k1 = p.k1;
-    pc.ncalls = plan_reads_icdf_dyn<Plan>() ? pair_calls(s_plan, p.d, Plan::is_copula) : 0;
+    pc.ncalls = plan_is_runtime_dispatched<Plan>() ? pair_calls(s_plan, p.d, Plan::is_copula) : 0;
 
     const int64_t q_begin = p.pair_base + c * p.pairs_per_item;
     int64_t q_end = q_begin + p.pairs_per_item;
@@ -630,6 +637,7 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
   if constexpr (plan_uses_icdf<Plan>()) icdf_init(threadIdx.x, kThreads);
   if constexpr (plan_reads_icdf_dyn<Plan>()) icdf_dyn_init(threadIdx.x, kThreads, nullptr);
   if constexpr (plan_is_qmc<Plan>::value) sobol_init(threadIdx.x, kThreads);
+  if constexpr (Plan::is_copula) phi_init(threadIdx.x, kThreads);
   if (threadIdx.x < p.d) s_plan[threadIdx.x] = p.plan[(int64_t)scenario * p.d + threadIdx.x];
   if (Plan::is_copula) {
     const double* L = p.chol + (p.chol_shared ? 0 : (int64_t)scenario * p.d * p.d);
@@ -640,7 +648,7 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const McParams p, int 
   pc.stream = p.stream_id ? p.stream_id[scenario] : (uint32_t)scenario;
   pc.k0 = p.k0;
   pc.k1 = p.k1;
-  pc.ncalls = plan_reads_icdf_dyn<Plan>() ? pair_calls(s_plan, p.d, Plan::is_copula) : 0;
+  pc.ncalls = plan_is_runtime_dispatched<Plan>() ? pair_calls(s_plan, p.d, Plan::is_copula) : 0;
   const int64_t q_last = (p.last + 1) >> 1;
   for (int64_t q = p.pair_base + (int64_t)blockIdx.x * kThreads + threadIdx.x; q < q_last;
        q += (int64_t)gridDim.x * kThreads) {

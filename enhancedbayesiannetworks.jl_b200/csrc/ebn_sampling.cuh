@@ -340,12 +340,6 @@ static __device__ __noinline__ void draw_pair_qmc(const DevInput& in, uint32_t v
   }
 }
 
-// Phi(z) clamped away from 0 and 1 so that the quantile functions stay finite.
-__device__ __forceinline__ double phi_clamped(double z) {
-  const double p = normcdf(z);
-  return fmin(fmax(p, 0x1p-60), 0x1.fffffffffffffp-1);
-}
-
 // Gaussian copula (UQ.jl JointDistribution + GaussianCopula): eps ~ N(0,I) by
 // Box-Muller (2 words per random input, in.woff), z = L*eps, then per marginal
 // x = a + b*z for the normal family and x = Q(Phi(z)) otherwise. L is row-major
@@ -354,16 +348,16 @@ static __device__ __noinline__ void draw_pair_copula(const DevInput* plan, const
                                                      const PairCtr& pc, const double* tables,
                                                      const FastMathSmem& sm, double* x0,
                                                      double* x1) {
-  double e0[EBN_MAX_INPUTS], e1[EBN_MAX_INPUTS];
+  double2 ee[EBN_MAX_INPUTS];   // the pair's two independent scores of input k side by side: one 16-byte load per use
   __align__(16) uint32_t wbuf[kMaxPairWords];
   pair_words(pc, wbuf);
   for (int j = 0; j < d; ++j) {
-    e0[j] = 0.0;
-    e1[j] = 0.0;
+    double a = 0.0, b = 0.0;
     if (plan[j].kind != DK_CONST) {
       const uint32_t* w = wbuf + plan[j].woff;
-      box_muller_words(w[0], w[1], sm, e0[j], e1[j]);
+      box_muller_words(w[0], w[1], sm, a, b);
     }
+    ee[j] = make_double2(a, b);
   }
   for (int j = 0; j < d; ++j) {
     const DevInput in = plan[j];
@@ -373,10 +367,12 @@ static __device__ __noinline__ void draw_pair_copula(const DevInput* plan, const
       continue;
     }
     double z0 = 0.0, z1 = 0.0;
+#pragma unroll 4
     for (int k = 0; k <= j; ++k) {
       const double l = L[j * d + k];
-      z0 = fma(l, e0[k], z0);
-      z1 = fma(l, e1[k], z1);
+      const double2 e = ee[k];
+      z0 = fma(l, e.x, z0);
+      z1 = fma(l, e.y, z1);
     }
     double a0, a1;
     switch (in.kind) {
@@ -389,28 +385,28 @@ static __device__ __noinline__ void draw_pair_copula(const DevInput* plan, const
         a1 = exp_fast(fma(z1, in.b, in.a), sm);
         break;
       case DK_UNIFORM:
-        a0 = fma(phi_clamped(z0), in.b, in.a);
-        a1 = fma(phi_clamped(z1), in.b, in.a);
+        a0 = fma(phi_clamped(z0, sm), in.b, in.a);
+        a1 = fma(phi_clamped(z1, sm), in.b, in.a);
         break;
       case DK_NORMAL_ICDF:
-        a0 = icdf<DK_NORMAL_ICDF>(in, tables, sm, phi_clamped(z0));
-        a1 = icdf<DK_NORMAL_ICDF>(in, tables, sm, phi_clamped(z1));
+        a0 = icdf<DK_NORMAL_ICDF>(in, tables, sm, phi_clamped(z0, sm));
+        a1 = icdf<DK_NORMAL_ICDF>(in, tables, sm, phi_clamped(z1, sm));
         break;
       case DK_LOGNORMAL_ICDF:
-        a0 = icdf<DK_LOGNORMAL_ICDF>(in, tables, sm, phi_clamped(z0));
-        a1 = icdf<DK_LOGNORMAL_ICDF>(in, tables, sm, phi_clamped(z1));
+        a0 = icdf<DK_LOGNORMAL_ICDF>(in, tables, sm, phi_clamped(z0, sm));
+        a1 = icdf<DK_LOGNORMAL_ICDF>(in, tables, sm, phi_clamped(z1, sm));
         break;
       case DK_GUMBEL:
-        a0 = icdf<DK_GUMBEL>(in, tables, sm, phi_clamped(z0));
-        a1 = icdf<DK_GUMBEL>(in, tables, sm, phi_clamped(z1));
+        a0 = icdf<DK_GUMBEL>(in, tables, sm, phi_clamped(z0, sm));
+        a1 = icdf<DK_GUMBEL>(in, tables, sm, phi_clamped(z1, sm));
         break;
       case DK_EXP_AFFINE:
-        a0 = icdf<DK_EXP_AFFINE>(in, tables, sm, phi_clamped(z0));
-        a1 = icdf<DK_EXP_AFFINE>(in, tables, sm, phi_clamped(z1));
+        a0 = icdf<DK_EXP_AFFINE>(in, tables, sm, phi_clamped(z0, sm));
+        a1 = icdf<DK_EXP_AFFINE>(in, tables, sm, phi_clamped(z1, sm));
         break;
       default:  // DK_TABLE (Gamma under a copula is tabulated by the caller)
-        a0 = icdf<DK_TABLE>(in, tables, sm, phi_clamped(z0));
-        a1 = icdf<DK_TABLE>(in, tables, sm, phi_clamped(z1));
+        a0 = icdf<DK_TABLE>(in, tables, sm, phi_clamped(z0, sm));
+        a1 = icdf<DK_TABLE>(in, tables, sm, phi_clamped(z1, sm));
         break;
     }
     x0[j] = a0;

@@ -651,6 +651,40 @@ def _corr_chol(d, rho, fixed=(0,)):
     return R, np.linalg.cholesky(R)
 
 
+def test_copula_normal_cdf_accuracy(ebn):
+    """The table-driven Phi between the correlated scores and a non-normal marginal (phi_clamped,
+    ebn_fastmath.cuh). A singular factor L = [[1, 0], [1, 0]] hands BOTH inputs the same score z: column 0
+    (Normal(0, 1)) shows z, column 1 (Uniform(0, 1)) shows Phi(z). Relative accuracy must hold down the lower
+    tail (quantiles of small u depend on it), absolute accuracy on the upper side."""
+    from scipy import special
+    L = ebn._lib
+    rows = [[(L.IN_NORMAL, 0.0, 1.0, 0, 0, -INF, INF), (L.IN_UNIFORM, 0.0, 1.0, 0, 0, -INF, INF)]]
+    chol = np.array([[1.0, 0.0], [1.0, 0.0]])
+    job = ebn.Job(L.LS_MIN_AFFINE, np.array([1.0, 0.0, 1.0, 1.0]), ebn.make_inputs(rows), n=4_000_000, seed=5,
+                  strict=True, corr_chol=chol, jit_plan=False)
+    X = ebn.sample_matrix(job, 0, 0, job.n)
+    z, u = X[:, 0], X[:, 1]
+    assert z.min() < -4.5 and z.max() > 4.5
+    ref = special.ndtr(z)
+    lower = z < 0
+    e_lo, e_up = np.max(np.abs(u[lower] - ref[lower]) / ref[lower]), np.max(np.abs(u[~lower] - ref[~lower]))
+    print(f"Phi cells vs scipy ndtr: {e_lo:.2e} relative below 0, {e_up:.2e} absolute above")
+    assert e_lo < 5e-14 and e_up < 3e-16          # scipy's own tail accuracy is a few 1e-15
+    import mpmath                                  # the tight bound, on the extremes and a thinned sample
+    mpmath.mp.prec = 120
+    pick = np.concatenate([np.argsort(z)[:300], np.argsort(z)[-300:], np.arange(0, z.size, 4001)])
+    exact = np.array([float(mpmath.ncdf(mpmath.mpf(float(v)))) for v in z[pick]])
+    rel = np.abs(u[pick] - exact) / np.minimum(exact, 1.0)
+    low = z[pick] < 0
+    print(f"Phi cells vs mpmath: {rel[low].max():.2e} relative below 0, {np.abs(u[pick] - exact)[~low].max():.2e} absolute above")
+    assert rel[low].max() < 1.5e-15 and np.abs(u[pick] - exact)[~low].max() < 2.5e-16
+    # scores far outside what Box-Muller can reach still give finite, clamped, monotone values: a large sigma
+    # column scaled through the factor (row 2 = 40 * eps would not be a correlation factor, so use the marginal)
+    assert np.all((u > 0) & (u < 1))
+    if L.jit_available():   # the unrolled copula plan compiled at run time shares the routine: same bits
+        assert np.array_equal(ebn.sample_matrix(dataclasses.replace(job, jit_plan=True), 0, 0, 200_000), X[:200_000])
+
+
 def test_gaussian_copula_sampler_and_count(ebn):
     from scipy import stats
     d = len(COPULA_ROW)
