@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,11 @@ namespace {
 using namespace ebn;
 
 thread_local std::string g_err;
+// Every entry point that touches the library's state (devices, staging buffers, communicators, statistics)
+// takes this lock: calls from several host threads are serialised, never interleaved. Recursive because
+// entry points call one another (ebn_init -> ebn_shutdown, ebn_sample_matrix -> ebn_sample_matrix_ex).
+std::recursive_mutex g_api_mu;
+#define API_LOCK std::lock_guard<std::recursive_mutex> api_lock_(g_api_mu)
 
 int fail(int code, const char* fmt, ...) {
   char buf[1024];
@@ -876,6 +882,7 @@ int ebn_device_count(void) {
 }
 
 int ebn_shutdown(void) {
+  API_LOCK;
   if (g.rank_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g.rank_comm);
   g.rank_comm = nullptr;
   g.rank = 0;
@@ -927,6 +934,7 @@ static int init_devices(const std::vector<int>& ids) {
 }
 
 int ebn_init(const int* devices, int ndev) {
+  API_LOCK;
   if (g.ready || !g.devs.empty()) ebn_shutdown();
   if (ndev < 0 || (ndev > 0 && !devices)) return fail(EBN_EINVAL, "bad device list");
   const int avail = ebn_device_count();
@@ -951,6 +959,7 @@ int ebn_init(const int* devices, int ndev) {
 }
 
 int ebn_set_stream(void* cuda_stream) {
+  API_LOCK;
   int rc = require_ready();
   if (rc) return rc;
   if (g.devs.size() != 1) return fail(EBN_ESTATE, "ebn_set_stream needs single-device mode");
@@ -959,6 +968,7 @@ int ebn_set_stream(void* cuda_stream) {
 }
 
 int ebn_nccl_unique_id(void* id128) {
+  API_LOCK;
   if (!id128) return fail(EBN_EINVAL, "id128 is NULL");
   int rc = nccl_load();
   if (rc) return rc;
@@ -967,6 +977,7 @@ int ebn_nccl_unique_id(void* id128) {
 }
 
 int ebn_comm_init_rank(const void* id128, int rank, int world) {
+  API_LOCK;
   int rc = require_ready();
   if (rc) return rc;
   if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(EBN_EINVAL, "bad rank/world");
@@ -983,6 +994,7 @@ int ebn_comm_init_rank(const void* id128, int rank, int world) {
 }
 
 int ebn_comm_destroy(void) {
+  API_LOCK;
   if (g.rank_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g.rank_comm);
   g.rank_comm = nullptr;
   g.rank = 0;
@@ -1081,6 +1093,7 @@ int run_batch_split(const ebn_job_t* job, int mode, const double* edges, int ned
 }
 
 int ebn_pf_batch(const ebn_job_t* job, int64_t* fail_count, double* pf, double* var) {
+  API_LOCK;
   if (!fail_count) return fail(EBN_EINVAL, "fail_count is NULL");
   int rc = run_batch_split(job, 0, nullptr, 0, fail_count, nullptr, nullptr);
   if (rc) return rc;
@@ -1095,6 +1108,7 @@ int ebn_pf_batch(const ebn_job_t* job, int64_t* fail_count, double* pf, double* 
 
 int ebn_hist_batch(const ebn_job_t* job, const double* edges, int nedges, int64_t* counts,
                    double* sum, double* sumsq) {
+  API_LOCK;
   if (!counts) return fail(EBN_EINVAL, "counts is NULL");
   if (!edges || nedges < 1 || nedges > EBN_MAX_EDGES)
     return fail(EBN_EINVAL, "need 1..%d histogram edges", EBN_MAX_EDGES);
@@ -1107,6 +1121,7 @@ int ebn_hist_batch(const ebn_job_t* job, const double* edges, int nedges, int64_
 
 int ebn_eval_matrix(int limit_state, const double* consts, int n_consts, const double* X, int64_t n,
                     int d, int64_t ld, int strict, int64_t* fail_count, double* g_out) {
+  API_LOCK;
   int rc = require_ready();
   if (rc) return rc;
   if (!fail_count) return fail(EBN_EINVAL, "fail_count is NULL");
@@ -1171,6 +1186,7 @@ int ebn_eval_matrix(int limit_state, const double* consts, int n_consts, const d
 
 int ebn_sample_matrix_ex(const ebn_job_t* job, int scenario, int64_t first, int64_t n, int ncols,
                          double* X, double* g_out) {
+  API_LOCK;
   int rc = require_ready();
   if (rc) return rc;
   if (!X) return fail(EBN_EINVAL, "X is NULL");
@@ -1213,11 +1229,13 @@ int ebn_sample_matrix_ex(const ebn_job_t* job, int scenario, int64_t first, int6
 
 int ebn_sample_matrix(const ebn_job_t* job, int scenario, int64_t first, int64_t n, double* X,
                       double* g_out) {
+  API_LOCK;
   if (!job) return fail(EBN_EINVAL, "job is NULL");
   return ebn_sample_matrix_ex(job, scenario, first, n, job->n_inputs, X, g_out);
 }
 
 int ebn_peak_fp64(double seconds, double* dfma_per_s) {
+  API_LOCK;
   int rc = require_ready();
   if (rc) return rc;
   if (!dfma_per_s) return fail(EBN_EINVAL, "dfma_per_s is NULL");
@@ -1291,6 +1309,7 @@ int64_t ebn_expression_source(const double* consts, int n_consts, int d, char* b
 }
 
 int ebn_jit_compile(const ebn_job_t* job, int role, int64_t* cubin_bytes) {
+  API_LOCK;
   if (role < 0 || role > 2) return fail(EBN_EINVAL, "role must be 0 (count), 1 (histogram) or 2 (replay)");
   if (!job) return fail(EBN_EINVAL, "job is NULL");
   ebn_job_t rewritten;
@@ -1316,6 +1335,7 @@ int ebn_jit_compile(const ebn_job_t* job, int role, int64_t* cubin_bytes) {
 }
 
 int ebn_last_stats(ebn_stats_t* out) {
+  API_LOCK;
   if (!out) return fail(EBN_EINVAL, "out is NULL");
   *out = g.stats;
   return EBN_OK;

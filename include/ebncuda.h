@@ -17,7 +17,10 @@
  *     implicit padding (checked by static_asserts in the implementation).
  *   - No CPU fallback: without a CUDA device every compute call fails with
  *     EBN_ENODEV.
- *   - Calls are blocking and not re-entrant; one call in flight per process.
+ *   - Calls are blocking. The library is safe to call from several host threads: entry points that touch
+ *     its state take one process-wide lock, so concurrent calls are serialised (one batch in flight per
+ *     process; a batch already uses every device the library was initialised with). ebn_last_error() is
+ *     per thread; ebn_last_stats() describes the most recent call of any thread.
  */
 #ifndef EBNCUDA_H
 #define EBNCUDA_H

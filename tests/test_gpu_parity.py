@@ -589,6 +589,38 @@ def test_truncated_normal_under_a_runtime_dispatched_plan(ebn):
             assert abs(s1[s] - y.sum()) < 1e-6 * n
 
 
+def test_concurrent_callers_are_serialised(ebn):
+    """ctypes releases the GIL around a C call, so these threads really are inside libebncuda at the same time.
+    Each must get the result of ITS job (shared staging buffers would mix them up without the library's lock),
+    and an error on one thread must not show up in another thread's ebn_last_error()."""
+    import threading
+    from ebn_b200 import workloads as W
+    jobs = [W.w1_vehicle(n=200_000 + 1000 * i, seed=100 + i) for i in range(4)] + \
+           [W.w2_straub(n=150_000 + 777 * i, seed=200 + i) for i in range(4)]
+    want = [ebn.pf_batch(j)[0].copy() for j in jobs]
+    got, errs = [None] * len(jobs), []
+
+    def worker(i):
+        try:
+            for _ in range(5):
+                got[i] = ebn.pf_batch(jobs[i])[0].copy()
+                assert np.array_equal(got[i], want[i]), i
+            if i == 0:
+                bad = W.w1_vehicle(n=0)
+                with pytest.raises(ebn.EbnError, match="EBN_EINVAL"):
+                    ebn.pf_batch(bad)
+        except BaseException as e:  # noqa: BLE001 - reported by the main thread
+            errs.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    assert all(np.array_equal(g, w) for g, w in zip(got, want))
+
+
 # ---------------------------------------------------------------------------
 # 7. error behaviour: never a fallback, always a code + message
 # ---------------------------------------------------------------------------
