@@ -263,8 +263,10 @@ def _evaluate_node(net, node, collect_samples=True):
 
 def _is_eliminable(net, node) -> bool:
     """evaluate_net.jl:42-56: reversing the node's edges must not create a cycle."""
-    if isinstance(node, (str, int)):
-        node = net.node(node) if isinstance(node, str) else net.nodes[node]
+    if isinstance(node, int):   # a topology index (evaluate_net.jl:57-61; 0-based here), not a position in net.nodes
+        node = next(name for name, i in net.topology_dict.items() if i == node)
+    if isinstance(node, str):
+        node = net.node(node)
     if not isinstance(node, (ContinuousNode, ContinuousFunctionalNode)):
         raise TypeError(f"node elimination algorithm is for continuous nodes and {node.name} is discrete")
     idx = net.topology_dict[node.name]

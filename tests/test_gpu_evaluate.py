@@ -364,6 +364,57 @@ def test_evaluate_net_chain_and_error_messages(E):
         E.evaluate(net)
 
 
+def test_no_ancestors_case(E):
+    """evaluate_net.jl:218-244 ("No Ancestors case"): a functional node whose only parent is a continuous root has
+    one (empty) scenario; the evaluated node is a root of the reduced net."""
+    for kind in ("continuous", "discrete"):
+        b = _cont_root(E, "B", E.Normal())
+        model = E.Model(E.Expression("df.B .+ 1"), "C")
+        sim = E.MonteCarlo(100_000)
+        node = (E.ContinuousFunctionalNode("C", [model], sim) if kind == "continuous"
+                else E.DiscreteFunctionalNode("C", [model], E.Expression("2 .- df.C"), sim))
+        net = E.EnhancedBayesianNetwork([b, node])
+        E.add_child(net, b, node)
+        E.order(net)
+        E.evaluate(net)
+        last = net.nodes[-1]
+        assert isinstance(last, E.ContinuousNode if kind == "continuous" else E.DiscreteNode) and last.isroot()
+        if kind == "discrete":   # P(2 - (B + 1) < 0) = P(B > 1)
+            assert last.cpt.column("C") == ["C_fail", "C_safe"]
+            assert abs(last.cpt[("C", "C_fail")] - ndtr(-1.0)) < 0.005
+        else:                    # C = B + 1 ~ N(1, 1)
+            d = last.cpt[()]
+            assert abs(d.mean() - 1.0) < 0.02 and abs(d.cdf(1.0) - 0.5) < 0.01
+
+
+def test_imprecise_node_with_discretization_messages(E):
+    """evaluate_net.jl:246-281: a p-box parent that is discretised stops being imprecise, so a DoubleLoop on its
+    child is refused; an interval parent under a precise simulation is refused the other way round."""
+    a = _root(E, "A", ["y", "n"], [0.5, 0.5])
+    cpt = E.ContinuousConditionalProbabilityTable(["A"], kind="pbox")
+    cpt[("A", "y")] = E.UnamedProbabilityBox(E.Normal, (E.Interval(-0.5, 0.5, "μ"), E.Interval(1, 2, "σ")))
+    cpt[("A", "n")] = E.UnamedProbabilityBox(E.Normal, (E.Interval(1, 2, "μ"), E.Interval(1, 2, "σ")))
+    b = E.ContinuousNode("B", cpt, E.ApproximatedDiscretization([-1, 0, 1], 2))
+    model = E.Model(E.Expression("df.B .+ 1"), "C")
+    f = E.DiscreteFunctionalNode("C", [model], E.Expression("2 .- df.C"), E.DoubleLoop(E.MonteCarlo(100_000)))
+    net = E.EnhancedBayesianNetwork([a, b, f])
+    E.add_child(net, a, b)
+    E.add_child(net, b, f)
+    E.order(net)
+    with pytest.raises(ValueError, match="node C has as simulation .*DoubleLoop.*but its imprecise parents will be "
+                                         "discretized and approximated with Uniform and Exponential assumption, therefore "
+                                         "are no longer imprecise. A prices simulation technique must be selected!"):
+        E.evaluate(net)
+    b = _cont_root(E, "B", (-1, 1), kind="interval")
+    f = E.DiscreteFunctionalNode("C", [model], E.Expression("2 .- df.C"), E.MonteCarlo(100_000))
+    net = E.EnhancedBayesianNetwork([b, f])
+    E.add_child(net, b, f)
+    E.order(net)
+    with pytest.raises(ValueError, match=r"node C has .* as simulation technique, but have \['B'\] as imprecise parent/s. "
+                                         "DoubleLoop or RandomSlicing technique must be employeed instead"):
+        E.evaluate(net)
+
+
 def straub_net(E, n, as_text=False, strict=False):
     """demo/straub_example.jl in the current API (test/inference/variableselimination.jl:133-206).
     as_text: the model closures typed in as their own text (Expression) instead of catalogue entries."""

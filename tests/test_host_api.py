@@ -181,6 +181,32 @@ def test_network_graph_helpers_and_add_child_rules():
         E.order(lonely)
 
 
+def test_is_eliminable_auxiliary_functions():
+    """test/networks/ebn/evaluate/evaluate_net.jl:283-335 ("Auxiliary functions"): the eight-node net with three
+    continuous functional nodes between the roots and two discrete functional nodes."""
+    x = _root("x", ["x1", "x2"], [0.3, 0.7], {"x1": [E.Parameter(0.5, "x")], "x2": [E.Parameter(0.7, "x")]})
+    y = _cont_root("y", E.Normal())
+    z = _root("z", ["z1", "z2"], [0.3, 0.7], {"z1": [E.Parameter(0.5, "z")], "z2": [E.Parameter(0.7, "z")]})
+    sim = E.MonteCarlo(300)
+    cf1 = E.ContinuousFunctionalNode("cf1", [E.Model(E.Expression("df.x .^ 2 .- 0.7 .+ df.y"), "c1")], sim)
+    cf2 = E.ContinuousFunctionalNode("cf2", [E.Model(E.Expression("df.z .^ 2 .- 0.7 .+ df.y"), "c2")], sim)
+    fd1 = E.DiscreteFunctionalNode("fd1", [E.Model(E.Expression("df.c1 .* 0.5 .+ df.c2"), "final1")],
+                                   E.Expression("df.final1 .- 0.5"), sim,
+                                   {"fail_fd1": [E.Parameter(1, "fd1")], "safe_fd1": [E.Parameter(0, "fd1")]})
+    c3 = E.ContinuousFunctionalNode("c3", [E.Model(E.Expression("df.c2 .* 0.5"), "c3")], sim)
+    fd = E.DiscreteFunctionalNode("fd", [E.Model(E.Expression("0.5 .+ df.c3"), "tot")], E.Expression("0.5 .- df.tot"), sim)
+    net = E.EnhancedBayesianNetwork([x, y, z, cf1, cf2, fd1, c3, fd])
+    for par, ch in ((x, cf1), (y, cf1), (y, cf2), (z, cf2), (cf1, fd1), (cf2, fd1), (cf2, c3), (fd1, fd), (c3, fd)):
+        E.add_child(net, par, ch)
+    E.order(net)
+    with pytest.raises(TypeError, match="node elimination algorithm is for continuous nodes and x is discrete"):
+        ev._is_eliminable(net, x)
+    assert ev._is_eliminable(net, cf2) is False
+    assert ev._is_eliminable(net, y) is True
+    assert ev._is_eliminable(net, net.topology_dict["y"]) is True      # by topology index (the reference's `2`)
+    assert ev._is_eliminable(net, "y") is True
+
+
 def test_scenario_enumeration_order_through_continuous_parents():
     """evaluate_node.jl:52-56 + networks_common.jl:37-45: direct discrete parents first, then the
     ancestors reached through continuous parents; combinations sorted lexicographically."""
