@@ -140,10 +140,31 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Julia+UQ.jl (not runnable here); this is the oracle's structural C port",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def keep_stdout_for_the_result():
+    """The contract is ONE JSON line on stdout. Libraries write there too (with NCCL_DEBUG set in the box's
+    environment NCCL prints its version banner on fd 1): keep a private copy of stdout for the result and point
+    fd 1 at stderr for everything else."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_FD if _RESULT_FD is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    keep_stdout_for_the_result()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -413,7 +434,7 @@ def main():
                 "sample": f"W1, 20 scenarios x {args.cpu_n} samples ({dt:.1f} s) — a bounded sample of the GPU arm's "
                           f"20 x {n_per_scenario:.3g} (throughput metric: samples/s does not depend on n); oracle structural "
                           "C port of the reference path (Julia/UQ.jl cannot run here)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     if dist is not None:
         ebn_b200._lib.comm_destroy()
