@@ -376,7 +376,7 @@ struct Prepared {
 // break-even near 1e11 samples.
 constexpr double kJitPlanMinSamples = 1e11;
 // Under a Gaussian copula the looping plan keeps scores, columns and words in local memory and runs at
-// 1.5e10 samples/s against 3.3e10 for the unrolled plan (profiles/r02_aa_workloads.txt): break-even near 5e10,
+// 1.5e10 samples/s against 3.3e10 for the unrolled plan (profiles/r02_af_workloads.txt): break-even near 5e10,
 // below BASELINE config 3's 6.4e10.
 constexpr double kJitCopulaMinSamples = 5e10;
 

@@ -39,6 +39,248 @@ std::string lit(double v) {
   return fmt("__longlong_as_double(0x%016llxLL)", (unsigned long long)b);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Sign-only failure predicate for fast mode.
+//
+// The failure count needs `g < 0` (NaN counts as safe, like `sum(g .< 0)` in the reference), not g. The
+// hand-written vehicle functor exploits that (VehicleSuspension::fails); this does the same for formulas:
+//   min(a, b) < 0        <=>  (a < 0 or b < 0) and neither is NaN            (Julia's minimum propagates NaN)
+//   a - b < 0            <=>  a < b
+//   c sqrt(z) < k        <=>  k/c > 0 and 0 <= z < (k/c)^2                   (c a positive literal, k constant)
+//   k < c sqrt(z)        <=>  z >= 0 and (k/c < 0 or z > (k/c)^2)
+//   P/Q compared with 0  <=>  the signs of P and Q, where a value built from + - * / over other values is
+//                             carried as a fraction (numerator, denominator) and never divided out
+//   sqrt(z), log(z) NaN  <=>  not (z >= 0)
+// Everything else falls back to the value eval() computes. Comparisons of fractions use the SIGNS of
+// numerator and denominator, not their product (no spurious under/overflow). What changes with respect to
+// `eval(x) < 0`: roundings (so: ties only), and the measure-zero events a division by exactly zero produces
+// (inf - inf, 0 * inf), which this predicate does not see as NaN. Strict mode never uses it.
+// ---------------------------------------------------------------------------------------------------
+struct Node {
+  int op;
+  double arg;            // literal value / column / powi exponent
+  int a = -1, b = -1;    // operand nodes (select and lt are opaque to the rewriter)
+  bool inv = false, leaf = false;
+  std::string name;      // how eval() refers to the value (an invariant that is not a leaf: how setup() does)
+  std::string slot;      // such an invariant's name inside eval()/fails(), once one was asked for
+};
+
+struct FailsGen {
+  std::vector<Node>& nodes;
+  std::string& setup;
+  int& nh;
+  std::string code;   // statements appended after eval()'s body
+  int nt = 0;
+  std::vector<int> div_memo;
+  std::vector<std::string> neg_memo, nan_memo;
+
+  FailsGen(std::vector<Node>& n, std::string& s, int& h) : nodes(n), setup(s), nh(h) {
+    div_memo.assign(n.size(), -1);
+    neg_memo.assign(n.size(), "");
+    nan_memo.assign(n.size(), "");
+  }
+  // value of a node inside fails()
+  std::string val(int id) {
+    Node& n = nodes[id];
+    if (!n.inv || n.leaf) return n.name;
+    if (n.slot.empty()) {
+      setup += fmt("    c.h[%d] = ", nh) + n.name + ";\n";
+      n.slot = fmt("c.h[%d]", nh++);
+    }
+    return n.slot;
+  }
+  // an invariant computed in setup() from an expression over setup-scope names
+  std::string inv_slot(const std::string& expr) {
+    setup += fmt("    c.h[%d] = ", nh) + expr + ";\n";
+    return fmt("c.h[%d]", nh++);
+  }
+  std::string setup_name(int id) { return nodes[id].name; }   // invariants only
+  std::string dtmp(const std::string& e) {
+    const std::string v = fmt("r%d", nt++);
+    code += "    const double " + v + " = " + e + ";\n";
+    return v;
+  }
+  std::string btmp(const std::string& e) {
+    if (e == "false" || e == "true") return e;
+    const std::string v = fmt("p%d", nt++);
+    code += "    const bool " + v + " = " + e + ";\n";
+    return v;
+  }
+  static std::string b_or(const std::string& x, const std::string& y) {
+    if (x == "true" || y == "true") return "true";
+    if (x == "false") return y;
+    if (y == "false") return x;
+    return "(" + x + " | " + y + ")";
+  }
+  static std::string b_and(const std::string& x, const std::string& y) {
+    if (x == "false" || y == "false") return "false";
+    if (x == "true") return y;
+    if (y == "true") return x;
+    return "(" + x + " & " + y + ")";
+  }
+  static std::string b_not(const std::string& x) {
+    if (x == "false") return "true";
+    if (x == "true") return "false";
+    return "!" + x;
+  }
+  bool arith(int op) const {
+    return op == EBN_OP_ADD || op == EBN_OP_SUB || op == EBN_OP_MUL || op == EBN_OP_DIV || op == EBN_OP_NEG;
+  }
+  // does a per-sample division sit under this node, reachable through + - * / neg ^2 only?
+  bool has_div(int id) {
+    if (div_memo[id] >= 0) return div_memo[id] != 0;
+    const Node& n = nodes[id];
+    bool r = false;
+    if (!n.inv) {
+      if (n.op == EBN_OP_DIV) r = !nodes[n.b].inv || has_div(n.a);
+      else if (arith(n.op)) r = has_div(n.a) || (n.b >= 0 && has_div(n.b));
+      else if (n.op == EBN_OP_POWI && (int)n.arg == 2) r = has_div(n.a);
+    }
+    div_memo[id] = r ? 1 : 0;
+    return r;
+  }
+  struct Frac { std::string num, den; };   // den empty: 1
+  std::string mul(const std::string& x, const std::string& y) {
+    if (x.empty()) return y;
+    if (y.empty()) return x;
+    return dtmp(x + " * " + y);
+  }
+  std::vector<Frac> frac_memo;
+  std::vector<char> frac_done;
+  Frac frac(int id) {
+    if (frac_done.empty()) {
+      frac_memo.resize(nodes.size());
+      frac_done.assign(nodes.size(), 0);
+    }
+    if (!frac_done[id]) {
+      frac_memo[id] = frac_build(id);
+      frac_done[id] = 1;
+    }
+    return frac_memo[id];
+  }
+  Frac frac_build(int id) {
+    const Node& n = nodes[id];
+    if (!has_div(id)) return {val(id), ""};
+    switch (n.op) {
+      case EBN_OP_DIV: {
+        const Frac a = frac(n.a), b = frac(n.b);
+        return {mul(a.num, b.den), mul(a.den, b.num)};
+      }
+      case EBN_OP_MUL: {
+        const Frac a = frac(n.a), b = frac(n.b);
+        return {mul(a.num, b.num), mul(a.den, b.den)};
+      }
+      case EBN_OP_NEG: {
+        const Frac a = frac(n.a);
+        return {dtmp("-" + a.num), a.den};
+      }
+      case EBN_OP_POWI: {
+        const Frac a = frac(n.a);
+        return {mul(a.num, a.num), mul(a.den, a.den)};
+      }
+      default: {   // add, sub
+        const Frac a = frac(n.a), b = frac(n.b);
+        const char* pm = n.op == EBN_OP_ADD ? " + " : " - ";
+        if (a.den.empty()) return {dtmp(mul(a.num, b.den) + pm + b.num), b.den};
+        if (b.den.empty()) return {dtmp(a.num + pm + mul(b.num, a.den)), a.den};
+        return {dtmp(mul(a.num, b.den) + pm + mul(b.num, a.den)), mul(a.den, b.den)};
+      }
+    }
+  }
+  // sign tests of a fraction (false when either part is NaN, or the denominator is zero)
+  std::string lt0(const Frac& f) {
+    if (f.den.empty()) return btmp("(" + f.num + " < 0.0)");
+    return btmp("(((" + f.num + " < 0.0) & (" + f.den + " > 0.0)) | ((" + f.num + " > 0.0) & (" + f.den + " < 0.0)))");
+  }
+  std::string gt0(const Frac& f) {
+    if (f.den.empty()) return btmp("(" + f.num + " > 0.0)");
+    return btmp("(((" + f.num + " > 0.0) & (" + f.den + " > 0.0)) | ((" + f.num + " < 0.0) & (" + f.den + " < 0.0)))");
+  }
+  std::string ge0(const Frac& f) {
+    if (f.den.empty()) return btmp("(" + f.num + " >= 0.0)");
+    return btmp("(((" + f.num + " >= 0.0) & (" + f.den + " > 0.0)) | ((" + f.num + " <= 0.0) & (" + f.den + " < 0.0)))");
+  }
+  // node minus a name, as a fraction
+  Frac minus(int id, const std::string& name) {
+    const Frac z = frac(id);
+    if (z.den.empty()) return {dtmp(z.num + " - " + name), ""};
+    return {dtmp(z.num + " - " + mul(name, z.den)), z.den};
+  }
+  // c * sqrt(z) with c a positive literal (or absent): true and (z, c) on a match
+  bool scaled_sqrt(int id, int* z, double* c) {
+    const Node& n = nodes[id];
+    if (n.op == EBN_OP_SQRT) { *z = n.a, *c = 1.0; return true; }
+    if (n.op != EBN_OP_MUL) return false;
+    for (int swap = 0; swap < 2; ++swap) {
+      const Node& k = nodes[swap ? n.b : n.a];
+      const Node& r = nodes[swap ? n.a : n.b];
+      if (k.op == EBN_OP_CONST && k.arg > 0.0 && std::isfinite(k.arg) && r.op == EBN_OP_SQRT) {
+        *z = r.a, *c = k.arg;
+        return true;
+      }
+    }
+    return false;
+  }
+  // value(a) < value(b), false if either is NaN
+  std::string less(int a, int b) {
+    int z;
+    double c;
+    if (nodes[b].inv && !nodes[a].inv && scaled_sqrt(a, &z, &c)) {          // c sqrt(z) < k
+      const std::string t = inv_slot(setup_name(b) + " / " + lit(c));
+      const std::string t2 = inv_slot(t + " * " + t);
+      return btmp(b_and(b_and("(" + t + " > 0.0)", ge0(frac(z))), lt0(minus(z, t2))));
+    }
+    if (nodes[a].inv && !nodes[b].inv && scaled_sqrt(b, &z, &c)) {          // k < c sqrt(z)
+      const std::string t = inv_slot(setup_name(a) + " / " + lit(c));
+      const std::string t2 = inv_slot(t + " * " + t);
+      return btmp(b_and(ge0(frac(z)), b_or("(" + t + " < 0.0)", gt0(minus(z, t2)))));
+    }
+    if (has_div(a) || has_div(b)) {
+      const Frac x = frac(a), y = frac(b);
+      Frac diff;
+      if (x.den.empty()) diff = {dtmp(mul(x.num, y.den) + " - " + y.num), y.den};
+      else if (y.den.empty()) diff = {dtmp(x.num + " - " + mul(y.num, x.den)), x.den};
+      else diff = {dtmp(mul(x.num, y.den) + " - " + mul(y.num, x.den)), mul(x.den, y.den)};
+      return lt0(diff);
+    }
+    return btmp("(" + val(a) + " < " + val(b) + ")");
+  }
+  // is the value NaN? ("false" when it cannot be, up to the caveats in the header comment)
+  std::string nanp(int id) {
+    if (!nan_memo[id].empty()) return nan_memo[id];
+    const Node& n = nodes[id];
+    std::string r;
+    if (n.op == EBN_OP_INPUT || n.op == EBN_OP_LT || (n.op == EBN_OP_CONST && n.arg == n.arg)) r = "false";
+    else if (n.inv) r = btmp("(" + val(id) + " != " + val(id) + ")");   // a constant sub-expression may well be NaN
+    else if (n.op == EBN_OP_SQRT || n.op == EBN_OP_LOG) r = btmp(b_not(ge0(frac(n.a))));
+    else if (arith(n.op) || n.op == EBN_OP_MIN || n.op == EBN_OP_MAX)
+      r = btmp(b_or(nanp(n.a), n.b >= 0 ? nanp(n.b) : "false"));
+    else if (n.op == EBN_OP_ABS || n.op == EBN_OP_EXP || (n.op == EBN_OP_POWI && (int)n.arg >= 0)) r = nanp(n.a);
+    else r = btmp("(" + val(id) + " != " + val(id) + ")");
+    return nan_memo[id] = r;
+  }
+  // value < 0, false if it is NaN
+  std::string negp(int id) {
+    if (!neg_memo[id].empty()) return neg_memo[id];
+    const Node& n = nodes[id];
+    std::string r;
+    if (n.inv) r = btmp("(" + val(id) + " < 0.0)");
+    else if (n.op == EBN_OP_MIN)
+      r = btmp(b_and(b_or(negp(n.a), negp(n.b)), b_not(b_or(nanp(n.a), nanp(n.b)))));
+    else if (n.op == EBN_OP_MAX) r = btmp(b_and(negp(n.a), negp(n.b)));
+    else if (n.op == EBN_OP_SUB) r = less(n.a, n.b);
+    else if (has_div(id)) r = lt0(frac(id));
+    else r = btmp("(" + val(id) + " < 0.0)");
+    return neg_memo[id] = r;
+  }
+};
+
+std::string expr_fails_codegen(std::vector<Node>& nodes, int root, int /*d*/, std::string& setup, int& nh) {
+  FailsGen g(nodes, setup, nh);
+  const std::string pred = g.negp(root);
+  return g.code + "    return " + pred + ";\n";
+}
+
 }  // namespace
 
 std::string expr_check(const double* consts, int n_consts, int d, ExprInfo* info) {
@@ -111,10 +353,19 @@ std::string expr_codegen(const double* consts, int n_consts, int d) {
     std::string name;  // how eval() refers to it (for an invariant: how setup() refers to it)
     bool inv;          // depends on runtime constants / literals only
     bool leaf;         // a constant or literal itself: usable in eval() directly
+    int node = -1;     // this value in the expression graph (below)
   };
+  std::vector<Node> nodes;     // the expression graph behind the SSA names (read by expr_fails_codegen)
+  std::vector<int> col_node;   // node of every stored column
   std::string setup, eval;
   std::vector<Val> st;
   int nv = 0, ns = 0, nh = 0, col = d;
+  auto new_node = [&](int op, double arg, int a, int b, const Val& v) {
+    Node n;
+    n.op = op, n.arg = arg, n.a = a, n.b = b, n.inv = v.inv, n.leaf = v.leaf, n.name = v.name;
+    nodes.push_back(n);
+    return (int)nodes.size() - 1;
+  };
   // name of `v` as seen from eval(): invariants computed in setup() get a context slot
   auto in_eval = [&](const Val& v) {
     if (!v.inv || v.leaf) return v.name;
@@ -220,14 +471,22 @@ std::string expr_codegen(const double* consts, int n_consts, int d) {
         break;
       case EBN_OP_STORE:
         eval += fmt("    x[%d] = ", col++) + in_eval(a) + ";\n";
+        col_node.push_back(a.node);
         break;
+    }
+    if (op != EBN_OP_STORE) {
+      Val& top = st.back();
+      if (op == EBN_OP_INPUT && (int)arg >= d) top.node = col_node[(int)arg - d];   // a stored column IS its value
+      else top.node = new_node(op, arg, kShape[op].pops >= 1 && kShape[op].pops <= 2 ? a.node : -1,
+                               kShape[op].pops == 2 ? b.node : -1, top);
     }
   }
   const std::string result = in_eval(st.back());
+  const std::string fails_body = expr_fails_codegen(nodes, st.back().node, d, setup, nh);
   std::string s;
   s += "namespace ebn {\ntemplate <class Ops>\nstruct JitExpr {\n";
   s += "  static constexpr int ID = EBN_LS_EXPRESSION;\n";
-  s += "  static constexpr bool HAS_FAILS = false;\n";
+  s += "  static constexpr bool HAS_FAILS = !Ops::strict;   // sign-only predicate for the failure count in fast mode\n";
   s += "  static constexpr int MIN_BLOCKS = EBN_BLOCKS_FOR_WARPS(16);\n";
   s += fmt("  static constexpr int D = %d;\n", d);
   s += fmt("  static constexpr int XCAP = %d;\n", d + I.n_store);
@@ -241,7 +500,13 @@ std::string expr_codegen(const double* consts, int n_consts, int d) {
   s += "  }\n";
   s += "  __device__ __forceinline__ static double eval(const Ctx& c, double* x) {\n";
   s += eval;
-  s += "    return " + result + ";\n  }\n};\n}  // namespace ebn\n";
+  s += "    return " + result + ";\n  }\n";
+  // g < 0 without the divisions and square roots whose VALUE does not matter for the sign (fast mode only; the
+  // values eval() computes that the predicate does not read are dead code here and the compiler drops them)
+  s += "  __device__ __forceinline__ static bool fails(const Ctx& c, double* x) {\n";
+  s += eval;
+  s += fails_body;
+  s += "  }\n};\n}  // namespace ebn\n";
   return s;
 }
 

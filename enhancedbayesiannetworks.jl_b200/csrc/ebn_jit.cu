@@ -362,7 +362,15 @@ bool jit_get(const JitSpec& spec, JitRole role, JitKernel** out, bool* compiled,
   if (compiled) *compiled = false;
   Unit u;
   if (!make_unit(spec, role, &u, err)) return false;
-  const std::string key = build_defines_key() + "\n" + u.name_expr + "\n" + u.source;
+  // everything that determines the machine code: the embedded headers (a cubin cached on disk by an older
+  // library must not be picked up by a newer one — McParams and the stream layout live there), the build's
+  // -D options, the kernel instantiation and the generated functor
+  static const std::string headers_key = [] {
+    uint64_t h = 1469598103934665603ull;
+    for (const auto& src : kJitSources) h = fnv1a(src.text, fnv1a(src.name, h));
+    return fmt("headers:%016llx", (unsigned long long)h);
+  }();
+  const std::string key = headers_key + "\n" + build_defines_key() + "\n" + u.name_expr + "\n" + u.source;
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
     *out = it->second.get();
