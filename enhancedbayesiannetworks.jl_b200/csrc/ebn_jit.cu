@@ -263,6 +263,12 @@ const char* const kBuildDefines[] = {
 #ifdef EBN_BM_OPT
     "-DEBN_BM_OPT=" EBN_STR(EBN_BM_OPT),
 #endif
+#ifdef EBN_GENERIC_WARPS
+    "-DEBN_GENERIC_WARPS=" EBN_STR(EBN_GENERIC_WARPS),
+#endif
+#ifdef EBN_PIPE_MAX_INPUTS
+    "-DEBN_PIPE_MAX_INPUTS=" EBN_STR(EBN_PIPE_MAX_INPUTS),
+#endif
 #ifdef EBN_PHILOX_ROUNDS
     "-DEBN_PHILOX_ROUNDS=" EBN_STR(EBN_PHILOX_ROUNDS),
 #endif

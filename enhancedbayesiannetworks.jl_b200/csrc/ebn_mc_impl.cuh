@@ -29,17 +29,6 @@ constexpr int kPairUnroll = EBN_UNROLL;  // pairs per trip of the static count l
 #define EBN_PINGPONG 0
 #endif
 
-// Runtime-dispatched plans under a variadic limit state: marginal transforms inlined into the input loop (1)
-// or one out-of-line call per input (0).
-#ifndef EBN_DYN_INLINE
-#define EBN_DYN_INLINE 1
-#endif
-// The same input loop for fixed-arity limit states under a run-time dispatched plan (1), or their unrolled
-// per-input calls (0).
-#ifndef EBN_DYN_LOOP_ALL
-#define EBN_DYN_LOOP_ALL 1
-#endif
-
 // Compile-time sampling plans ------------------------------------------------
 template <int... K>
 struct StaticPlan {
@@ -225,16 +214,12 @@ __device__ __forceinline__ void draw_inputs(const DevInput* sp, const double* sL
     __align__(16) uint32_t wbuf[kMaxPairWords];
     pair_words(pc, wbuf);
     if constexpr (LOOPED) {
-      // variadic limit states index x[] at run time anyway: a real loop over the d inputs keeps the columns
-      // in local memory instead of a 16-way predicated unroll with compare trees for every x[k]
+      // the fused kernels: ONE loop over the d inputs with the marginal transforms inlined into it and the
+      // columns in local memory (measured, profiles/r02_tune_generic.txt: against a 16-way predicated unroll
+      // with an out-of-line call per input and, for the variadic limit states that index x[] at run time,
+      // compare trees behind every x[k]); the replay kernels keep the unrolled form
 #pragma unroll 1
-      for (int j = 0; j < d; ++j) {
-#if EBN_DYN_INLINE
-        draw_pair_dyn_body(sp[j], pc, wbuf, (uint32_t)j, tables, sm, x0[j], x1[j]);
-#else
-        draw_pair_dyn(sp[j], pc, wbuf, (uint32_t)j, tables, sm, x0[j], x1[j]);
-#endif
-      }
+      for (int j = 0; j < d; ++j) draw_pair_dyn_body(sp[j], pc, wbuf, (uint32_t)j, tables, sm, x0[j], x1[j]);
     } else {
 #pragma unroll
       for (int j = 0; j < XCAP; ++j) {
@@ -542,9 +527,9 @@ __global__ void __launch_bounds__(kThreads, LS::MIN_BLOCKS) mc_kernel(const McPa
       double x0[XCAP], x1[XCAP];
       if constexpr (plan_is_qmc<Plan>::value) {
         qmc_move(qs, (uint32_t)(q << 1), qmc_nd);
-        draw_inputs_qmc<XCAP, (LS::D < 0 || EBN_DYN_LOOP_ALL)>(s_plan, p.d, qs, p.tables, s_fm, x0, x1);
+        draw_inputs_qmc<XCAP, true>(s_plan, p.d, qs, p.tables, s_fm, x0, x1);
       } else {
-        draw_inputs<Plan, XCAP, (LS::D < 0 || EBN_DYN_LOOP_ALL)>(plan_ptr, s_chol, p.d, pc, p.tables, s_fm, x0, x1);
+        draw_inputs<Plan, XCAP, true>(plan_ptr, s_chol, p.d, pc, p.tables, s_fm, x0, x1);
       }
       const int64_t i0 = q << 1;
       const bool v0 = i0 >= p.first;           // i0 < last holds by construction
