@@ -9,7 +9,7 @@ namespace ebn {
 // PLAN_STATIC0 + i: the i-th compile-time plan of the limit state (or, for a run-time compiled kernel,
 // the job's own kinds)
 enum PlanClass { PLAN_DYNAMIC = 0, PLAN_COPULA = 1, PLAN_STATIC0 = 2, PLAN_QMC = 100 };  // PLAN_STATIC0 + i, i < kMaxStaticPlans
-constexpr int kMaxStaticPlans = 8;
+constexpr int kMaxStaticPlans = 12;
 
 #ifndef __CUDACC_RTC__
 int threads_per_block();

@@ -151,13 +151,15 @@ def test_run_time_compilation_without_a_device():
     trunc = W.w1_vehicle(n=1000)
     trunc.inputs[:, 3]["lo"] = 400.0
     assert L.jit_compile(trunc, 0) == 0                   # C truncated: a compiled-in plan (discretised root)
-    trunc.inputs[:, 4]["hi"] = 1500.0                     # C and Ck truncated: no compiled-in plan
+    trunc.inputs[:, 4]["hi"] = 1500.0                     # C and Ck truncated: compiled in as well (all 8 combinations are)
+    assert L.jit_compile(trunc, 0) == 0
+    trunc.inputs[:, 5]["kind"], trunc.inputs[:, 5]["p"] = L.IN_LOGNORMAL, (4.0, 0.18, 0, 0)   # K log-normal: no compiled-in plan
     assert L.jit_compile(trunc, 0) == 0                   # small job: runtime-dispatched plan
     trunc.jit_plan = True
     assert L.jit_compile(trunc, 0) > 10_000               # forced: StaticPlan compiled on demand
     big = W.w1_vehicle(n=10**10)
     big.inputs[:, 3]["lo"] = 400.0
-    big.inputs[:, 4]["hi"] = 1500.0
+    big.inputs[:, 5]["kind"], big.inputs[:, 5]["p"] = L.IN_LOGNORMAL, (4.0, 0.18, 0, 0)
     assert L.jit_compile(big, 0) > 10_000                 # large job: automatic
     big.jit_plan = False
     assert L.jit_compile(big, 0) == 0
@@ -220,7 +222,7 @@ def test_kernel_cache_on_disk_is_opt_in(tmp_path):
         pytest.skip("libnvrtc not loadable here")
     code = ("import sys; sys.path.insert(0, %r)\n"
             "from ebn_b200 import workloads as W, _lib as L\n"
-            "j = W.w1_vehicle(n=1000); j.inputs[:, 5]['hi'] = 90.0; j.inputs[:, 4]['lo'] = 1400.0; j.jit_plan = True\n"
+            "j = W.w1_vehicle(n=1000); j.inputs[:, 5]['kind'] = L.IN_LOGNORMAL; j.inputs[:, 5]['p'] = (4.0, 0.18, 0, 0); j.jit_plan = True\n"
             "assert L.jit_compile(j, 0) > 10000; print(L.last_stats()['jit_compiles'])\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, EBN_JIT_CACHE=str(tmp_path))
     runs = [subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True) for _ in range(2)]

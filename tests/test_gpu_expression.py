@@ -133,12 +133,13 @@ def test_expression_reference_toy_models(ebn):
 
 
 def test_jit_sampling_plan_matches_dynamic_plan(ebn):
-    """A job no compiled-in plan covers (truncated normals): the run-time compiled StaticPlan gives
+    """A job no compiled-in plan covers (C truncated, K log-normal): the run-time compiled StaticPlan gives
     exactly the counts and streams of the runtime-dispatched plan."""
     from ebn_b200 import workloads as W
     n = 300_001
     base = W.w1_vehicle(n=n, strict=True)
     base.inputs[:, 3]["lo"] = 400.0       # C truncated at 400 → inverse-CDF kind
+    base.inputs[:, 5]["kind"], base.inputs[:, 5]["p"] = ebn._lib.IN_LOGNORMAL, (4.0, 0.18, 0, 0)
     base.inputs[:, 5]["hi"] = 80.0
     dyn = ebn.Job(base.limit_state, base.consts, base.inputs, n=n, seed=base.seed, strict=True, jit_plan=False)
     jit = ebn.Job(base.limit_state, base.consts, base.inputs, n=n, seed=base.seed, strict=True, jit_plan=True)

@@ -28,7 +28,8 @@ def test_single_process_multi_device_counts_match_one_gpu():
     ebase = ebn_b200.pf_batch(ejob)[0]
     tjob = W.w1_vehicle(n=1_000_001)
     tjob.inputs[:, 3]["lo"] = 400.0
-    tjob.inputs[:, 4]["hi"] = 1500.0     # C and Ck truncated: no compiled-in plan, compiled at run time
+    tjob.inputs[:, 5]["kind"], tjob.inputs[:, 5]["p"] = ebn_b200._lib.IN_LOGNORMAL, (4.0, 0.18, 0, 0)
+    # C truncated, K log-normal: no compiled-in plan, compiled at run time
     tjob.jit_plan = True
     tbase = ebn_b200.pf_batch(tjob)[0]
     for devs in ([0, 1], list(range(ndev))):

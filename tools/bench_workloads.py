@@ -48,11 +48,14 @@ run("W4 vehicle, V fixed: 4 states x 25 outer-loop values", W.w4_vehicle_fixed_v
 j = W.w1_vehicle(n=10**8)
 j.inputs[:, 3]["lo"] = 400.0   # truncated normal: inverse CDF on the truncation window
 run("W1 with C truncated at 400 (compiled-in plan P,P,U,I,N,N)", j)
-j.inputs[:, 4]["hi"] = 1500.0  # two truncated normals: no compiled-in plan
+j.inputs[:, 4]["hi"] = 1500.0  # two truncated normals: compiled in too (all eight combinations of C, Ck, K are)
+run("W1 with C and Ck truncated (compiled-in plan P,P,U,I,I,N)", j)
+j.inputs[:, 4]["hi"] = np.inf
+j.inputs[:, 5]["kind"], j.inputs[:, 5]["p"] = ebn_b200._lib.IN_LOGNORMAL, (4.0, 0.18, 0, 0)  # K log-normal: no compiled-in plan
 j.jit_plan = False
-run("W1 with C and Ck truncated (runtime-dispatched plan)", j)
+run("W1 with C truncated and K log-normal (runtime-dispatched plan)", j)
 j.jit_plan = True
-run("W1 with C and Ck truncated (plan compiled at run time)", j)
+run("W1 with C truncated and K log-normal (plan compiled at run time)", j)
 j = W.w1_vehicle(n=10**8)
 for col, (lo, hi) in ((3, (400.0, 460.0)), (4, (1440.0, 1500.0)), (5, (30.0, 80.0))):
     j.inputs[:, col]["lo"], j.inputs[:, col]["hi"] = lo, hi

@@ -18,10 +18,10 @@ elif wl == "w2":
 elif wl == "w3":
     job = W.w3_straub_copula(n=n // 64)
     job.jit_plan = False
-elif wl == "w1t2":   # W1 with C and Ck truncated: runtime-dispatched plan, Phi^-1 cells in dynamic shared memory
+elif wl == "w1t2":   # W1 with C truncated and K log-normal: runtime-dispatched plan, Phi^-1 cells in dynamic shared memory
     job = W.w1_vehicle(n=n // 20)
     job.inputs[:, 3]["lo"] = 400.0
-    job.inputs[:, 4]["hi"] = 1500.0
+    job.inputs[:, 5]["kind"], job.inputs[:, 5]["p"] = ebn_b200._lib.IN_LOGNORMAL, (4.0, 0.18, 0, 0)
     job.jit_plan = False
 else:
     prog = np.array([1, 2, 1.0, 1, 0, 1.0, 1, 1])

@@ -2,7 +2,7 @@
 subprocess per library: EBN_LIB selects it) and prints samples/s. GPU box only.
     python tools/tune_bench.py [w1|w2|w3|poly|hist|w1t2] [n]
 (poly / hist: A + B through the interpreted polynomial functor and the runtime-dispatched plan, count and
-histogram mode; w1t2: W1 with C and Ck truncated, runtime-dispatched plan; w3: copula, looping plan)"""
+histogram mode; w1t2: W1 with C truncated and K log-normal, runtime-dispatched plan; w3: copula, looping plan)"""
 import glob
 import os
 import subprocess
@@ -29,7 +29,7 @@ elif wl == 'w3':
 elif wl == 'w1t2':
     job = W.w1_vehicle(n=n)
     job.inputs[:, 3]["lo"] = 400.0
-    job.inputs[:, 4]["hi"] = 1500.0
+    job.inputs[:, 5]["kind"], job.inputs[:, 5]["p"] = ebn_b200._lib.IN_LOGNORMAL, (4.0, 0.18, 0, 0)
     job.jit_plan = False
 else:
     prog = np.array([1, 2, 1.0, 1, 0, 1.0, 1, 1])
