@@ -25,6 +25,8 @@ import pytest
 
 from oracle import cpu as ocpu
 
+import formula_fuzz
+
 pytestmark = pytest.mark.gpu
 
 INF = math.inf
@@ -163,26 +165,6 @@ def test_compiled_formula_fast_mode_on_adversarial_marginals(ebn):
     print(f"adversarial JitExpr<FastOps>: {rows} samples, {100 * nan_frac:.1f}% NaN g, {len(bad)} tie flips")
 
 
-def _rational(rng, atoms, depth):
-    if depth == 0 or rng.random() < 0.25:
-        return str(rng.choice(atoms)) if rng.random() < 0.8 else repr(round(float(rng.normal(0, 2)), 2))
-    a, b = _rational(rng, atoms, depth - 1), _rational(rng, atoms, depth - 1)
-    return f"({a} {rng.choice(['+', '-', '*', '/', '/'])} {b})"
-
-
-def _mechanism(rng, atoms):
-    """Shapes the sign-only predicate generator rewrites (ebn_expr.cu: FailsGen): scaled square roots against
-    constants on either side, differences of fractions, squares of fractions, and things it must leave alone."""
-    R = lambda: _rational(rng, atoms, int(rng.integers(1, 4)))  # noqa: E731
-    c = repr(round(float(rng.uniform(0.2, 3.0)), 2))
-    k = str(rng.choice(["k0", "k1", repr(round(float(rng.normal(0.5, 1.0)), 2))]))
-    return str(rng.choice([
-        f"{c} * sqrt({R()}) - {k}", f"sqrt({R()}) * {c} - {k}", f"{k} - {c} * sqrt({R()})", f"sqrt({R()}) - {k}",
-        f"{k} - {R()}", f"{R()} - {k}", f"1 - ({R()} / {R()}) * {R()}", f"({R()})^2 - {k}", f"-({R()})",
-        f"sqrt({R()}) - sqrt(abs({R()}))", f"log({R()}) - {k}", f"abs({R()}) - {c}", f"{R()} + {k}",
-        f"min({R()}, {R()}) - {k}", f"exp({R()} / 8) - {c}"]))
-
-
 def test_sign_only_predicates_generated_for_formulas(ebn):
     """JitExpr<FastOps>::fails, the predicate the generator derives for `g < 0` in fast mode (no division, no
     square root where only the sign matters): 40 random chains of mechanisms under min / max over inputs that
@@ -199,23 +181,7 @@ def test_sign_only_predicates_generated_for_formulas(ebn):
     names = ["x0", "x1", "x2", "x3"]
     total_nan, total_fail, total = 0.0, 0, 0
     for trial in range(40):
-        consts = {"k0": float(rng.normal(0.5, 1.0)), "k1": float(rng.uniform(0.1, 2.0))}
-        models, avail = [], list(names)
-        for t in range(int(rng.integers(1, 4))):
-            models.append((f"m{t}", _mechanism(rng, avail)))
-            avail.append(f"m{t}")
-        stored = [f"m{t}" for t in range(len(models))]
-        extra = [_mechanism(rng, avail) for _ in range(int(rng.integers(0, 3)))]
-        shape = int(rng.integers(0, 4))
-        terms = stored + extra
-        if shape == 0 or len(terms) == 1:
-            perf = "minimum([" + ", ".join(terms) + "])"
-        elif shape == 1:
-            perf = "max(" + ", ".join(terms[:2]) + ")"
-        elif shape == 2:
-            perf = "min(" + terms[0] + ", max(" + ", ".join(terms[1:3] if len(terms) > 2 else terms[:2]) + "))"
-        else:
-            perf = terms[-1]
+        models, perf, consts = formula_fuzz.chain(rng, names)
         prog = expr.compile_program(names, models, perf, consts)
         n = 150_001
         job = L.Job(L.LS_EXPRESSION, prog.consts, L.make_inputs(rows), n, seed=0x51C0 + trial, strict=False)
