@@ -52,9 +52,13 @@ std::string lit(double v) {
 //                             carried as a fraction (numerator, denominator) and never divided out
 //   sqrt(z), log(z) NaN  <=>  not (z >= 0)
 // Everything else falls back to the value eval() computes. Comparisons of fractions use the SIGNS of
-// numerator and denominator, not their product (no spurious under/overflow). What changes with respect to
-// `eval(x) < 0`: roundings (so: ties only), and the measure-zero events a division by exactly zero produces
-// (inf - inf, 0 * inf), which this predicate does not see as NaN. Strict mode never uses it.
+// numerator and denominator, not their product (no spurious under/overflow). A divisor that is exactly zero or
+// infinite (a Parameter state of 0, a self-cancelling formula, a literal -0.0 — never a continuous random input)
+// makes IEEE arithmetic produce infinities, signed zeros and, from them, NaNs that no sign rule sees: every
+// divisor the rewriting looked through is tested, and a sample with such a one takes eval()'s own arithmetic
+// instead (a cold block; the condition is the same for all samples of a scenario in practice). What is left different from `eval(x) < 0`:
+// roundings (ties), and products of numerators / denominators that overflow where the quotient would not
+// (magnitudes beyond 1e150). Strict mode never uses the predicate.
 // ---------------------------------------------------------------------------------------------------
 struct Node {
   int op;
@@ -147,6 +151,7 @@ struct FailsGen {
   }
   std::vector<Frac> frac_memo;
   std::vector<char> frac_done;
+  std::vector<std::string> zero_tests;   // "this divisor is exactly zero", one per division looked through
   Frac frac(int id) {
     if (frac_done.empty()) {
       frac_memo.resize(nodes.size());
@@ -164,6 +169,8 @@ struct FailsGen {
     switch (n.op) {
       case EBN_OP_DIV: {
         const Frac a = frac(n.a), b = frac(n.b);
+        // the divisor is b.num / b.den: zero or not finite (a literal -0.0 under another division does that) -> cold block
+        zero_tests.push_back("!((fabs(" + b.num + ") > 0.0) & (fabs(" + b.num + ") < __longlong_as_double(0x7ff0000000000000LL)))");
         return {mul(a.num, b.den), mul(a.den, b.num)};
       }
       case EBN_OP_MUL: {
@@ -275,10 +282,20 @@ struct FailsGen {
   }
 };
 
-std::string expr_fails_codegen(std::vector<Node>& nodes, int root, int /*d*/, std::string& setup, int& nh) {
+// eval_body / eval_result: eval()'s statements and the name of g, pasted into the cold block.
+std::string expr_fails_codegen(std::vector<Node>& nodes, int root, int /*d*/, std::string& setup, int& nh,
+                               const std::string& eval_body, const std::string& eval_result) {
   FailsGen g(nodes, setup, nh);
   const std::string pred = g.negp(root);
-  return g.code + "    return " + pred + ";\n";
+  std::string s = g.code;
+  if (!g.zero_tests.empty()) {
+    std::string z;
+    for (const std::string& t : g.zero_tests) z += (z.empty() ? "" : " | ") + t;
+    s += "    if (" + z + ") {   // a divisor is zero or not finite: IEEE infinities, signed zeros and NaNs as eval() produces them\n";
+    s += eval_body;
+    s += "    return " + eval_result + " < 0.0;\n    }\n";
+  }
+  return s + "    return " + pred + ";\n";
 }
 
 }  // namespace
@@ -482,7 +499,7 @@ std::string expr_codegen(const double* consts, int n_consts, int d) {
     }
   }
   const std::string result = in_eval(st.back());
-  const std::string fails_body = expr_fails_codegen(nodes, st.back().node, d, setup, nh);
+  const std::string fails_body = expr_fails_codegen(nodes, st.back().node, d, setup, nh, eval, result);
   std::string s;
   s += "namespace ebn {\ntemplate <class Ops>\nstruct JitExpr {\n";
   s += "  static constexpr int ID = EBN_LS_EXPRESSION;\n";

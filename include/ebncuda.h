@@ -116,8 +116,9 @@ enum {
  * negative number gives NaN (a safe sample) where Julia would throw a DomainError.
  * Outside strict mode the failure count of ebn_pf_batch may come from a sign-only predicate derived from
  * the program (min -> or, square roots against constants -> comparisons of the radicand, quotients ->
- * comparisons of numerator and denominator): it agrees with `g < 0` except on ties and on samples where a
- * divisor is exactly zero. ebn_hist_batch, ebn_eval_matrix and ebn_sample_matrix_ex always evaluate g.
+ * comparisons of numerator and denominator; a sample with a zero or infinite divisor is evaluated in full):
+ * it agrees with `g < 0` except on ties, as long as products of the formula's numerators and denominators
+ * stay finite. ebn_hist_batch, ebn_eval_matrix and ebn_sample_matrix_ex always evaluate g.
  * exp, log, sin, cos and pow are within 1-2 ulp of Julia's, not bit-identical. min / max of two
  * zeros of opposite sign return the first operand (Julia orders -0.0 below 0.0); `g < 0` cannot tell.
  */

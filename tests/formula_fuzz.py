@@ -20,7 +20,21 @@ def mechanism(rng, atoms):
         f"{c} * sqrt({R()}) - {k}", f"sqrt({R()}) * {c} - {k}", f"{k} - {c} * sqrt({R()})", f"sqrt({R()}) - {k}",
         f"{k} - {R()}", f"{R()} - {k}", f"1 - ({R()} / {R()}) * {R()}", f"({R()})^2 - {k}", f"-({R()})",
         f"sqrt({R()}) - sqrt(abs({R()}))", f"log({R()}) - {k}", f"abs({R()}) - {c}", f"{R()} + {k}",
-        f"min({R()}, {R()}) - {k}", f"exp({R()} / 8) - {c}"]))
+        f"min({R()}, {R()}) - {k}", f"exp(min(max({R()}, -40), 40) / 8) - {c}"]))
+
+
+def unstable_rows(eval_g, X, g):
+    """Rows on which the SIGN of g is not a property of the formula but of its rounding: g changes sign (or turns
+    NaN, or stops being NaN) when every input moves by a relative 1e-12 — catastrophic cancellation between huge
+    intermediates, a square-root argument that is a rounding error away from zero. A predicate evaluated in
+    another order of operations may legitimately disagree there, exactly as it may on a tie.
+    eval_g(X) -> g is the reference evaluator."""
+    import numpy as np
+    bad = np.zeros(len(X), dtype=bool)
+    for eps in (1e-12, -1e-12):
+        gp = eval_g(X * (1.0 + eps))
+        bad |= (np.isnan(gp) != np.isnan(g)) | ((gp < 0) != (g < 0))
+    return bad
 
 
 def chain(rng, names):

@@ -23,6 +23,9 @@ import math
 import numpy as np
 import pytest
 
+# EBN_FUZZ_SEED=k shifts the seeds of the randomised tests (extra fuzzing runs); the default is what CI runs
+FUZZ_SEED = int(__import__("os").environ.get("EBN_FUZZ_SEED", "0"))
+
 from oracle import cpu as ocpu
 
 import formula_fuzz
@@ -175,7 +178,7 @@ def test_sign_only_predicates_generated_for_formulas(ebn):
     from ebn_b200 import expr
     if not L.jit_available():
         pytest.skip("no NVRTC on this machine")
-    rng = np.random.default_rng(77001)
+    rng = np.random.default_rng(77001 + FUZZ_SEED)
     rows = [[(L.IN_NORMAL, 0.3, 1.5, 0, 0, -INF, INF), (L.IN_NORMAL, -0.2, 1.0, 0, 0, -INF, INF),
              (L.IN_UNIFORM, -1.0, 2.0, 0, 0, -INF, INF), (L.IN_NORMAL, 1.0, 0.7, 0, 0, -INF, INF)]]
     names = ["x0", "x1", "x2", "x3"]
@@ -186,7 +189,12 @@ def test_sign_only_predicates_generated_for_formulas(ebn):
         n = 150_001
         job = L.Job(L.LS_EXPRESSION, prog.consts, L.make_inputs(rows), n, seed=0x51C0 + trial, strict=False)
         _, nan_frac, bad = _explain_by_ties(ebn, job, ocpu.LS_EXPRESSION, prog.consts, window=1 << 15)
-        not_ties = [(s, r, g) for (s, r, g) in bad if not abs(g) < 1e-9]
+        not_ties = []
+        for (s, r, g) in bad:   # only samples whose sign is a matter of rounding may differ (ties, cancellation)
+            x = ebn.sample_matrix(job, s, job.sample_offset + r, 1)
+            oracle_g = lambda Y: ocpu.eval_matrix(ocpu.LS_EXPRESSION, prog.consts, Y, want_g=True)[1]  # noqa: E731
+            if not formula_fuzz.unstable_rows(oracle_g, x, np.array([g]))[0]:
+                not_ties.append((s, r, g))
         assert not not_ties, (trial, models, perf, not_ties[:5])
         total_nan += nan_frac
         total_fail += int(ebn.pf_batch(job)[0][0])

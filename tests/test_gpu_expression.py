@@ -6,6 +6,9 @@ import math
 import numpy as np
 import pytest
 
+# EBN_FUZZ_SEED=k shifts the seeds of the randomised tests (extra fuzzing runs); the default is what CI runs
+FUZZ_SEED = int(__import__("os").environ.get("EBN_FUZZ_SEED", "0"))
+
 from oracle import cpu as ocpu
 from oracle import replay
 
@@ -230,7 +233,7 @@ def test_random_formulas_against_the_oracle(ebn):
     selections) evaluated in strict mode equal the C oracle's stack machine bit for bit, NaNs included;
     the fast mode stays within rounding."""
     from ebn_b200 import expr
-    rng = np.random.default_rng(20261020)
+    rng = np.random.default_rng(20261020 + FUZZ_SEED)
     X = rng.normal(0.5, 2.0, (20_000, 4))
     X[:3] = [[0.0, -0.0, 1.0, 2.0], [1e300, 1e-300, -1e300, 3.0], [np.nan, 1.0, 2.0, np.inf]]
     for trial in range(25):
@@ -263,7 +266,7 @@ def test_random_jobs_end_to_end(ebn):
     import dataclasses
     from ebn_b200 import expr
     from test_gpu_parity import _random_marginal
-    rng = np.random.default_rng(9001)
+    rng = np.random.default_rng(9001 + FUZZ_SEED)
     for trial in range(8):
         d = int(rng.integers(2, 6))
         base = [_random_marginal(rng) for _ in range(d)]

@@ -12,6 +12,9 @@ import math
 import numpy as np
 import pytest
 
+# EBN_FUZZ_SEED=k shifts the seeds of the randomised tests (extra fuzzing runs); the default is what CI runs
+FUZZ_SEED = int(__import__("os").environ.get("EBN_FUZZ_SEED", "0"))
+
 from oracle import cpu as ocpu
 from oracle import replay
 
@@ -247,7 +250,7 @@ def test_random_marginal_rows_against_the_twin(ebn):
     """Randomised version of the twin comparison: 16 random scenario rows (kinds, parameters,
     truncation windows), drawn by the runtime-dispatched plan, equal the NumPy twin to 5e-12; and for
     each row the plan compiled at run time for exactly these kinds draws the same bits."""
-    rng = np.random.default_rng(777)
+    rng = np.random.default_rng(777 + FUZZ_SEED)
     seed = 0x1234_5678_9ABC_DEF0
     for trial in range(16):
         d = int(rng.integers(2, 9))
@@ -765,7 +768,7 @@ def test_random_copulas_against_the_twin(ebn):
     """Random correlation matrices over random marginal rows (Gamma excluded: it must be tabulated
     under a copula): the looping copula plan equals the NumPy twin, and the plan unrolled at run time
     draws the same bits."""
-    rng = np.random.default_rng(4242)
+    rng = np.random.default_rng(4242 + FUZZ_SEED)
     for trial in range(6):
         d = int(rng.integers(2, 7))
         row = []
