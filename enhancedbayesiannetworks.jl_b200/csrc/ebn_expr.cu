@@ -69,6 +69,14 @@ struct Node {
   std::string slot;      // such an invariant's name inside eval()/fails(), once one was asked for
 };
 
+// Truth values are opaque ints. Written with bools (bitwise or logical operators alike), the predicate was
+// miscompiled twice — found by re-seeding the fuzz test (tests/test_gpu_adversarial.py), never on the host:
+//   * nvcc 12.9 folds  a = (k != k), b = (k != k), c = b; ((p | q) & !c) ... ((r | s) & !(c | a))  down to one
+//     comparison, the p | q terms vanish, even at -O0 (a minimal kernel reproduces it);
+//   * NVRTC 12.9, inside the fused kernel only, drops the `|| p24` term of  ((p29 || p24) && !(p3 || p8))  nested
+//     under another `&& !(...)` with repeated NaN flags (the same text in a small kernel compiles correctly).
+// Both are boolean re-derivations by the optimiser. Every temporary therefore goes through an empty asm that makes
+// it opaque: the logic is evaluated exactly as written (one SETP + SEL per comparison, LOP3 for the rest).
 struct FailsGen {
   std::vector<Node>& nodes;
   std::string& setup;
@@ -104,28 +112,37 @@ struct FailsGen {
     code += "    const double " + v + " = " + e + ";\n";
     return v;
   }
-  std::string btmp(const std::string& e) {
-    if (e == "false" || e == "true") return e;
+  // A truth value is an int (0 / 1) that the optimiser cannot see through: the empty asm makes every temporary
+  // opaque, so the compiler evaluates the logic as written instead of re-deriving it with boolean algebra (see the
+  // note above FailsGen). cmp(): one comparison; btmp(): a combination of temporaries.
+  std::string cmp(const std::string& e) {
     const std::string v = fmt("p%d", nt++);
-    code += "    const bool " + v + " = " + e + ";\n";
+    code += "    int " + v + " = (" + e + ") ? 1 : 0;\n    asm volatile(\"\" : \"+r\"(" + v + "));\n";
+    return v;
+  }
+  std::string btmp(const std::string& e) {
+    if (e == "0" || e == "1") return e;
+    if (e.size() > 1 && e[0] == 'p' && e.find_first_not_of("0123456789", 1) == std::string::npos) return e;   // already a temporary
+    const std::string v = fmt("p%d", nt++);
+    code += "    int " + v + " = " + e + ";\n    asm volatile(\"\" : \"+r\"(" + v + "));\n";
     return v;
   }
   static std::string b_or(const std::string& x, const std::string& y) {
-    if (x == "true" || y == "true") return "true";
-    if (x == "false") return y;
-    if (y == "false") return x;
+    if (x == "1" || y == "1") return "1";
+    if (x == "0") return y;
+    if (y == "0") return x;
     return "(" + x + " | " + y + ")";
   }
   static std::string b_and(const std::string& x, const std::string& y) {
-    if (x == "false" || y == "false") return "false";
-    if (x == "true") return y;
-    if (y == "true") return x;
+    if (x == "0" || y == "0") return "0";
+    if (x == "1") return y;
+    if (y == "1") return x;
     return "(" + x + " & " + y + ")";
   }
   static std::string b_not(const std::string& x) {
-    if (x == "false") return "true";
-    if (x == "true") return "false";
-    return "!" + x;
+    if (x == "0") return "1";
+    if (x == "1") return "0";
+    return "(" + x + " ^ 1)";
   }
   bool arith(int op) const {
     return op == EBN_OP_ADD || op == EBN_OP_SUB || op == EBN_OP_MUL || op == EBN_OP_DIV || op == EBN_OP_NEG;
@@ -170,7 +187,7 @@ struct FailsGen {
       case EBN_OP_DIV: {
         const Frac a = frac(n.a), b = frac(n.b);
         // the divisor is b.num / b.den: zero or not finite (a literal -0.0 under another division does that) -> cold block
-        zero_tests.push_back("!((fabs(" + b.num + ") > 0.0) & (fabs(" + b.num + ") < __longlong_as_double(0x7ff0000000000000LL)))");
+        zero_tests.push_back(b_not(b_and(cmp("fabs(" + b.num + ") > 0.0"), cmp("fabs(" + b.num + ") < __longlong_as_double(0x7ff0000000000000LL)"))));
         return {mul(a.num, b.den), mul(a.den, b.num)};
       }
       case EBN_OP_MUL: {
@@ -195,18 +212,15 @@ struct FailsGen {
     }
   }
   // sign tests of a fraction (false when either part is NaN, or the denominator is zero)
-  std::string lt0(const Frac& f) {
-    if (f.den.empty()) return btmp("(" + f.num + " < 0.0)");
-    return btmp("(((" + f.num + " < 0.0) & (" + f.den + " > 0.0)) | ((" + f.num + " > 0.0) & (" + f.den + " < 0.0)))");
+  std::string signs(const Frac& f, const char* n_pos_side, const char* n_neg_side) {
+    // (N <op1> 0 and D > 0) or (N <op2> 0 and D < 0)
+    const std::string a = cmp(f.num + " " + n_pos_side + " 0.0"), b = cmp(f.den + " > 0.0");
+    const std::string c = cmp(f.num + " " + n_neg_side + " 0.0"), d = cmp(f.den + " < 0.0");
+    return btmp(b_or(b_and(a, b), b_and(c, d)));
   }
-  std::string gt0(const Frac& f) {
-    if (f.den.empty()) return btmp("(" + f.num + " > 0.0)");
-    return btmp("(((" + f.num + " > 0.0) & (" + f.den + " > 0.0)) | ((" + f.num + " < 0.0) & (" + f.den + " < 0.0)))");
-  }
-  std::string ge0(const Frac& f) {
-    if (f.den.empty()) return btmp("(" + f.num + " >= 0.0)");
-    return btmp("(((" + f.num + " >= 0.0) & (" + f.den + " > 0.0)) | ((" + f.num + " <= 0.0) & (" + f.den + " < 0.0)))");
-  }
+  std::string lt0(const Frac& f) { return f.den.empty() ? cmp(f.num + " < 0.0") : signs(f, "<", ">"); }
+  std::string gt0(const Frac& f) { return f.den.empty() ? cmp(f.num + " > 0.0") : signs(f, ">", "<"); }
+  std::string ge0(const Frac& f) { return f.den.empty() ? cmp(f.num + " >= 0.0") : signs(f, ">=", "<="); }
   // node minus a name, as a fraction
   Frac minus(int id, const std::string& name) {
     const Frac z = frac(id);
@@ -235,12 +249,12 @@ struct FailsGen {
     if (nodes[b].inv && !nodes[a].inv && scaled_sqrt(a, &z, &c)) {          // c sqrt(z) < k
       const std::string t = inv_slot(setup_name(b) + " / " + lit(c));
       const std::string t2 = inv_slot(t + " * " + t);
-      return btmp(b_and(b_and("(" + t + " > 0.0)", ge0(frac(z))), lt0(minus(z, t2))));
+      return btmp(b_and(b_and(cmp(t + " > 0.0"), ge0(frac(z))), lt0(minus(z, t2))));
     }
     if (nodes[a].inv && !nodes[b].inv && scaled_sqrt(b, &z, &c)) {          // k < c sqrt(z)
       const std::string t = inv_slot(setup_name(a) + " / " + lit(c));
       const std::string t2 = inv_slot(t + " * " + t);
-      return btmp(b_and(ge0(frac(z)), b_or("(" + t + " < 0.0)", gt0(minus(z, t2)))));
+      return btmp(b_and(ge0(frac(z)), b_or(cmp(t + " < 0.0"), gt0(minus(z, t2)))));
     }
     if (has_div(a) || has_div(b)) {
       const Frac x = frac(a), y = frac(b);
@@ -250,20 +264,20 @@ struct FailsGen {
       else diff = {dtmp(mul(x.num, y.den) + " - " + mul(y.num, x.den)), mul(x.den, y.den)};
       return lt0(diff);
     }
-    return btmp("(" + val(a) + " < " + val(b) + ")");
+    return cmp(val(a) + " < " + val(b));
   }
   // is the value NaN? ("false" when it cannot be, up to the caveats in the header comment)
   std::string nanp(int id) {
     if (!nan_memo[id].empty()) return nan_memo[id];
     const Node& n = nodes[id];
     std::string r;
-    if (n.op == EBN_OP_INPUT || n.op == EBN_OP_LT || (n.op == EBN_OP_CONST && n.arg == n.arg)) r = "false";
-    else if (n.inv) r = btmp("(" + val(id) + " != " + val(id) + ")");   // a constant sub-expression may well be NaN
+    if (n.op == EBN_OP_INPUT || n.op == EBN_OP_LT || (n.op == EBN_OP_CONST && n.arg == n.arg)) r = "0";
+    else if (n.inv) r = cmp("isnan(" + val(id) + ")");   // a constant sub-expression may well be NaN
     else if (n.op == EBN_OP_SQRT || n.op == EBN_OP_LOG) r = btmp(b_not(ge0(frac(n.a))));
     else if (arith(n.op) || n.op == EBN_OP_MIN || n.op == EBN_OP_MAX)
-      r = btmp(b_or(nanp(n.a), n.b >= 0 ? nanp(n.b) : "false"));
+      r = btmp(b_or(nanp(n.a), n.b >= 0 ? nanp(n.b) : "0"));
     else if (n.op == EBN_OP_ABS || n.op == EBN_OP_EXP || (n.op == EBN_OP_POWI && (int)n.arg >= 0)) r = nanp(n.a);
-    else r = btmp("(" + val(id) + " != " + val(id) + ")");
+    else r = cmp("isnan(" + val(id) + ")");
     return nan_memo[id] = r;
   }
   // value < 0, false if it is NaN
@@ -271,13 +285,13 @@ struct FailsGen {
     if (!neg_memo[id].empty()) return neg_memo[id];
     const Node& n = nodes[id];
     std::string r;
-    if (n.inv) r = btmp("(" + val(id) + " < 0.0)");
+    if (n.inv) r = cmp(val(id) + " < 0.0");
     else if (n.op == EBN_OP_MIN)
       r = btmp(b_and(b_or(negp(n.a), negp(n.b)), b_not(b_or(nanp(n.a), nanp(n.b)))));
     else if (n.op == EBN_OP_MAX) r = btmp(b_and(negp(n.a), negp(n.b)));
     else if (n.op == EBN_OP_SUB) r = less(n.a, n.b);
     else if (has_div(id)) r = lt0(frac(id));
-    else r = btmp("(" + val(id) + " < 0.0)");
+    else r = cmp(val(id) + " < 0.0");
     return neg_memo[id] = r;
   }
 };
@@ -291,11 +305,11 @@ std::string expr_fails_codegen(std::vector<Node>& nodes, int root, int /*d*/, st
   if (!g.zero_tests.empty()) {
     std::string z;
     for (const std::string& t : g.zero_tests) z += (z.empty() ? "" : " | ") + t;
-    s += "    if (" + z + ") {   // a divisor is zero or not finite: IEEE infinities, signed zeros and NaNs as eval() produces them\n";
+    s += "    if ((" + z + ") != 0) {   // a divisor is zero or not finite: IEEE infinities, signed zeros and NaNs as eval() produces them\n";
     s += eval_body;
     s += "    return " + eval_result + " < 0.0;\n    }\n";
   }
-  return s + "    return " + pred + ";\n";
+  return s + "    return (" + pred + ") != 0;\n";
 }
 
 }  // namespace
