@@ -168,17 +168,19 @@ def test_compiled_formula_fast_mode_on_adversarial_marginals(ebn):
     print(f"adversarial JitExpr<FastOps>: {rows} samples, {100 * nan_frac:.1f}% NaN g, {len(bad)} tie flips")
 
 
-def test_sign_only_predicates_generated_for_formulas(ebn):
+@pytest.mark.parametrize("seed", [0, 7])
+def test_sign_only_predicates_generated_for_formulas(ebn, seed):
     """JitExpr<FastOps>::fails, the predicate the generator derives for `g < 0` in fast mode (no division, no
     square root where only the sign matters): 40 random chains of mechanisms under min / max over inputs that
     change sign — so denominators change sign and square-root and log arguments go negative (NaN: safe) — each
     compared sample by sample with the oracle's strict stack machine on the replayed matrix. The two may
-    differ on ties only."""
+    differ on ties only. Seed 7 holds the chain on which NVRTC miscompiled the first, bool-valued form of the
+    predicate inside the fused kernel (ebn_expr.cu, note above FailsGen)."""
     L = ebn._lib
     from ebn_b200 import expr
     if not L.jit_available():
         pytest.skip("no NVRTC on this machine")
-    rng = np.random.default_rng(77001 + FUZZ_SEED)
+    rng = np.random.default_rng(77001 + seed + FUZZ_SEED)
     rows = [[(L.IN_NORMAL, 0.3, 1.5, 0, 0, -INF, INF), (L.IN_NORMAL, -0.2, 1.0, 0, 0, -INF, INF),
              (L.IN_UNIFORM, -1.0, 2.0, 0, 0, -INF, INF), (L.IN_NORMAL, 1.0, 0.7, 0, 0, -INF, INF)]]
     names = ["x0", "x1", "x2", "x3"]
